@@ -1,0 +1,328 @@
+"""ctypes binding of librbphd.so -- the same C ABI the C# GpuPHDNavigator P/Invokes (include/rbphd.h).
+
+There is no CPU fallback: loading fails loudly when the library has not been built, and every
+computing call returns an error when no sm_100a device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "librbphd.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+
+OK, ERR_GENERIC, ERR_CUDA, ERR_CAPACITY, ERR_ARGUMENT, ERR_NO_DEVICE = 0, -1, 1, 2, 3, 4
+
+
+class RbphdConfig(C.Structure):
+    _fields_ = [
+        ("model", C.c_int32), ("max_quantity", C.c_int32), ("gate_metric", C.c_int32), ("nthreads", C.c_int32),
+        ("R", C.c_double * 9), ("Q", C.c_double * 36), ("pd", C.c_double), ("clutter", C.c_double),
+        ("birth_cov", C.c_double * 9), ("birth_weight", C.c_double), ("min_weight", C.c_double),
+        ("merge_threshold", C.c_double), ("exploration_threshold", C.c_double),
+        ("density_distance_threshold", C.c_double), ("min_effective_particle", C.c_double),
+        ("visibility_ramp", C.c_double * 3), ("measurer", C.c_double * 7),
+    ]
+
+
+class RbphdLimits(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32), ("max_particles", C.c_int32), ("max_components", C.c_int32),
+        ("max_measurements", C.c_int32), ("max_pairs", C.c_int32), ("reserved", C.c_int32 * 3),
+    ]
+
+
+# every symbol include/rbphd.h declares (tests/test_capi_exports.py checks the header against this list)
+EXPORTS = [
+    "rbphd_new", "rbphd_delete", "rbphd_last_error", "rbphd_reset", "rbphd_clear_maps", "rbphd_particle_count",
+    "rbphd_update", "rbphd_set_pose", "rbphd_set_poses", "rbphd_get_poses", "rbphd_slam_update",
+    "rbphd_frame_async", "rbphd_upload_frame_inputs", "rbphd_synchronize", "rbphd_resample",
+    "rbphd_particle_depleted", "rbphd_get_weights", "rbphd_set_weights", "rbphd_get_alphas", "rbphd_get_best",
+    "rbphd_get_ancestors", "rbphd_get_map_counts", "rbphd_get_map", "rbphd_set_map", "rbphd_stage_predict",
+    "rbphd_stage_correct", "rbphd_stage_prune", "rbphd_stage_weight_alpha", "rbphd_stage_set_loglikelihood",
+    "rbphd_slam_update_local", "rbphd_device_weights", "rbphd_resample_global", "rbphd_pack_particles",
+    "rbphd_unpack_particles", "rbphd_commit_resample_local", "rbphd_kernel_launches", "rbphd_last_stage_ms",
+    "rbphd_stream",
+]
+
+_lib = None
+
+
+class RbphdError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("librbphd error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load():
+    """dlopen librbphd.so; raises if it has not been built (python -m monorfs_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("librbphd.so is not built (run `python -m monorfs_b200.build`); "
+                               "monorfs_b200 has no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        lib.rbphd_new.restype = C.c_void_p
+        lib.rbphd_new.argtypes = [C.POINTER(RbphdConfig), C.POINTER(RbphdLimits)]
+        lib.rbphd_delete.argtypes = [C.c_void_p]
+        lib.rbphd_delete.restype = None
+        lib.rbphd_last_error.restype = C.c_char_p
+        lib.rbphd_last_error.argtypes = [C.c_void_p]
+        lib.rbphd_kernel_launches.restype = C.c_int64
+        lib.rbphd_kernel_launches.argtypes = [C.c_void_p]
+        lib.rbphd_stream.restype = C.c_void_p
+        lib.rbphd_stream.argtypes = [C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def make_config(p):
+    c = RbphdConfig()
+    for k in ("model", "max_quantity", "gate_metric", "nthreads"):
+        setattr(c, k, int(p[k]))
+    for k in ("pd", "clutter", "birth_weight", "min_weight", "merge_threshold", "exploration_threshold",
+              "density_distance_threshold", "min_effective_particle"):
+        setattr(c, k, float(p[k]))
+    for k, n in (("R", 9), ("Q", 36), ("birth_cov", 9), ("visibility_ramp", 3), ("measurer", 7)):
+        arr = np.asarray(p[k], dtype=np.float64).reshape(-1)
+        assert arr.size == n, (k, arr.size)
+        getattr(c, k)[:] = arr.tolist()
+    return c
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _view(ptr, n, dtype=np.float64):
+    if n <= 0:
+        return np.zeros(0, dtype=dtype)
+    ct = C.c_double if dtype == np.float64 else C.c_int
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,)).copy()
+
+
+class Handle:
+    """Thin RAII wrapper over rbphd_navigator* (mirrors the HandleRef + Dispose pattern of ISAM2Navigator.cs:446-452)."""
+
+    def __init__(self, params, max_particles, max_components=0, max_measurements=0, max_pairs=0, device=0):
+        self.lib = load()
+        self.cfg = make_config(params)
+        lim = RbphdLimits()
+        lim.device = device
+        lim.max_particles = int(max_particles)
+        lim.max_components = int(max_components)
+        lim.max_measurements = int(max_measurements)
+        lim.max_pairs = int(max_pairs)
+        self._h = self.lib.rbphd_new(C.byref(self.cfg), C.byref(lim))
+        if not self._h:
+            raise RbphdError(ERR_NO_DEVICE, self.lib.rbphd_last_error(None).decode())
+        self._h = C.c_void_p(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.rbphd_delete(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, code):
+        if code != OK:
+            raise RbphdError(code, self.lib.rbphd_last_error(self._h).decode())
+
+    # ---- state
+    def reset(self, particles, pose, w, m, P):
+        w, m, P = _d(w).reshape(-1), _d(m).reshape(-1, 3), _d(P).reshape(-1, 9)
+        self._ck(self.lib.rbphd_reset(self._h, int(particles), _p(_d(pose)), len(w), _p(w), _p(m), _p(P)))
+
+    @property
+    def particles(self):
+        return self.lib.rbphd_particle_count(self._h)
+
+    def set_pose(self, i, pose):
+        self._ck(self.lib.rbphd_set_pose(self._h, int(i), _p(_d(pose))))
+
+    def set_poses(self, poses):
+        poses = _d(poses).reshape(-1, 7)
+        assert len(poses) == self.particles
+        self._ck(self.lib.rbphd_set_poses(self._h, _p(poses)))
+
+    def get_poses(self):
+        ptr, n = c_double_p(), C.c_int()
+        self._ck(self.lib.rbphd_get_poses(self._h, C.byref(ptr), C.byref(n)))
+        return _view(ptr, 7 * n.value).reshape(-1, 7)
+
+    def get_weights(self):
+        ptr, n = c_double_p(), C.c_int()
+        self._ck(self.lib.rbphd_get_weights(self._h, C.byref(ptr), C.byref(n)))
+        return _view(ptr, n.value)
+
+    def get_alphas(self):
+        ptr, n = c_double_p(), C.c_int()
+        self._ck(self.lib.rbphd_get_alphas(self._h, C.byref(ptr), C.byref(n)))
+        return _view(ptr, n.value)
+
+    def set_weights(self, w):
+        w = _d(w)
+        assert len(w) == self.particles
+        self._ck(self.lib.rbphd_set_weights(self._h, _p(w)))
+
+    def get_best(self):
+        b = C.c_int()
+        self._ck(self.lib.rbphd_get_best(self._h, C.byref(b)))
+        return b.value
+
+    def get_ancestors(self):
+        ptr, n = c_int_p(), C.c_int()
+        self._ck(self.lib.rbphd_get_ancestors(self._h, C.byref(ptr), C.byref(n)))
+        return _view(ptr, n.value, np.int32)
+
+    def get_map_counts(self):
+        ptr, n = c_int_p(), C.c_int()
+        self._ck(self.lib.rbphd_get_map_counts(self._h, C.byref(ptr), C.byref(n)))
+        return _view(ptr, n.value, np.int32)
+
+    def _maps_out(self, pw, pm, pP, n):
+        n = n.value
+        return _view(pw, n), _view(pm, 3 * n).reshape(-1, 3), _view(pP, 9 * n).reshape(-1, 3, 3)
+
+    def get_map(self, i):
+        pw, pm, pP, n = c_double_p(), c_double_p(), c_double_p(), C.c_int()
+        self._ck(self.lib.rbphd_get_map(self._h, int(i), C.byref(pw), C.byref(pm), C.byref(pP), C.byref(n)))
+        return self._maps_out(pw, pm, pP, n)
+
+    def set_map(self, i, w, m, P):
+        w, m, P = _d(w).reshape(-1), _d(m).reshape(-1, 3), _d(P).reshape(-1, 9)
+        self._ck(self.lib.rbphd_set_map(self._h, int(i), len(w), _p(w), _p(m), _p(P)))
+
+    def clear_maps(self):
+        self._ck(self.lib.rbphd_clear_maps(self._h))
+
+    # ---- frame
+    def update(self, reading, dt, gauss, perfect_still=False):
+        g = _d(gauss).reshape(-1, 6)
+        assert len(g) == self.particles
+        self._ck(self.lib.rbphd_update(self._h, _p(_d(reading)), C.c_double(dt), _p(g), int(perfect_still)))
+
+    def slam_update(self, z, u, only_mapping=False):
+        z = _d(z).reshape(-1, 3)
+        best, res = C.c_int(), C.c_int()
+        self._ck(self.lib.rbphd_slam_update(self._h, _p(z), len(z), int(only_mapping), C.c_double(u),
+                                            C.byref(best), C.byref(res)))
+        return best.value, bool(res.value)
+
+    def upload_frame_inputs(self, gauss, z):
+        g = _d(gauss).reshape(-1, 6) if gauss is not None else None
+        zz = _d(z).reshape(-1, 3) if z is not None else None
+        self._ck(self.lib.rbphd_upload_frame_inputs(self._h, _p(g) if g is not None else None,
+                                                    _p(zz) if zz is not None else None,
+                                                    len(zz) if zz is not None else 0))
+
+    def frame_async(self, reading, dt, m, u, only_mapping=False, perfect_still=False):
+        self._ck(self.lib.rbphd_frame_async(self._h, _p(_d(reading)) if reading is not None else None,
+                                            C.c_double(dt), int(perfect_still), int(m), int(only_mapping),
+                                            C.c_double(u)))
+
+    def synchronize(self):
+        self._ck(self.lib.rbphd_synchronize(self._h))
+
+    def resample(self, u):
+        self._ck(self.lib.rbphd_resample(self._h, C.c_double(u)))
+
+    def particle_depleted(self):
+        d = C.c_int()
+        self._ck(self.lib.rbphd_particle_depleted(self._h, C.byref(d)))
+        return bool(d.value)
+
+    # ---- stages
+    def stage_predict(self, pose, w, m, P, z):
+        w, m, P, z = _d(w).reshape(-1), _d(m).reshape(-1, 3), _d(P).reshape(-1, 9), _d(z).reshape(-1, 3)
+        pw, pm, pP, n = c_double_p(), c_double_p(), c_double_p(), C.c_int()
+        self._ck(self.lib.rbphd_stage_predict(self._h, _p(_d(pose)), len(w), _p(w), _p(m), _p(P), _p(z), len(z),
+                                              C.byref(pw), C.byref(pm), C.byref(pP), C.byref(n)))
+        return self._maps_out(pw, pm, pP, n)
+
+    def stage_correct(self, pose, w, m, P, z, gate_radius=None):
+        w, m, P, z = _d(w).reshape(-1), _d(m).reshape(-1, 3), _d(P).reshape(-1, 9), _d(z).reshape(-1, 3)
+        if gate_radius is None:
+            gate_radius = self.cfg.density_distance_threshold
+        pw, pm, pP, n = c_double_p(), c_double_p(), c_double_p(), C.c_int()
+        self._ck(self.lib.rbphd_stage_correct(self._h, _p(_d(pose)), len(w), _p(w), _p(m), _p(P), _p(z), len(z),
+                                              C.c_double(gate_radius), C.byref(pw), C.byref(pm), C.byref(pP),
+                                              C.byref(n)))
+        return self._maps_out(pw, pm, pP, n)
+
+    def stage_prune(self, w, m, P):
+        w, m, P = _d(w).reshape(-1), _d(m).reshape(-1, 3), _d(P).reshape(-1, 9)
+        pw, pm, pP, n = c_double_p(), c_double_p(), c_double_p(), C.c_int()
+        self._ck(self.lib.rbphd_stage_prune(self._h, len(w), _p(w), _p(m), _p(P), C.byref(pw), C.byref(pm),
+                                            C.byref(pP), C.byref(n)))
+        return self._maps_out(pw, pm, pP, n)
+
+    def stage_weight_alpha(self, pose, z, pred, corr):
+        pw, pm, pP = _d(pred[0]).reshape(-1), _d(pred[1]).reshape(-1, 3), _d(pred[2]).reshape(-1, 9)
+        cw, cm, cP = _d(corr[0]).reshape(-1), _d(corr[1]).reshape(-1, 3), _d(corr[2]).reshape(-1, 9)
+        z = _d(z).reshape(-1, 3)
+        out = np.zeros(7)
+        self._ck(self.lib.rbphd_stage_weight_alpha(self._h, _p(_d(pose)), _p(z), len(z), len(pw), _p(pw), _p(pm),
+                                                   _p(pP), len(cw), _p(cw), _p(cm), _p(cP), _p(out)))
+        return dict(alpha=out[0], setloglik=out[1], ploglik=out[2], cloglik=out[3], pcount=out[4],
+                    ccount=out[5], J=int(out[6]))
+
+    def stage_set_loglikelihood(self, pose, jm, z):
+        jm, z = _d(jm).reshape(-1, 3), _d(z).reshape(-1, 3)
+        out = C.c_double()
+        self._ck(self.lib.rbphd_stage_set_loglikelihood(self._h, _p(_d(pose)), len(jm), _p(jm), _p(z), len(z),
+                                                        C.byref(out)))
+        return out.value
+
+    # ---- multi-GPU plumbing
+    def slam_update_local(self, m, only_mapping=False):
+        self._ck(self.lib.rbphd_slam_update_local(self._h, int(m), int(only_mapping)))
+
+    def device_weights(self):
+        ptr, n = C.c_void_p(), C.c_int()
+        self._ck(self.lib.rbphd_device_weights(self._h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def resample_global(self, dev_ptr, global_particles, rank_offset, u):
+        best, res, anc = C.c_int(), C.c_int(), c_int_p()
+        self._ck(self.lib.rbphd_resample_global(self._h, C.c_void_p(dev_ptr), int(global_particles),
+                                                int(rank_offset), C.c_double(u), C.byref(best), C.byref(res),
+                                                C.byref(anc)))
+        return best.value, bool(res.value), _view(anc, global_particles, np.int32)
+
+    def pack_particles(self, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        ptr, nbytes = C.c_void_p(), C.c_int64()
+        self._ck(self.lib.rbphd_pack_particles(self._h, idx.ctypes.data_as(c_int_p), len(idx), C.byref(ptr),
+                                               C.byref(nbytes)))
+        return ptr.value, nbytes.value
+
+    def unpack_particles(self, dev_ptr, slots):
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        self._ck(self.lib.rbphd_unpack_particles(self._h, C.c_void_p(dev_ptr), slots.ctypes.data_as(c_int_p),
+                                                 len(slots)))
+
+    def commit_resample_local(self, sources):
+        sources = np.ascontiguousarray(sources, dtype=np.int32)
+        self._ck(self.lib.rbphd_commit_resample_local(self._h, sources.ctypes.data_as(c_int_p), len(sources)))
+
+    # ---- instrumentation
+    @property
+    def kernel_launches(self):
+        return int(self.lib.rbphd_kernel_launches(self._h))
+
+    @property
+    def stream(self):
+        return self.lib.rbphd_stream(self._h)

@@ -1,0 +1,1100 @@
+// rbphd_api.cu -- the C ABI of librbphd.so (include/rbphd.h): handle lifecycle, host<->device
+// staging, kernel sequencing on the handle's stream.  No CPU fallback exists: every entry point
+// that computes fails with RBPHD_ERR_NO_DEVICE / RBPHD_ERR_CUDA when the device path is unavailable.
+#include "../../include/rbphd.h"
+#include "rbphd_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace rbphd;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    void* get(size_t n)
+    {
+        if (n > bytes) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            size_t want = std::max(n, bytes * 2);
+            if (cudaMallocHost(&p, want) != cudaSuccess) { p = nullptr; bytes = 0; return nullptr; }
+            bytes = want;
+        }
+        return p;
+    }
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+};
+
+}  // namespace
+
+struct rbphd_navigator {
+    rbphd_config cfg{};
+    rbphd_limits lim{};
+    DevCfg dcfg{};
+    ScratchLayout lay{};
+    int device = 0;
+    int P = 0;              // current particle count
+    int maxP = 0, cap = 0, Mcap = 0;
+    cudaStream_t stream = nullptr;
+    // device state
+    double* maps[2] = {nullptr, nullptr};
+    int* counts[2] = {nullptr, nullptr};
+    double *poses = nullptr, *poses_tmp = nullptr, *weights = nullptr, *alphas = nullptr, *alpha_parts = nullptr;
+    double *z = nullptr, *gauss = nullptr, *pts = nullptr;
+    int* ancestors = nullptr;
+    DeviceState* st = nullptr;
+    FrameGrid *vgrid = nullptr, *zgrid = nullptr;
+    int *vitems = nullptr, *zitems = nullptr;
+    unsigned char* scratch = nullptr;
+    double* dump = nullptr;
+    int* dump_count = nullptr;
+    int dump_cap = 0;
+    double* gweights = nullptr;   // multi-GPU: global weight vector workspace
+    int* ganc = nullptr;
+    int gcap = 0;
+    double* packbuf = nullptr;
+    size_t packbytes = 0;
+    int* idxbuf = nullptr;
+    int idxcap = 0;
+    // launch geometry
+    int nslab = 0;
+    size_t smem = 0, sort_cap = 0;
+    int M_last = 0;
+    // host mirrors (library-owned outputs)
+    PinnedBuf h_in, h_out, h_state, h_map;
+    std::vector<double> o_w, o_m, o_P;
+    std::vector<int> o_anc;
+    int64_t launches = 0;
+    std::string error;
+    rbphd_navigator* stage = nullptr;   // lazily created 2-slot navigator for the stage entry points
+    cudaEvent_t ev[8] = {};
+    bool ev_ok = false;
+    double stage_ms[8] = {};
+};
+
+namespace {
+
+int fail(rbphd_navigator* nav, int code, const std::string& msg)
+{
+    if (nav) nav->error = msg;
+    g_last_error = msg;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(nav, RBPHD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+double inv3(const double* a, double* inv)
+{
+    double c00 = a[4] * a[8] - a[5] * a[7];
+    double c01 = a[3] * a[8] - a[5] * a[6];
+    double c02 = a[3] * a[7] - a[4] * a[6];
+    double det = a[0] * c00 - a[1] * c01 + a[2] * c02;
+    double id = 1.0 / det;
+    inv[0] = c00 * id;
+    inv[1] = (a[2] * a[7] - a[1] * a[8]) * id;
+    inv[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+    inv[3] = (a[5] * a[6] - a[3] * a[8]) * id;
+    inv[4] = (a[0] * a[8] - a[2] * a[6]) * id;
+    inv[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+    inv[6] = c02 * id;
+    inv[7] = (a[1] * a[6] - a[0] * a[7]) * id;
+    inv[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+    return det;
+}
+
+// UTIL:173-202: lower Cholesky root, diagonal floored at 1e-40
+void cholesky6(const double* Qin, double* C)
+{
+    double Q[36];
+    std::memcpy(Q, Qin, sizeof Q);
+    for (int i = 0; i < 6; i++) if (Q[i * 6 + i] < 1e-40) Q[i * 6 + i] = 1e-40;
+    for (int i = 0; i < 36; i++) C[i] = 0;
+    for (int j = 0; j < 6; j++) {
+        double s = Q[j * 6 + j];
+        for (int k = 0; k < j; k++) s -= C[j * 6 + k] * C[j * 6 + k];
+        C[j * 6 + j] = std::sqrt(s);
+        for (int i = j + 1; i < 6; i++) {
+            double t = Q[i * 6 + j];
+            for (int k = 0; k < j; k++) t -= C[i * 6 + k] * C[j * 6 + k];
+            C[i * 6 + j] = t / C[j * 6 + j];
+        }
+    }
+}
+
+void make_devcfg(const rbphd_config& c, DevCfg& d, double gate_radius_override, bool use_override)
+{
+    std::memset(&d, 0, sizeof d);
+    std::memcpy(d.R, c.R, sizeof d.R);
+    double det = inv3(c.R, d.Rinv);
+    d.multR = (1.0 / (2 * 3.14159265358979323846)) / std::sqrt(det);
+    d.logmultR = std::log(d.multR);
+    cholesky6(c.Q, d.chol);
+    d.pd = c.pd;
+    d.clutter = c.clutter;
+    d.logclutter = std::log(c.clutter);
+    std::memcpy(d.birth_cov, c.birth_cov, sizeof d.birth_cov);
+    d.birth_w = c.birth_weight;
+    d.min_w = c.min_weight;
+    d.merge_t = c.merge_threshold;
+    d.explore_thr = c.exploration_threshold;
+    double gr = use_override ? gate_radius_override : c.density_distance_threshold;
+    d.ungated = (use_override && gate_radius_override < 0) ? 1 : 0;
+    if (d.ungated) gr = c.density_distance_threshold;
+    double er = 3 * c.density_distance_threshold;
+    if (c.gate_metric == 0) {
+        d.gate_r2 = gr * gr;  d.gate_r = gr;
+        d.explore_r2 = er * er;  d.explore_r = er;
+    }
+    else {
+        d.gate_r2 = gr;  d.gate_r = std::sqrt(gr > 0 ? gr : 0);
+        d.explore_r2 = er;  d.explore_r = std::sqrt(er > 0 ? er : 0);
+    }
+    d.min_eff = c.min_effective_particle;
+    for (int i = 0; i < 3; i++) d.ramp[i] = c.visibility_ramp[i];
+    d.focal = c.measurer[0];
+    int left = (int)c.measurer[3], top = (int)c.measurer[4];
+    d.left = left;  d.top = top;
+    d.right = left + (int)c.measurer[5];
+    d.bottom = top + (int)c.measurer[6];
+    d.rmin = (double)(float)c.measurer[1];   // AForge.Range holds floats (PRM:65,110)
+    d.rmax = (double)(float)c.measurer[2];
+    d.maxq = c.max_quantity;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+void make_layout(ScratchLayout& l, int cap, int Mcap, int cap_pairs, int maxq)
+{
+    std::memset(&l, 0, sizeof l);
+    l.cap_pred = cap + Mcap;
+    l.cap_pairs = cap_pairs;
+    l.cap_list = l.cap_pred + cap_pairs;
+    l.cap_j = 2 * cap;
+    int need = std::max(l.cap_list, cap + l.cap_j);
+    int ps = 1;
+    while (ps < need) ps <<= 1;
+    l.cap_sort = ps;
+    l.cap_top = std::max(1, std::min(maxq, cap));
+    l.cap_edges = 8 * l.cap_top + 64;
+    l.cap_ll = std::max(8 * Mcap, 1024);
+    l.cap_nodes = std::max(l.cap_pred, l.cap_top) + 2;
+    size_t off = 0;
+    auto take = [&](size_t& field, size_t bytes) { field = off; off = align_up(off + bytes, 16); };
+    const size_t D = sizeof(double), I = sizeof(int), U = sizeof(unsigned long long);
+    take(l.pm, 3 * D * l.cap_pred);  take(l.pwt, D * l.cap_pred);  take(l.pwmd, D * l.cap_pred);
+    take(l.ppd, D * l.cap_pred);     take(l.flagf, I * (l.cap_pred + 2));  take(l.fidx, I * (l.cap_pred + 2));
+    take(l.bidx, I * (cap_pairs + 2));
+    take(l.pkey, U * cap_pairs);     take(l.pt, D * cap_pairs);    take(l.pmean, 3 * D * cap_pairs);
+    take(l.pcov, 9 * D * cap_pairs); take(l.pwgt, D * cap_pairs);
+    take(l.skey, U * l.cap_sort);    take(l.sval, sizeof(unsigned) * l.cap_sort);
+    take(l.tw, D * l.cap_top);       take(l.tm, 3 * D * l.cap_top); take(l.tP, 9 * D * l.cap_top);
+    take(l.rho, D * l.cap_top);
+    take(l.ecnt, I * (l.cap_top + 2)); take(l.edst, I * l.cap_edges);
+    take(l.nstate, I * l.cap_nodes); take(l.nowner, I * l.cap_nodes); take(l.nflag, I * l.cap_nodes);
+    take(l.gitems, I * l.cap_nodes);
+    take(l.jidx, I * l.cap_j);       take(l.jm, 3 * D * l.cap_j);  take(l.jmp, 3 * D * l.cap_j);
+    take(l.jpd, D * l.cap_j);        take(l.vsum, D * l.cap_j);
+    take(l.cinv, 9 * D * l.cap_pred); take(l.cnorm, D * l.cap_pred); take(l.crad, D * l.cap_pred);
+    take(l.fat, I * l.cap_nodes);    take(l.clist, I * l.cap_nodes); take(l.gx, 3 * D * l.cap_pred);
+    take(l.llkey, U * l.cap_ll);     take(l.llval, D * l.cap_ll);
+    take(l.uf, I * (l.cap_j + Mcap + 2)); take(l.bcnt, I * (l.cap_j + Mcap + 2));
+    take(l.bsum, 16); take(l.bmin, 16); take(l.mslots, 16);
+    l.bytes = align_up(off, 256);
+}
+
+void free_device(rbphd_navigator* nav)
+{
+    cudaSetDevice(nav->device);
+    for (int b = 0; b < 2; b++) { cudaFree(nav->maps[b]); cudaFree(nav->counts[b]); }
+    cudaFree(nav->poses); cudaFree(nav->poses_tmp); cudaFree(nav->weights); cudaFree(nav->alphas);
+    cudaFree(nav->alpha_parts); cudaFree(nav->z); cudaFree(nav->gauss); cudaFree(nav->pts);
+    cudaFree(nav->ancestors); cudaFree(nav->st); cudaFree(nav->vgrid); cudaFree(nav->zgrid);
+    cudaFree(nav->vitems); cudaFree(nav->zitems); cudaFree(nav->scratch); cudaFree(nav->dump);
+    cudaFree(nav->dump_count); cudaFree(nav->gweights); cudaFree(nav->ganc); cudaFree(nav->packbuf);
+    cudaFree(nav->idxbuf);
+    if (nav->ev_ok) for (auto& e : nav->ev) cudaEventDestroy(e);
+    if (nav->stream) cudaStreamDestroy(nav->stream);
+}
+
+int set_device(rbphd_navigator* nav)
+{
+    CK(cudaSetDevice(nav->device));
+    return RBPHD_OK;
+}
+
+KParams base_params(rbphd_navigator* nav, int mode, int M, int only_mapping)
+{
+    KParams k;
+    std::memset(&k, 0, sizeof k);
+    k.cfg = nav->dcfg;
+    k.lay = nav->lay;
+    k.P = nav->P;
+    k.first = 0;
+    k.M = M;
+    k.cap = nav->cap;
+    k.mode = mode;
+    k.only_mapping = only_mapping;
+    k.maps[0] = nav->maps[0];  k.maps[1] = nav->maps[1];
+    k.counts[0] = nav->counts[0];  k.counts[1] = nav->counts[1];
+    k.poses = nav->poses;
+    k.weights = nav->weights;
+    k.alphas = nav->alphas;
+    k.alpha_parts = nav->alpha_parts;
+    k.z = nav->z;
+    k.vgrid = nav->vgrid;  k.vitems = nav->vitems;
+    k.zgrid = nav->zgrid;  k.zitems = nav->zitems;
+    k.scratch = nav->scratch;
+    k.st = nav->st;
+    k.dump = nav->dump;
+    k.dump_count = nav->dump_count;
+    k.dump_cap = nav->dump_cap;
+    k.smem_sort_cap = nav->sort_cap;
+    return k;
+}
+
+int check_async(rbphd_navigator* nav, const char* what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nav, RBPHD_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return RBPHD_OK;
+}
+
+// prep + fused per-particle kernel
+int enqueue_map_update(rbphd_navigator* nav, int M, int only_mapping, int mode)
+{
+    launch_frame_prep(nav->stream, nav->dcfg, nav->z, M, nav->vgrid, nav->vitems, nav->zgrid, nav->zitems, nav->pts);
+    KParams k = base_params(nav, mode, M, only_mapping);
+    int grid = std::min(nav->nslab, std::max(1, nav->P));
+    launch_particle_update(nav->stream, k, grid, nav->smem);
+    nav->launches += 2;
+    nav->M_last = M;
+    return check_async(nav, "particle update launch");
+}
+
+int read_state(rbphd_navigator* nav, DeviceState* out)
+{
+    DeviceState* h = (DeviceState*)nav->h_state.get(sizeof(DeviceState));
+    if (!h) return fail(nav, RBPHD_ERR_CUDA, "pinned allocation failed");
+    CK(cudaMemcpyAsync(h, nav->st, sizeof(DeviceState), cudaMemcpyDeviceToHost, nav->stream));
+    CK(cudaStreamSynchronize(nav->stream));
+    *out = *h;
+    return RBPHD_OK;
+}
+
+int status_to_error(rbphd_navigator* nav, int status)
+{
+    if (!status) return RBPHD_OK;
+    std::string msg = "capacity exceeded:";
+    if (status & ST_OVER_COMPONENTS) msg += " components(max_components)";
+    if (status & ST_OVER_PAIRS) msg += " gated-pairs(max_pairs)";
+    if (status & ST_OVER_EDGES) msg += " merge-edges";
+    if (status & ST_OVER_JMAP) msg += " map-estimate-size";
+    if (status & ST_OVER_LL) msg += " likelihood-edges";
+    if (status & ST_OVER_BLOCK) msg += " association-block>5-rows(Murty lane not available)";
+    return fail(nav, RBPHD_ERR_CAPACITY, msg);
+}
+
+int upload(rbphd_navigator* nav, void* dst, const void* src, size_t bytes, size_t stage_off = 0)
+{
+    if (bytes == 0) return RBPHD_OK;
+    char* h = (char*)nav->h_in.get(stage_off + bytes);
+    if (!h) return fail(nav, RBPHD_ERR_CUDA, "pinned allocation failed");
+    std::memcpy(h + stage_off, src, bytes);
+    CK(cudaMemcpyAsync(dst, h + stage_off, bytes, cudaMemcpyHostToDevice, nav->stream));
+    return RBPHD_OK;
+}
+
+// AoS (w[n], mean[n*3], cov[n*9]) -> the particle's SoA slab of buffer b
+int write_map(rbphd_navigator* nav, int buffer, int particle, int n, const double* w, const double* mean,
+              const double* cov)
+{
+    if (n > nav->cap) return fail(nav, RBPHD_ERR_CAPACITY, "map larger than max_components");
+    const int cap = nav->cap;
+    size_t bytes = sizeof(double) * kFields * cap + sizeof(int);
+    // a dedicated staging area per call: synchronise before reuse
+    CK(cudaStreamSynchronize(nav->stream));
+    double* h = (double*)nav->h_map.get(bytes);
+    if (!h) return fail(nav, RBPHD_ERR_CUDA, "pinned allocation failed");
+    std::memset(h, 0, sizeof(double) * kFields * cap);
+    for (int i = 0; i < n; i++) {
+        h[i] = w[i];
+        for (int a = 0; a < 3; a++) h[(size_t)(1 + a) * cap + i] = mean[3 * i + a];
+        for (int a = 0; a < 9; a++) h[(size_t)(4 + a) * cap + i] = cov[9 * i + a];
+    }
+    int* hc = (int*)(h + (size_t)kFields * cap);
+    *hc = n;
+    CK(cudaMemcpyAsync(nav->maps[buffer] + (size_t)particle * kFields * cap, h, sizeof(double) * kFields * cap,
+                       cudaMemcpyHostToDevice, nav->stream));
+    CK(cudaMemcpyAsync(nav->counts[buffer] + particle, hc, sizeof(int), cudaMemcpyHostToDevice, nav->stream));
+    CK(cudaStreamSynchronize(nav->stream));
+    return RBPHD_OK;
+}
+
+int soa_to_outputs(rbphd_navigator* nav, const double* h, int stride, int n, const double** w, const double** mean,
+                   const double** cov, int* on)
+{
+    nav->o_w.resize(std::max(n, 1));
+    nav->o_m.resize(std::max(3 * n, 1));
+    nav->o_P.resize(std::max(9 * n, 1));
+    for (int i = 0; i < n; i++) {
+        nav->o_w[i] = h[i];
+        for (int a = 0; a < 3; a++) nav->o_m[3 * i + a] = h[(size_t)(1 + a) * stride + i];
+        for (int a = 0; a < 9; a++) nav->o_P[9 * i + a] = h[(size_t)(4 + a) * stride + i];
+    }
+    if (w) *w = nav->o_w.data();
+    if (mean) *mean = nav->o_m.data();
+    if (cov) *cov = nav->o_P.data();
+    if (on) *on = n;
+    return RBPHD_OK;
+}
+
+int ensure_stage(rbphd_navigator* nav)
+{
+    if (nav->stage) return RBPHD_OK;
+    rbphd_limits lim = nav->lim;
+    lim.max_particles = 1;
+    nav->stage = rbphd_new(&nav->cfg, &lim);
+    if (!nav->stage) return fail(nav, RBPHD_ERR_CUDA, "stage navigator: " + g_last_error);
+    return RBPHD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rbphd_last_error(const rbphd_navigator* nav)
+{
+    return nav ? nav->error.c_str() : g_last_error.c_str();
+}
+
+rbphd_navigator* rbphd_new(const rbphd_config* config, const rbphd_limits* limits)
+{
+    if (!config) { g_last_error = "null config"; return nullptr; }
+    if (config->model != 0) { g_last_error = "only the PRM3D model (0) runs on the GPU"; return nullptr; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_last_error = std::string("no CUDA device (") + cudaGetErrorString(e) + "); librbphd has no CPU fallback";
+        return nullptr;
+    }
+    rbphd_navigator* nav = new rbphd_navigator();
+    nav->cfg = *config;
+    rbphd_limits lim{};
+    if (limits) lim = *limits;
+    nav->device = lim.device;
+    if (lim.max_particles <= 0) lim.max_particles = 1;
+    if (lim.max_components <= 0) lim.max_components = std::max(config->max_quantity, 64);
+    lim.max_components = std::max(lim.max_components, std::min(config->max_quantity, 1 << 20));
+    lim.max_components = (lim.max_components + 31) / 32 * 32;
+    if (lim.max_measurements <= 0) lim.max_measurements = 1024;
+    lim.max_measurements = (lim.max_measurements + 1) & ~1;
+    if (lim.max_pairs <= 0) lim.max_pairs = 4 * lim.max_measurements;
+    nav->lim = lim;
+    nav->maxP = lim.max_particles;
+    nav->cap = lim.max_components;
+    nav->Mcap = lim.max_measurements;
+    make_devcfg(*config, nav->dcfg, 0, false);
+    make_layout(nav->lay, nav->cap, nav->Mcap, lim.max_pairs, config->max_quantity);
+
+    auto bail = [&](const std::string& msg) -> rbphd_navigator* {
+        g_last_error = msg;
+        free_device(nav);
+        delete nav;
+        return nullptr;
+    };
+#define CKN(call)                                                                       \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess) return bail(std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+    CKN(cudaSetDevice(nav->device));
+    cudaDeviceProp prop;
+    CKN(cudaGetDeviceProperties(&prop, nav->device));
+    if (prop.major < 10)
+        return bail("device compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor) +
+                    " < 10.0: librbphd is built for sm_100a only");
+    CKN(cudaStreamCreateWithFlags(&nav->stream, cudaStreamNonBlocking));
+    const size_t mapbytes = sizeof(double) * kFields * (size_t)nav->cap * nav->maxP;
+    for (int b = 0; b < 2; b++) {
+        CKN(cudaMalloc(&nav->maps[b], mapbytes));
+        CKN(cudaMalloc(&nav->counts[b], sizeof(int) * nav->maxP));
+        CKN(cudaMemsetAsync(nav->counts[b], 0, sizeof(int) * nav->maxP, nav->stream));
+    }
+    CKN(cudaMalloc(&nav->poses, sizeof(double) * 7 * nav->maxP));
+    CKN(cudaMalloc(&nav->poses_tmp, sizeof(double) * 7 * nav->maxP));
+    CKN(cudaMalloc(&nav->weights, sizeof(double) * nav->maxP));
+    CKN(cudaMalloc(&nav->alphas, sizeof(double) * nav->maxP));
+    CKN(cudaMalloc(&nav->alpha_parts, sizeof(double) * 8 * nav->maxP));
+    CKN(cudaMalloc(&nav->z, sizeof(double) * 3 * nav->Mcap + 64));
+    CKN(cudaMalloc(&nav->gauss, sizeof(double) * 6 * nav->maxP));
+    CKN(cudaMalloc(&nav->pts, sizeof(double) * 6 * nav->Mcap + 64));
+    CKN(cudaMalloc(&nav->ancestors, sizeof(int) * nav->maxP));
+    CKN(cudaMalloc(&nav->st, sizeof(DeviceState)));
+    CKN(cudaMemsetAsync(nav->st, 0, sizeof(DeviceState), nav->stream));
+    CKN(cudaMemsetAsync(nav->alphas, 0, sizeof(double) * nav->maxP, nav->stream));
+    CKN(cudaMemsetAsync(nav->gauss, 0, sizeof(double) * 6 * nav->maxP, nav->stream));
+    CKN(cudaMalloc(&nav->vgrid, sizeof(FrameGrid)));
+    CKN(cudaMalloc(&nav->zgrid, sizeof(FrameGrid)));
+    CKN(cudaMalloc(&nav->vitems, sizeof(int) * (nav->Mcap + 2)));
+    CKN(cudaMalloc(&nav->zitems, sizeof(int) * (nav->Mcap + 2)));
+    nav->dump_cap = nav->lay.cap_list;
+    CKN(cudaMalloc(&nav->dump, sizeof(double) * kFields * (size_t)nav->dump_cap));
+    CKN(cudaMalloc(&nav->dump_count, sizeof(int)));
+
+    nav->smem = particle_update_smem(nav->Mcap, &nav->sort_cap);
+    if (nav->smem > (size_t)prop.sharedMemPerBlockOptin)
+        return bail("max_measurements too large for shared memory (" + std::to_string(nav->smem) + " B needed)");
+    int per_sm = particle_update_max_ctas_per_sm(nav->smem);
+    if (per_sm < 1) return bail("k_particle_update cannot be resident (shared memory / registers)");
+    nav->nslab = std::max(1, std::min(prop.multiProcessorCount * per_sm, nav->maxP));
+    CKN(cudaMalloc(&nav->scratch, nav->lay.bytes * (size_t)nav->nslab));
+    for (auto& ev : nav->ev) CKN(cudaEventCreate(&ev));
+    nav->ev_ok = true;
+    CKN(cudaStreamSynchronize(nav->stream));
+#undef CKN
+    nav->P = 0;
+    return nav;
+}
+
+void rbphd_delete(rbphd_navigator* nav)
+{
+    if (!nav) return;
+    if (nav->stage) rbphd_delete(nav->stage);
+    cudaSetDevice(nav->device);
+    if (nav->stream) cudaStreamSynchronize(nav->stream);
+    free_device(nav);
+    delete nav;
+}
+
+int rbphd_particle_count(const rbphd_navigator* nav) { return nav ? nav->P : 0; }
+
+int rbphd_reset(rbphd_navigator* nav, int particles, const double* pose7, int n, const double* w,
+                const double* mean, const double* cov)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (particles < 1 || particles > nav->maxP) return fail(nav, RBPHD_ERR_ARGUMENT, "particle count out of range");
+    if (n < 0 || n > nav->cap) return fail(nav, RBPHD_ERR_CAPACITY, "map larger than max_components");
+    if (int r = set_device(nav)) return r;
+    nav->P = particles;
+    const int cap = nav->cap;
+    // buffer 0 becomes current; particle 0 is uploaded, the rest replicated on the device
+    DeviceState st0{};
+    if (int r = upload(nav, nav->st, &st0, sizeof st0)) return r;
+    CK(cudaStreamSynchronize(nav->stream));
+    if (int r = write_map(nav, 0, 0, n, w, mean, cov)) return r;
+    for (int filled = 1; filled < particles;) {
+        int cnt = std::min(filled, particles - filled);
+        CK(cudaMemcpyAsync(nav->maps[0] + (size_t)filled * kFields * cap, nav->maps[0],
+                           sizeof(double) * kFields * cap * (size_t)cnt, cudaMemcpyDeviceToDevice, nav->stream));
+        CK(cudaMemcpyAsync(nav->counts[0] + filled, nav->counts[0], sizeof(int) * cnt, cudaMemcpyDeviceToDevice,
+                           nav->stream));
+        filled += cnt;
+    }
+    std::vector<double> hp(7 * (size_t)particles), hw(particles, 1.0 / particles);
+    for (int i = 0; i < particles; i++) std::memcpy(&hp[7 * (size_t)i], pose7, 7 * sizeof(double));
+    if (int r = upload(nav, nav->poses, hp.data(), hp.size() * sizeof(double))) return r;
+    CK(cudaStreamSynchronize(nav->stream));
+    if (int r = upload(nav, nav->weights, hw.data(), hw.size() * sizeof(double))) return r;
+    CK(cudaMemsetAsync(nav->alphas, 0, sizeof(double) * particles, nav->stream));
+    CK(cudaStreamSynchronize(nav->stream));
+    nav->o_anc.assign(particles, 0);
+    for (int i = 0; i < particles; i++) nav->o_anc[i] = i;
+    return RBPHD_OK;
+}
+
+int rbphd_clear_maps(rbphd_navigator* nav)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    for (int b = 0; b < 2; b++) CK(cudaMemsetAsync(nav->counts[b], 0, sizeof(int) * nav->maxP, nav->stream));
+    CK(cudaStreamSynchronize(nav->stream));
+    return RBPHD_OK;
+}
+
+int rbphd_upload_frame_inputs(rbphd_navigator* nav, const double* gauss, const double* z, int m)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (m < 0 || m > nav->Mcap) return fail(nav, RBPHD_ERR_ARGUMENT, "m > max_measurements");
+    if (int r = set_device(nav)) return r;
+    size_t gb = gauss ? sizeof(double) * 6 * (size_t)nav->P : 0;
+    size_t zb = z ? sizeof(double) * 3 * (size_t)m : 0;
+    // the pinned staging buffer may still be in flight from the previous frame
+    CK(cudaStreamSynchronize(nav->stream));
+    if (gauss) if (int r = upload(nav, nav->gauss, gauss, gb, 0)) return r;
+    if (z) if (int r = upload(nav, nav->z, z, zb, gb)) return r;
+    return RBPHD_OK;
+}
+
+int rbphd_update(rbphd_navigator* nav, const double* reading6, double dt, const double* gauss, int perfect_still)
+{
+    if (!nav || !reading6) return RBPHD_ERR_ARGUMENT;
+    if (nav->P < 1) return fail(nav, RBPHD_ERR_ARGUMENT, "navigator not reset");
+    if (int r = set_device(nav)) return r;
+    if (gauss) if (int r = rbphd_upload_frame_inputs(nav, gauss, nullptr, 0)) return r;
+    Reading6 rd;
+    std::memcpy(rd.v, reading6, sizeof rd.v);
+    launch_predict_pose(nav->stream, nav->dcfg, nav->P, nav->poses, rd, dt, nav->gauss, perfect_still);
+    nav->launches += 1;
+    if (int r = check_async(nav, "predict_pose launch")) return r;
+    CK(cudaStreamSynchronize(nav->stream));
+    return RBPHD_OK;
+}
+
+int rbphd_set_pose(rbphd_navigator* nav, int particle, const double* pose7)
+{
+    if (!nav || !pose7) return RBPHD_ERR_ARGUMENT;
+    if (particle < 0 || particle >= nav->P) return fail(nav, RBPHD_ERR_ARGUMENT, "particle index out of range");
+    if (int r = set_device(nav)) return r;
+    CK(cudaStreamSynchronize(nav->stream));
+    if (int r = upload(nav, nav->poses + 7 * (size_t)particle, pose7, 7 * sizeof(double))) return r;
+    CK(cudaStreamSynchronize(nav->stream));
+    return RBPHD_OK;
+}
+
+int rbphd_set_poses(rbphd_navigator* nav, const double* poses)
+{
+    if (!nav || !poses) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    CK(cudaStreamSynchronize(nav->stream));
+    if (int r = upload(nav, nav->poses, poses, 7 * sizeof(double) * (size_t)nav->P)) return r;
+    CK(cudaStreamSynchronize(nav->stream));
+    return RBPHD_OK;
+}
+
+static int download(rbphd_navigator* nav, const void* dev, size_t bytes, void** host)
+{
+    void* h = nav->h_out.get(std::max<size_t>(bytes, 16));
+    if (!h) return fail(nav, RBPHD_ERR_CUDA, "pinned allocation failed");
+    CK(cudaMemcpyAsync(h, dev, bytes, cudaMemcpyDeviceToHost, nav->stream));
+    CK(cudaStreamSynchronize(nav->stream));
+    *host = h;
+    return RBPHD_OK;
+}
+
+int rbphd_get_poses(rbphd_navigator* nav, const double** poses, int* particles)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    void* h;
+    if (int r = download(nav, nav->poses, sizeof(double) * 7 * (size_t)nav->P, &h)) return r;
+    if (poses) *poses = (const double*)h;
+    if (particles) *particles = nav->P;
+    return RBPHD_OK;
+}
+
+int rbphd_get_weights(rbphd_navigator* nav, const double** weights, int* particles)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    void* h;
+    if (int r = download(nav, nav->weights, sizeof(double) * (size_t)nav->P, &h)) return r;
+    if (weights) *weights = (const double*)h;
+    if (particles) *particles = nav->P;
+    return RBPHD_OK;
+}
+
+int rbphd_get_alphas(rbphd_navigator* nav, const double** alphas, int* particles)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    void* h;
+    if (int r = download(nav, nav->alphas, sizeof(double) * (size_t)nav->P, &h)) return r;
+    if (alphas) *alphas = (const double*)h;
+    if (particles) *particles = nav->P;
+    return RBPHD_OK;
+}
+
+int rbphd_set_weights(rbphd_navigator* nav, const double* weights)
+{
+    if (!nav || !weights) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    CK(cudaStreamSynchronize(nav->stream));
+    if (int r = upload(nav, nav->weights, weights, sizeof(double) * (size_t)nav->P)) return r;
+    CK(cudaStreamSynchronize(nav->stream));
+    return RBPHD_OK;
+}
+
+int rbphd_get_best(rbphd_navigator* nav, int* best)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    DeviceState st;
+    if (int r = read_state(nav, &st)) return r;
+    if (best) *best = st.best;
+    return RBPHD_OK;
+}
+
+int rbphd_get_ancestors(rbphd_navigator* nav, const int** ancestors, int* particles)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    void* h;
+    nav->o_anc.resize(std::max(nav->P, 1));
+    if (int r = download(nav, nav->ancestors, sizeof(int) * (size_t)nav->P, &h)) return r;
+    std::memcpy(nav->o_anc.data(), h, sizeof(int) * (size_t)nav->P);
+    if (ancestors) *ancestors = nav->o_anc.data();
+    if (particles) *particles = nav->P;
+    return RBPHD_OK;
+}
+
+int rbphd_get_map_counts(rbphd_navigator* nav, const int** counts, int* particles)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    DeviceState st;
+    if (int r = read_state(nav, &st)) return r;
+    void* h;
+    if (int r = download(nav, nav->counts[st.cur], sizeof(int) * (size_t)nav->P, &h)) return r;
+    if (counts) *counts = (const int*)h;
+    if (particles) *particles = nav->P;
+    return RBPHD_OK;
+}
+
+int rbphd_get_map(rbphd_navigator* nav, int particle, const double** w, const double** mean, const double** cov,
+                  int* n)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (particle < 0 || particle >= nav->P) return fail(nav, RBPHD_ERR_ARGUMENT, "particle index out of range");
+    if (int r = set_device(nav)) return r;
+    DeviceState st;
+    if (int r = read_state(nav, &st)) return r;
+    void* hc;
+    if (int r = download(nav, nav->counts[st.cur] + particle, sizeof(int), &hc)) return r;
+    int cnt = std::min(*(int*)hc, nav->cap);
+    void* h;
+    if (int r = download(nav, nav->maps[st.cur] + (size_t)particle * kFields * nav->cap,
+                         sizeof(double) * kFields * (size_t)nav->cap, &h))
+        return r;
+    return soa_to_outputs(nav, (const double*)h, nav->cap, cnt, w, mean, cov, n);
+}
+
+int rbphd_set_map(rbphd_navigator* nav, int particle, int n, const double* w, const double* mean, const double* cov)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (particle < 0 || particle >= nav->P) return fail(nav, RBPHD_ERR_ARGUMENT, "particle index out of range");
+    if (int r = set_device(nav)) return r;
+    DeviceState st;
+    if (int r = read_state(nav, &st)) return r;
+    return write_map(nav, st.cur, particle, n, w, mean, cov);
+}
+
+int rbphd_synchronize(rbphd_navigator* nav)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    CK(cudaStreamSynchronize(nav->stream));
+    DeviceState st;
+    if (int r = read_state(nav, &st)) return r;
+    if (st.status) {
+        int status = st.status;
+        CK(cudaMemsetAsync(&nav->st->status, 0, sizeof(int), nav->stream));
+        CK(cudaStreamSynchronize(nav->stream));
+        return status_to_error(nav, status);
+    }
+    return RBPHD_OK;
+}
+
+static int enqueue_slam_tail(rbphd_navigator* nav, int only_mapping, double u, int force)
+{
+    if (only_mapping) {
+        launch_flip(nav->stream, nav->st);
+        nav->launches += 1;
+    }
+    else {
+        launch_normalize_resample(nav->stream, nav->dcfg, nav->P, nav->weights, u, force, nav->ancestors, nav->st);
+        launch_copy_particles(nav->stream, nav->P, nav->cap, nav->maps, nav->counts, nav->poses, nav->poses_tmp,
+                              nav->ancestors, nav->st);
+        nav->launches += 3;
+    }
+    return check_async(nav, "slam tail launch");
+}
+
+int rbphd_frame_async(rbphd_navigator* nav, const double* reading6, double dt, int perfect_still, int m,
+                      int only_mapping, double u_resample)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (nav->P < 1) return fail(nav, RBPHD_ERR_ARGUMENT, "navigator not reset");
+    if (m < 0 || m > nav->Mcap) return fail(nav, RBPHD_ERR_ARGUMENT, "m > max_measurements");
+    if (int r = set_device(nav)) return r;
+    if (reading6 && !only_mapping) {
+        Reading6 rd;
+        std::memcpy(rd.v, reading6, sizeof rd.v);
+        launch_predict_pose(nav->stream, nav->dcfg, nav->P, nav->poses, rd, dt, nav->gauss, perfect_still);
+        nav->launches += 1;
+    }
+    if (int r = enqueue_map_update(nav, m, only_mapping, MODE_FRAME)) return r;
+    return enqueue_slam_tail(nav, only_mapping, u_resample, 0);
+}
+
+int rbphd_slam_update(rbphd_navigator* nav, const double* z, int m, int only_mapping, double u_resample, int* best,
+                      int* resampled)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (nav->P < 1) return fail(nav, RBPHD_ERR_ARGUMENT, "navigator not reset");
+    if (m < 0 || m > nav->Mcap) return fail(nav, RBPHD_ERR_ARGUMENT, "m > max_measurements");
+    if (m > 0 && !z) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    if (int r = rbphd_upload_frame_inputs(nav, nullptr, z, m)) return r;
+    if (int r = enqueue_map_update(nav, m, only_mapping, MODE_FRAME)) return r;
+    if (int r = enqueue_slam_tail(nav, only_mapping, u_resample, 0)) return r;
+    DeviceState st;
+    if (int r = read_state(nav, &st)) return r;
+    if (best) *best = st.best;
+    if (resampled) *resampled = only_mapping ? 0 : st.resampled;
+    if (st.status) {
+        int status = st.status;
+        CK(cudaMemsetAsync(&nav->st->status, 0, sizeof(int), nav->stream));
+        CK(cudaStreamSynchronize(nav->stream));
+        return status_to_error(nav, status);
+    }
+    return RBPHD_OK;
+}
+
+int rbphd_resample(rbphd_navigator* nav, double u_resample)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (nav->P < 1) return fail(nav, RBPHD_ERR_ARGUMENT, "navigator not reset");
+    if (int r = set_device(nav)) return r;
+    // the copy kernel moves particles from buffer 1-cur to buffer cur: make the current maps "1-cur" first
+    launch_flip(nav->stream, nav->st);
+    launch_normalize_resample(nav->stream, nav->dcfg, nav->P, nav->weights, u_resample, 2, nav->ancestors, nav->st);
+    launch_copy_particles(nav->stream, nav->P, nav->cap, nav->maps, nav->counts, nav->poses, nav->poses_tmp,
+                          nav->ancestors, nav->st);
+    nav->launches += 4;
+    if (int r = check_async(nav, "resample launch")) return r;
+    CK(cudaStreamSynchronize(nav->stream));
+    return RBPHD_OK;
+}
+
+int rbphd_particle_depleted(rbphd_navigator* nav, int* depleted)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    const double* w;
+    int P;
+    if (int r = rbphd_get_weights(nav, &w, &P)) return r;
+    double cum = 0;   // PHD:768-777 on the host mirror (a query, not part of the frame path)
+    for (int i = 0; i < P; i++) cum += w[i] * w[i];
+    if (depleted) *depleted = (1.0 / cum < nav->cfg.min_effective_particle * P) ? 1 : 0;
+    return RBPHD_OK;
+}
+
+// ------------------------------------------------------------------ stage entry points
+static int stage_run(rbphd_navigator* nav, rbphd_navigator** sp, const double* pose7, int n, const double* w,
+                     const double* mean, const double* cov, const double* z, int m)
+{
+    if (int r = ensure_stage(nav)) return r;
+    rbphd_navigator* s = nav->stage;
+    *sp = s;
+    static const double ident[7] = {0, 0, 0, 1, 0, 0, 0};
+    if (int r = rbphd_reset(s, 1, pose7 ? pose7 : ident, n, w, mean, cov)) return fail(nav, r, s->error);
+    if (m > s->Mcap) return fail(nav, RBPHD_ERR_ARGUMENT, "m > max_measurements");
+    if (int r = rbphd_upload_frame_inputs(s, nullptr, z, m)) return fail(nav, r, s->error);
+    return RBPHD_OK;
+}
+
+static int stage_finish_dump(rbphd_navigator* nav, rbphd_navigator* s, const double** ow, const double** om,
+                             const double** oP, int* on)
+{
+    DeviceState st;
+    if (int r = read_state(s, &st)) return fail(nav, r, s->error);
+    void* hc;
+    if (int r = download(s, s->dump_count, sizeof(int), &hc)) return fail(nav, r, s->error);
+    int cnt = *(int*)hc;
+    if (cnt > s->dump_cap) return fail(nav, RBPHD_ERR_CAPACITY, "stage output larger than the dump buffer");
+    void* h;
+    if (int r = download(s, s->dump, sizeof(double) * kFields * (size_t)s->dump_cap, &h)) return fail(nav, r, s->error);
+    soa_to_outputs(nav, (const double*)h, s->dump_cap, cnt, ow, om, oP, on);
+    if (st.status) {
+        cudaMemsetAsync(&s->st->status, 0, sizeof(int), s->stream);
+        cudaStreamSynchronize(s->stream);
+        return status_to_error(nav, st.status);
+    }
+    return RBPHD_OK;
+}
+
+int rbphd_stage_predict(rbphd_navigator* nav, const double* pose7, int n, const double* w, const double* mean,
+                        const double* cov, const double* z, int m, const double** ow, const double** omean,
+                        const double** ocov, int* on)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    rbphd_navigator* s;
+    if (int r = stage_run(nav, &s, pose7, n, w, mean, cov, z, m)) return r;
+    if (int r = enqueue_map_update(s, m, 1, MODE_STAGE_PREDICT)) return fail(nav, r, s->error);
+    return stage_finish_dump(nav, s, ow, omean, ocov, on);
+}
+
+int rbphd_stage_correct(rbphd_navigator* nav, const double* pose7, int n, const double* w, const double* mean,
+                        const double* cov, const double* z, int m, double gate_radius, const double** ow,
+                        const double** omean, const double** ocov, int* on)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    rbphd_navigator* s;
+    if (int r = stage_run(nav, &s, pose7, n, w, mean, cov, z, m)) return r;
+    DevCfg saved = s->dcfg;
+    make_devcfg(s->cfg, s->dcfg, gate_radius, true);
+    if ((long long)n * m + n > s->dump_cap && gate_radius < 0) {
+        s->dcfg = saved;
+        return fail(nav, RBPHD_ERR_CAPACITY, "ungated stage_correct output exceeds max_pairs");
+    }
+    int r = enqueue_map_update(s, m, 1, MODE_STAGE_CORRECT);
+    s->dcfg = saved;
+    if (r) return fail(nav, r, s->error);
+    return stage_finish_dump(nav, s, ow, omean, ocov, on);
+}
+
+int rbphd_stage_prune(rbphd_navigator* nav, int n, const double* w, const double* mean, const double* cov,
+                      const double** ow, const double** omean, const double** ocov, int* on)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    rbphd_navigator* s;
+    if (int r = stage_run(nav, &s, nullptr, n, w, mean, cov, nullptr, 0)) return r;
+    if (int r = enqueue_map_update(s, 0, 1, MODE_STAGE_PRUNE)) return fail(nav, r, s->error);
+    launch_flip(s->stream, s->st);
+    s->launches += 1;
+    DeviceState st;
+    if (int r = read_state(s, &st)) return fail(nav, r, s->error);
+    const double *tw, *tm, *tP;
+    int tn;
+    if (int r = rbphd_get_map(s, 0, &tw, &tm, &tP, &tn)) return fail(nav, r, s->error);
+    nav->o_w.assign(tw, tw + std::max(tn, 1));
+    nav->o_m.assign(tm, tm + std::max(3 * tn, 1));
+    nav->o_P.assign(tP, tP + std::max(9 * tn, 1));
+    if (ow) *ow = nav->o_w.data();
+    if (omean) *omean = nav->o_m.data();
+    if (ocov) *ocov = nav->o_P.data();
+    if (on) *on = tn;
+    if (st.status) {
+        cudaMemsetAsync(&s->st->status, 0, sizeof(int), s->stream);
+        cudaStreamSynchronize(s->stream);
+        return status_to_error(nav, st.status);
+    }
+    return RBPHD_OK;
+}
+
+int rbphd_stage_weight_alpha(rbphd_navigator* nav, const double* pose7, const double* z, int m, int np,
+                             const double* pw, const double* pmean, const double* pcov, int nc, const double* cw,
+                             const double* cmean, const double* ccov, double* out7)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    rbphd_navigator* s;
+    if (int r = stage_run(nav, &s, pose7, np, pw, pmean, pcov, z, m)) return r;
+    if (int r = write_map(s, 1, 0, nc, cw, cmean, ccov)) return fail(nav, r, s->error);
+    if (int r = enqueue_map_update(s, m, 0, MODE_STAGE_WEIGHT)) return fail(nav, r, s->error);
+    DeviceState st;
+    if (int r = read_state(s, &st)) return fail(nav, r, s->error);
+    void* h;
+    if (int r = download(s, s->alpha_parts, sizeof(double) * 8, &h)) return fail(nav, r, s->error);
+    if (out7) std::memcpy(out7, h, 7 * sizeof(double));
+    if (st.status) {
+        cudaMemsetAsync(&s->st->status, 0, sizeof(int), s->stream);
+        cudaStreamSynchronize(s->stream);
+        return status_to_error(nav, st.status);
+    }
+    return RBPHD_OK;
+}
+
+int rbphd_stage_set_loglikelihood(rbphd_navigator* nav, const double* pose7, int j, const double* jmean,
+                                  const double* z, int m, double* loglik)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    std::vector<double> w(std::max(j, 1), 1.0), P(9 * (size_t)std::max(j, 1), 0.0);
+    for (int i = 0; i < j; i++) P[9 * (size_t)i] = P[9 * (size_t)i + 4] = P[9 * (size_t)i + 8] = 1.0;
+    rbphd_navigator* s;
+    if (int r = stage_run(nav, &s, pose7, j, w.data(), jmean, P.data(), z, m)) return r;
+    if (j > s->lay.cap_j) return fail(nav, RBPHD_ERR_CAPACITY, "landmark list larger than the map-estimate capacity");
+    if (int r = enqueue_map_update(s, m, 0, MODE_STAGE_SETLL)) return fail(nav, r, s->error);
+    DeviceState st;
+    if (int r = read_state(s, &st)) return fail(nav, r, s->error);
+    void* h;
+    if (int r = download(s, s->alphas, sizeof(double), &h)) return fail(nav, r, s->error);
+    if (loglik) *loglik = *(double*)h;
+    if (st.status) {
+        cudaMemsetAsync(&s->st->status, 0, sizeof(int), s->stream);
+        cudaStreamSynchronize(s->stream);
+        return status_to_error(nav, st.status);
+    }
+    return RBPHD_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU plumbing
+int rbphd_slam_update_local(rbphd_navigator* nav, int m, int only_mapping)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (nav->P < 1) return fail(nav, RBPHD_ERR_ARGUMENT, "navigator not reset");
+    if (m < 0 || m > nav->Mcap) return fail(nav, RBPHD_ERR_ARGUMENT, "m > max_measurements");
+    if (int r = set_device(nav)) return r;
+    if (int r = enqueue_map_update(nav, m, only_mapping, MODE_FRAME)) return r;
+    if (only_mapping) { launch_flip(nav->stream, nav->st); nav->launches += 1; }
+    return check_async(nav, "local slam update");
+}
+
+int rbphd_device_weights(rbphd_navigator* nav, void** dev_ptr, int* particles)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (dev_ptr) *dev_ptr = nav->weights;
+    if (particles) *particles = nav->P;
+    return RBPHD_OK;
+}
+
+int rbphd_resample_global(rbphd_navigator* nav, const void* dev_global_weights, int global_particles,
+                          int rank_offset, double u_resample, int* best_global, int* resampled,
+                          const int** ancestors_global)
+{
+    if (!nav || !dev_global_weights) return RBPHD_ERR_ARGUMENT;
+    if (rank_offset < 0 || rank_offset + nav->P > global_particles)
+        return fail(nav, RBPHD_ERR_ARGUMENT, "rank slice outside the global particle range");
+    if (int r = set_device(nav)) return r;
+    if (global_particles > nav->gcap) {
+        CK(cudaStreamSynchronize(nav->stream));
+        cudaFree(nav->gweights); cudaFree(nav->ganc);
+        nav->gweights = nullptr; nav->ganc = nullptr;
+        CK(cudaMalloc(&nav->gweights, sizeof(double) * (size_t)global_particles));
+        CK(cudaMalloc(&nav->ganc, sizeof(int) * (size_t)global_particles));
+        nav->gcap = global_particles;
+    }
+    CK(cudaMemcpyAsync(nav->gweights, dev_global_weights, sizeof(double) * (size_t)global_particles,
+                       cudaMemcpyDeviceToDevice, nav->stream));
+    // identical code on the identical vector on every rank -> identical ancestors, no further exchange
+    launch_normalize_resample(nav->stream, nav->dcfg, global_particles, nav->gweights, u_resample, 0, nav->ganc,
+                              nav->st);
+    nav->launches += 1;
+    CK(cudaMemcpyAsync(nav->weights, nav->gweights + rank_offset, sizeof(double) * (size_t)nav->P,
+                       cudaMemcpyDeviceToDevice, nav->stream));
+    if (int r = check_async(nav, "global resample")) return r;
+    DeviceState st;
+    if (int r = read_state(nav, &st)) return r;
+    if (best_global) *best_global = st.best;
+    if (resampled) *resampled = st.resampled;
+    if (ancestors_global) {
+        nav->o_anc.resize(global_particles);
+        if (st.resampled) {
+            void* h;
+            if (int r = download(nav, nav->ganc, sizeof(int) * (size_t)global_particles, &h)) return r;
+            std::memcpy(nav->o_anc.data(), h, sizeof(int) * (size_t)global_particles);
+        }
+        else
+            for (int i = 0; i < global_particles; i++) nav->o_anc[i] = i;
+        *ancestors_global = nav->o_anc.data();
+    }
+    return RBPHD_OK;
+}
+
+// One migration record = [count as double][pose 7][13 * cap map slab], 8 + 13*cap doubles.
+static size_t record_doubles(const rbphd_navigator* nav) { return 8 + (size_t)kFields * nav->cap; }
+
+int rbphd_pack_particles(rbphd_navigator* nav, const int* local_indices, int count, void** dev_buf, int64_t* bytes)
+{
+    if (!nav || count < 0) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    DeviceState st;
+    if (int r = read_state(nav, &st)) return r;
+    const int src = st.resampled ? 1 - st.cur : st.cur;   // after a resampling decision the posterior is in 1-cur
+    size_t need = record_doubles(nav) * sizeof(double) * (size_t)std::max(count, 1);
+    if (need > nav->packbytes) {
+        cudaFree(nav->packbuf);
+        nav->packbuf = nullptr;
+        CK(cudaMalloc(&nav->packbuf, need));
+        nav->packbytes = need;
+    }
+    std::vector<int> hc(std::max(nav->P, 1));
+    void* h;
+    if (int r = download(nav, nav->counts[src], sizeof(int) * (size_t)nav->P, &h)) return r;
+    std::memcpy(hc.data(), h, sizeof(int) * (size_t)nav->P);
+    for (int j = 0; j < count; j++) {
+        int i = local_indices[j];
+        if (i < 0 || i >= nav->P) return fail(nav, RBPHD_ERR_ARGUMENT, "pack index out of range");
+        double* rec = nav->packbuf + record_doubles(nav) * (size_t)j;
+        double cnt = hc[i];
+        CK(cudaMemcpyAsync(rec, &cnt, sizeof(double), cudaMemcpyHostToDevice, nav->stream));
+        CK(cudaStreamSynchronize(nav->stream));
+        CK(cudaMemcpyAsync(rec + 1, nav->poses + 7 * (size_t)i, 7 * sizeof(double), cudaMemcpyDeviceToDevice,
+                           nav->stream));
+        CK(cudaMemcpyAsync(rec + 8, nav->maps[src] + (size_t)i * kFields * nav->cap,
+                           sizeof(double) * kFields * (size_t)nav->cap, cudaMemcpyDeviceToDevice, nav->stream));
+    }
+    CK(cudaStreamSynchronize(nav->stream));
+    if (dev_buf) *dev_buf = nav->packbuf;
+    if (bytes) *bytes = (int64_t)(record_doubles(nav) * sizeof(double) * (size_t)count);
+    return RBPHD_OK;
+}
+
+int rbphd_unpack_particles(rbphd_navigator* nav, const void* dev_buf, const int* slots, int count)
+{
+    if (!nav || count < 0) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    DeviceState st;
+    if (int r = read_state(nav, &st)) return r;
+    const int dst = st.cur;   // new particles are assembled in buffer cur (see k_copy_particles)
+    const double* base = (const double*)dev_buf;
+    for (int j = 0; j < count; j++) {
+        int i = slots[j];
+        if (i < 0 || i >= nav->P) return fail(nav, RBPHD_ERR_ARGUMENT, "unpack slot out of range");
+        const double* rec = base + record_doubles(nav) * (size_t)j;
+        double cnt;
+        CK(cudaMemcpyAsync(&cnt, rec, sizeof(double), cudaMemcpyDeviceToHost, nav->stream));
+        CK(cudaStreamSynchronize(nav->stream));
+        int n = (int)cnt;
+        CK(cudaMemcpyAsync(nav->counts[dst] + i, &n, sizeof(int), cudaMemcpyHostToDevice, nav->stream));
+        CK(cudaStreamSynchronize(nav->stream));
+        CK(cudaMemcpyAsync(nav->poses_tmp + 7 * (size_t)i, rec + 1, 7 * sizeof(double), cudaMemcpyDeviceToDevice,
+                           nav->stream));
+        CK(cudaMemcpyAsync(nav->maps[dst] + (size_t)i * kFields * nav->cap, rec + 8,
+                           sizeof(double) * kFields * (size_t)nav->cap, cudaMemcpyDeviceToDevice, nav->stream));
+    }
+    CK(cudaStreamSynchronize(nav->stream));
+    return RBPHD_OK;
+}
+
+int rbphd_commit_resample_local(rbphd_navigator* nav, const int* local_sources, int count)
+{
+    if (!nav || count != nav->P) return fail(nav, RBPHD_ERR_ARGUMENT, "one source per local particle expected");
+    if (int r = set_device(nav)) return r;
+    DeviceState st;
+    if (int r = read_state(nav, &st)) return r;
+    const int src = 1 - st.cur, dst = st.cur;
+    for (int i = 0; i < count; i++) {
+        int a = local_sources[i];
+        if (a < 0) continue;   // filled by rbphd_unpack_particles
+        if (a >= nav->P) return fail(nav, RBPHD_ERR_ARGUMENT, "local source out of range");
+        CK(cudaMemcpyAsync(nav->maps[dst] + (size_t)i * kFields * nav->cap,
+                           nav->maps[src] + (size_t)a * kFields * nav->cap,
+                           sizeof(double) * kFields * (size_t)nav->cap, cudaMemcpyDeviceToDevice, nav->stream));
+        CK(cudaMemcpyAsync(nav->counts[dst] + i, nav->counts[src] + a, sizeof(int), cudaMemcpyDeviceToDevice,
+                           nav->stream));
+        CK(cudaMemcpyAsync(nav->poses_tmp + 7 * (size_t)i, nav->poses + 7 * (size_t)a, 7 * sizeof(double),
+                           cudaMemcpyDeviceToDevice, nav->stream));
+    }
+    CK(cudaMemcpyAsync(nav->poses, nav->poses_tmp, 7 * sizeof(double) * (size_t)nav->P, cudaMemcpyDeviceToDevice,
+                       nav->stream));
+    CK(cudaStreamSynchronize(nav->stream));
+    return RBPHD_OK;
+}
+
+int64_t rbphd_kernel_launches(const rbphd_navigator* nav) { return nav ? nav->launches : 0; }
+
+int rbphd_last_stage_ms(rbphd_navigator* nav, double* ms, int n)
+{
+    if (!nav || !ms) return RBPHD_ERR_ARGUMENT;
+    for (int i = 0; i < n && i < 8; i++) ms[i] = nav->stage_ms[i];
+    return RBPHD_OK;
+}
+
+void* rbphd_stream(rbphd_navigator* nav) { return nav ? (void*)nav->stream : nullptr; }
+
+}  // extern "C"

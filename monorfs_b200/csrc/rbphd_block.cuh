@@ -1,0 +1,246 @@
+// rbphd_block.cuh -- CTA-wide primitives used by the per-particle kernels:
+// reductions, exclusive scans, a bitonic (key,val) sort and a small uniform 3-D cell grid.
+// All functions must be called by every thread of the CTA (they contain __syncthreads()).
+#pragma once
+#include "rbphd_math.cuh"
+
+namespace rbphd {
+
+constexpr int kBlock = 256;          // threads per CTA of the per-particle kernels
+constexpr int kWarps = kBlock / 32;
+constexpr int kGridMaxDim = 16;      // per-particle cell grid: at most 16^3 cells, offsets in shared memory
+constexpr int kGridMaxCells = kGridMaxDim * kGridMaxDim * kGridMaxDim;
+
+struct BlockShared {                 // small fixed scratch in shared memory
+    int    warp_i[kWarps + 1];
+    double warp_d[2 * kWarps];
+    int    carry;
+    int    counter[8];
+    double bb[6];
+};
+
+__device__ __forceinline__ int warp_incl_scan(int v)
+{
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= (unsigned)o) v += t;
+    }
+    return v;
+}
+
+// exclusive scan of one int per thread; returns prefix, total in *total
+__device__ __forceinline__ int block_excl_scan(BlockShared& sh, int v, int* total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = warp_incl_scan(v);
+    __syncthreads();
+    if (lane == 31) sh.warp_i[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = (lane < kWarps) ? sh.warp_i[lane] : 0;
+        int wi = warp_incl_scan(w);
+        if (lane < kWarps) sh.warp_i[lane] = wi - w;
+        if (lane == kWarps - 1) sh.warp_i[kWarps] = wi;
+    }
+    __syncthreads();
+    int res = incl - v + sh.warp_i[warp];
+    *total = sh.warp_i[kWarps];
+    return res;
+}
+
+// in-place exclusive scan of an int array of length n (any memory space); returns the total
+__device__ inline int block_scan_array(BlockShared& sh, int* a, int n)
+{
+    int carry = 0;
+    for (int base = 0; base < n; base += kBlock) {
+        int i = base + threadIdx.x;
+        int v = (i < n) ? a[i] : 0;
+        int tot;
+        int ex = block_excl_scan(sh, v, &tot);
+        if (i < n) a[i] = carry + ex;
+        carry += tot;
+    }
+    __syncthreads();
+    return carry;
+}
+
+__device__ __forceinline__ double block_sum(BlockShared& sh, double v)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) sh.warp_d[warp] = v;
+    __syncthreads();
+    double s = 0;
+    for (int w = 0; w < kWarps; w++) s += sh.warp_d[w];
+    return s;
+}
+
+__device__ __forceinline__ int block_sum_int(BlockShared& sh, int v)
+{
+    int tot;
+    block_excl_scan(sh, v, &tot);
+    return tot;
+}
+
+__device__ __forceinline__ int next_pow2(int n)
+{
+    int p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+// Bitonic sort of (key,val) pairs ascending by (key, then val); n must be a power of two
+// (pad with key = ~0ull, val = ~0u).  Works on shared or global arrays.
+__device__ inline void block_bitonic_sort(unsigned long long* key, unsigned int* val, int n)
+{
+    __syncthreads();
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (n >> 1); t += kBlock) {
+                int i = ((t / j) * (j << 1)) + (t % j);
+                int p = i + j;
+                bool asc = ((i & k) == 0);
+                unsigned long long ki = key[i], kp = key[p];
+                unsigned int vi = val[i], vp = val[p];
+                bool gt = (ki > kp) || (ki == kp && vi > vp);
+                if (gt == asc) {
+                    key[i] = kp; key[p] = ki;
+                    val[i] = vp; val[p] = vi;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// first index in sorted key[0..n) with key >= k
+__device__ __forceinline__ int lower_bound_u64(const unsigned long long* key, int n, unsigned long long k)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (key[mid] < k) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Uniform 3-D cell grid over n points given as three arrays.  Cell offsets live in shared memory
+// (start[ncell+1]); the point indices, ascending within each cell, in `items` (any memory).
+// ---------------------------------------------------------------------------------------------
+struct CellGrid {
+    double org[3];
+    double inv[3];     // 1 / cell size per axis
+    double hi[3];      // bounding box maximum
+    int    dim[3];
+    int    ncell;
+    int    n;
+};
+
+__device__ __forceinline__ int grid_coord(const CellGrid& g, int a, double x)
+{
+    double f = floor((x - g.org[a]) * g.inv[a]);
+    int c = (f < 0) ? 0 : ((f >= (double)g.dim[a]) ? g.dim[a] - 1 : (int)f);
+    return c;
+}
+__device__ __forceinline__ int grid_cell(const CellGrid& g, double x, double y, double z)
+{
+    return (grid_coord(g, 2, z) * g.dim[1] + grid_coord(g, 1, y)) * g.dim[0] + grid_coord(g, 0, x);
+}
+
+// Build.  mincell = smallest useful cell edge (a typical query radius).  start must hold
+// kGridMaxCells + 1 ints of shared memory; items n ints.
+__device__ inline void grid_build(BlockShared& sh, CellGrid& g, int* start, int* items, const double* px,
+                                  const double* py, const double* pz, int n, double mincell0,
+                                  double mincell1, double mincell2)
+{
+    const double mincell3[3] = {mincell0, mincell1, mincell2};
+    // bounding box
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = threadIdx.x; i < n; i += kBlock) {
+        double x = px[i], y = py[i], z = pz[i];
+        lo[0] = fmin(lo[0], x); hi[0] = fmax(hi[0], x);
+        lo[1] = fmin(lo[1], y); hi[1] = fmax(hi[1], y);
+        lo[2] = fmin(lo[2], z); hi[2] = fmax(hi[2], z);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fmin(lo[a], __shfl_down_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmax(hi[a], __shfl_down_sync(0xffffffffu, hi[a], o));
+        }
+        __syncthreads();
+        if (lane == 0) { sh.warp_d[warp] = lo[a]; sh.warp_d[kWarps + warp] = hi[a]; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double l = INFINITY, h = -INFINITY;
+            for (int w = 0; w < kWarps; w++) { l = fmin(l, sh.warp_d[w]); h = fmax(h, sh.warp_d[kWarps + w]); }
+            if (!(l <= h)) { l = 0; h = 0; }
+            double ext = h - l;
+            double mc = mincell3[a];
+            double dd = (mc > 0) ? ceil(ext / mc) : (double)kGridMaxDim;
+            int d = (dd >= (double)kGridMaxDim) ? kGridMaxDim : ((dd >= 1.0) ? (int)dd : 1);
+            double cs = ext / d;
+            if (!(cs > 0)) cs = 1.0;
+            cs = cs * (1.0 + 1e-12) + 1e-300;
+            g.org[a] = l; g.hi[a] = h; g.dim[a] = d; g.inv[a] = 1.0 / cs;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { g.ncell = g.dim[0] * g.dim[1] * g.dim[2]; g.n = n; }
+    __syncthreads();
+    const int ncell = g.ncell;
+    for (int c = threadIdx.x; c <= ncell; c += kBlock) start[c] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kBlock) atomicAdd(&start[grid_cell(g, px[i], py[i], pz[i])], 1);
+    __syncthreads();
+    block_scan_array(sh, start, ncell + 1);   // start[c] = first slot of cell c, start[ncell] = n
+    // scatter with a per-cell cursor kept in items' tail?  Use a second pass with atomics on a copy:
+    // cursor = start (consumed), then restore by shifting.
+    for (int i = threadIdx.x; i < n; i += kBlock) {
+        int c = grid_cell(g, px[i], py[i], pz[i]);
+        int slot = atomicAdd(&start[c], 1);
+        items[slot] = i;
+    }
+    __syncthreads();
+    // start[c] now = end of cell c = original start[c+1]; shift right by one to restore
+    // (chunks from the top down, so a chunk never reads a slot a previous chunk already rewrote)
+    for (int base = (ncell / kBlock) * kBlock; base >= 0; base -= kBlock) {
+        int c = base + threadIdx.x;
+        int v = (c <= ncell && c > 0) ? start[c - 1] : 0;
+        __syncthreads();
+        if (c <= ncell) start[c] = v;
+        __syncthreads();
+    }
+    // ascending order inside each cell (deterministic enumeration)
+    for (int c = threadIdx.x; c < ncell; c += kBlock) {
+        int b = start[c], e = start[c + 1];
+        for (int i = b + 1; i < e; i++) {
+            int v = items[i], j = i - 1;
+            while (j >= b && items[j] > v) { items[j + 1] = items[j]; j--; }
+            items[j + 1] = v;
+        }
+    }
+    __syncthreads();
+}
+
+// cell range covered by the ball (x,y,z; r); returns false if it misses the bounding box
+__device__ __forceinline__ bool grid_range(const CellGrid& g, double x, double y, double z, double r, int* lo,
+                                           int* hi)
+{
+    const double q[3] = {x, y, z};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        if (!(q[a] + r >= g.org[a]) || !(q[a] - r <= g.hi[a])) return false;
+        lo[a] = grid_coord(g, a, q[a] - r);
+        hi[a] = grid_coord(g, a, q[a] + r);
+    }
+    return true;
+}
+
+}  // namespace rbphd

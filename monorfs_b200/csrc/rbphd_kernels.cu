@@ -1,0 +1,1040 @@
+// rbphd_kernels.cu -- sm_100a kernels of the RB-PHD SLAM per-frame update.
+//
+//   k_predict_pose        particle prediction                       (PHD:295-314, TRK:89-102, POSE:314-333)
+//   k_frame_prep          per-frame measurement grids (camera frame + measurement space), shared by all particles
+//   k_particle_update     persistent, one CTA per particle at a time: PredictConditional + CorrectConditional
+//                         + PruneModel + WeightAlpha fused; every intermediate (gated pairs, pre-prune list,
+//                         merge graph) stays in a per-CTA scratch slab that is reused particle after particle,
+//                         so it lives in L2 and only the prior map is read from / the pruned map written to HBM
+//   k_normalize_resample  weight normalisation, best particle, ESS test, systematic wheel   (PHD:343-358, 724-777)
+//   k_copy_particles      device-side copy of the ancestors' maps and poses                (PHD:740-742)
+//
+// FP64 CUDA-core arithmetic throughout (batched 3x3 algebra; tensor cores do not apply); compiled with
+// -fmad=false so results match the CPU oracle bit for bit apart from libm transcendentals.
+#include "rbphd_kernels.cuh"
+
+
+namespace rbphd {
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory context of one CTA of k_particle_update
+// ------------------------------------------------------------------------------------------------
+struct Ctx {
+    int N, B, Npred, npairs, npairs_prior, L, ncand, W0, nedges, nout, nF;
+    int status;
+    double pose[7];
+    CellGrid grid;
+};
+
+struct Smem {
+    BlockShared sh;
+    Ctx ctx;
+    double* zs;      // 3*M
+    double* cs;      // 3*M   measurement points in map space for the current particle
+    int* kflag;      // M     explored flag
+    int* kidx;       // M+1   birth index / generic per-measurement ints
+    int* gstart;     // kGridMaxCells+1
+    unsigned long long* skey;   // sort buffer (smem_sort_cap)
+    unsigned int* sval;
+};
+
+struct Slab {
+    // predicted map = prior components followed by births
+    double *pm, *pwt, *pwmd, *ppd;
+    int *flagf, *fidx, *bidx;
+    unsigned long long* pkey;
+    double *pt, *pmean, *pcov, *pwgt;
+    unsigned long long* skey;
+    unsigned int* sval;
+    double *tw, *tm, *tP, *rho;
+    int *ecnt, *edst, *nstate, *nowner, *nflag, *gitems;
+    int *jidx;
+    double *jm, *jmp, *jpd, *vsum, *cinv, *cnorm, *crad;
+    int *fat, *clist;
+    double* gx;
+    unsigned long long* llkey;
+    double* llval;
+    int *uf;
+    double* bsum;
+    int *bcnt, *bmin;
+    unsigned char* mslots;
+};
+
+__device__ __forceinline__ Slab make_slab(unsigned char* base, const ScratchLayout& l)
+{
+    Slab s;
+    s.pm = (double*)(base + l.pm); s.pwt = (double*)(base + l.pwt); s.pwmd = (double*)(base + l.pwmd);
+    s.ppd = (double*)(base + l.ppd); s.flagf = (int*)(base + l.flagf); s.fidx = (int*)(base + l.fidx);
+    s.bidx = (int*)(base + l.bidx);
+    s.pkey = (unsigned long long*)(base + l.pkey); s.pt = (double*)(base + l.pt);
+    s.pmean = (double*)(base + l.pmean); s.pcov = (double*)(base + l.pcov); s.pwgt = (double*)(base + l.pwgt);
+    s.skey = (unsigned long long*)(base + l.skey); s.sval = (unsigned int*)(base + l.sval);
+    s.tw = (double*)(base + l.tw); s.tm = (double*)(base + l.tm); s.tP = (double*)(base + l.tP);
+    s.rho = (double*)(base + l.rho);
+    s.ecnt = (int*)(base + l.ecnt); s.edst = (int*)(base + l.edst); s.nstate = (int*)(base + l.nstate);
+    s.nowner = (int*)(base + l.nowner); s.nflag = (int*)(base + l.nflag); s.gitems = (int*)(base + l.gitems);
+    s.jidx = (int*)(base + l.jidx); s.jm = (double*)(base + l.jm); s.jmp = (double*)(base + l.jmp);
+    s.jpd = (double*)(base + l.jpd); s.vsum = (double*)(base + l.vsum); s.cinv = (double*)(base + l.cinv);
+    s.cnorm = (double*)(base + l.cnorm); s.crad = (double*)(base + l.crad); s.fat = (int*)(base + l.fat);
+    s.clist = (int*)(base + l.clist); s.gx = (double*)(base + l.gx);
+    s.llkey = (unsigned long long*)(base + l.llkey); s.llval = (double*)(base + l.llval);
+    s.uf = (int*)(base + l.uf); s.bsum = (double*)(base + l.bsum); s.bcnt = (int*)(base + l.bcnt);
+    s.bmin = (int*)(base + l.bmin); s.mslots = base + l.mslots;
+    return s;
+}
+
+// map field accessors: slab of 13*cap doubles
+__device__ __forceinline__ const double* mfield(const double* map, int cap, int f) { return map + (size_t)f * cap; }
+__device__ __forceinline__ double* mfield(double* map, int cap, int f) { return map + (size_t)f * cap; }
+
+// component i of the predicted map (prior component i < N, otherwise a birth)
+__device__ __forceinline__ void load_pred(const KParams& p, const Slab& s, const double* in, int N, int i,
+                                          double& w, double* m, double* P)
+{
+    const int capp = p.lay.cap_pred;
+    w = s.pwt[i];
+    m[0] = s.pm[i]; m[1] = s.pm[capp + i]; m[2] = s.pm[2 * capp + i];
+    if (i < N) {
+#pragma unroll
+        for (int a = 0; a < 9; a++) P[a] = mfield(in, p.cap, 4 + a)[i];
+    }
+    else {
+#pragma unroll
+        for (int a = 0; a < 9; a++) P[a] = p.cfg.birth_cov[a];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gate lookup: append every (k, i) with |m_i - c_k|^2 within the correct gate (PHD:882, MAP:170-184)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gate_append(const KParams& p, Smem& sm, const Slab& s, int i, const double* m,
+                                            const Quat& local)
+{
+    const DevCfg& c = p.cfg;
+    const int M = p.M;
+    if (c.ungated) {
+        for (int k = 0; k < M; k++) {
+            int j = atomicAdd(&sm.ctx.npairs, 1);
+            if (j < p.lay.cap_pairs) s.pkey[j] = ((unsigned long long)k << 32) | (unsigned)i;
+        }
+        return;
+    }
+    const CellGrid& g = p.vgrid->g;
+    int lo[3], hi[3];
+    if (!grid_range(g, local.x, local.y, local.z, c.gate_r + 1e-9, lo, hi)) return;
+    for (int cz = lo[2]; cz <= hi[2]; cz++)
+        for (int cy = lo[1]; cy <= hi[1]; cy++) {
+            int rowc = (cz * g.dim[1] + cy) * g.dim[0];
+            int b = __ldg(&p.vgrid->start[rowc + lo[0]]), e = __ldg(&p.vgrid->start[rowc + hi[0] + 1]);
+            for (int t = b; t < e; t++) {
+                int k = __ldg(&p.vitems[t]);
+                double dx = m[0] - sm.cs[3 * k], dy = m[1] - sm.cs[3 * k + 1], dz = m[2] - sm.cs[3 * k + 2];
+                double d2 = dx * dx + dy * dy + dz * dz;
+                if (d2 <= c.gate_r2) {
+                    int j = atomicAdd(&sm.ctx.npairs, 1);
+                    if (j < p.lay.cap_pairs) s.pkey[j] = ((unsigned long long)k << 32) | (unsigned)i;
+                }
+            }
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one gated pair: measurement-space Gaussian of the component, Kalman gain, updated mean and
+// covariance, un-normalised weight term (PHD:858-870, 886-902) and, for prior components, the
+// exploration density term w_i N(c_k; m_i, P_i) (PHD:956-959, MAP:210-220)
+// ------------------------------------------------------------------------------------------------
+__device__ inline void eval_pair(const KParams& p, Smem& sm, const Slab& s, const double* in, int j)
+{
+    const DevCfg& c = p.cfg;
+    const int N = sm.ctx.N, capq = p.lay.cap_pairs;
+    const unsigned long long key = s.pkey[j];
+    const int i = (int)(key & 0xffffffffu), k = (int)(key >> 32);
+    double w, m[3], P[9];
+    load_pred(p, s, in, N, i, w, m, P);
+    Pose pose = pose_load(sm.ctx.pose);
+    double diff[3], mp[3], H[9], PH[9], S[9], Sinv[9];
+    Quat local;
+    to_local(pose, m, diff, local);
+    measure_from_local(c, diff, local, mp);
+    jacobian_l(c, pose, local, H);
+    mat3_mul_bt(P, H, PH);          // PH = P H^T
+    mat3_mul(H, PH, S);             // S = H P H^T + R
+#pragma unroll
+    for (int a = 0; a < 9; a++) S[a] = S[a] + c.R[a];
+    double det = mat3_inv(S, Sinv);
+    double mult = gauss_mult(det);
+    const double* zk = &sm.zs[3 * k];
+    double innov[3] = {zk[0] - mp[0], zk[1] - mp[1], zk[2] - mp[2]};
+    double q = mult * exp(-0.5 * quadform3(Sinv, innov));
+    double pdi = s.ppd[i];
+    s.pt[j] = pdi * w * q;
+
+    double K[9], kd[3], KH[9], IKH[9], Pn[9];
+    mat3_mul(PH, Sinv, K);
+    mat3_vec(K, innov, kd);
+    s.pmean[j] = m[0] + kd[0]; s.pmean[capq + j] = m[1] + kd[1]; s.pmean[2 * capq + j] = m[2] + kd[2];
+    mat3_mul(K, H, KH);
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) IKH[a * 3 + b] = ((a == b) ? 1.0 : 0.0) - KH[a * 3 + b];
+    mat3_mul(IKH, P, Pn);
+#pragma unroll
+    for (int a = 0; a < 9; a++) s.pcov[(size_t)a * capq + j] = Pn[a];
+
+    if (i < N && !sm.kflag[k]) {   // exploration term of a prior component (one term >= threshold decides)
+        double Pinv[9];
+        double detp = mat3_inv(P, Pinv);
+        const double* ck = &sm.cs[3 * k];
+        double dc[3] = {ck[0] - m[0], ck[1] - m[1], ck[2] - m[2]};
+        double e = w * (gauss_mult(detp) * exp(-0.5 * quadform3(Pinv, dc)));
+        if (e >= c.explore_thr) sm.kflag[k] = 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase A: PredictConditional + CorrectConditional
+// ------------------------------------------------------------------------------------------------
+__device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s, const double* in, int particle)
+{
+    const DevCfg& c = p.cfg;
+    const int M = p.M, tid = threadIdx.x, capp = p.lay.cap_pred;
+    const int N = sm.ctx.N;
+    const Pose pose = pose_load(sm.ctx.pose);
+    const bool do_births = (p.mode == MODE_FRAME || p.mode == MODE_STAGE_PREDICT);
+    const bool do_correct = (p.mode == MODE_FRAME || p.mode == MODE_STAGE_CORRECT);
+
+    // A1: measurements in map space (PRM:299-312)
+    for (int k = tid; k < M; k += kBlock) {
+        double ck[3];
+        measure_to_map(c, pose, &sm.zs[3 * k], ck);
+        sm.cs[3 * k] = ck[0]; sm.cs[3 * k + 1] = ck[1]; sm.cs[3 * k + 2] = ck[2];
+        sm.kflag[k] = do_births ? 0 : 1;
+    }
+    __syncthreads();
+
+    // A2: prior components: miss-detection weight (PHD:837-840), gate lookup, frustum flag
+    const CellGrid& vg = p.vgrid->g;
+    for (int i = tid; i < N; i += kBlock) {
+        double w = mfield(in, p.cap, 0)[i];
+        double m[3] = {mfield(in, p.cap, 1)[i], mfield(in, p.cap, 2)[i], mfield(in, p.cap, 3)[i]};
+        s.pm[i] = m[0]; s.pm[capp + i] = m[1]; s.pm[2 * capp + i] = m[2];
+        s.pwt[i] = w;
+        double diff[3], mp[3];
+        Quat local;
+        to_local(pose, m, diff, local);
+        measure_from_local(c, diff, local, mp);
+        double pdi = detection_probability(c, mp);
+        s.ppd[i] = pdi;
+        s.pwmd[i] = (1 - pdi) * w;
+        if (do_correct) gate_append(p, sm, s, i, m, local);
+        int lo[3], hi[3];
+        s.flagf[i] = (do_births && M > 0 && grid_range(vg, local.x, local.y, local.z, c.explore_r + 1e-9, lo, hi)) ? 1 : 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (sm.ctx.npairs > p.lay.cap_pairs) { sm.ctx.npairs = p.lay.cap_pairs; sm.ctx.status |= ST_OVER_PAIRS; }
+        sm.ctx.npairs_prior = sm.ctx.npairs;
+    }
+    __syncthreads();
+
+    // A3: gated pairs of prior components
+    for (int j = tid; j < sm.ctx.npairs_prior; j += kBlock) eval_pair(p, sm, s, in, j);
+    __syncthreads();
+
+    int B = 0;
+    if (do_births) {
+        // A4: measurements not yet known to be explored: exact gated density sum over the prior map,
+        // in component order (MAP:210-220).  One warp per measurement; only components near the frustum.
+        int nF = block_scan_array(sm.sh, s.flagf, N);   // flagf -> exclusive prefix
+        for (int i = tid; i < N; i += kBlock) {
+            int pos = s.flagf[i];
+            int nxt = (i + 1 < N) ? s.flagf[i + 1] : nF;
+            if (nxt > pos) s.fidx[pos] = i;
+        }
+        __syncthreads();
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int k = warp; k < M; k += kWarps) {
+            if (sm.kflag[k]) continue;
+            const double ck[3] = {sm.cs[3 * k], sm.cs[3 * k + 1], sm.cs[3 * k + 2]};
+            double sum = 0;
+            for (int base = 0; base < nF; base += 32) {
+                int f = base + lane;
+                bool hit = false;
+                double term = 0;
+                if (f < nF) {
+                    int i = s.fidx[f];
+                    double m[3] = {s.pm[i], s.pm[capp + i], s.pm[2 * capp + i]};
+                    double dx = m[0] - ck[0], dy = m[1] - ck[1], dz = m[2] - ck[2];
+                    double d2 = dx * dx + dy * dy + dz * dz;
+                    if (d2 <= c.explore_r2) {
+                        hit = true;
+                        double P[9], Pinv[9];
+#pragma unroll
+                        for (int a = 0; a < 9; a++) P[a] = mfield(in, p.cap, 4 + a)[i];
+                        double detp = mat3_inv(P, Pinv);
+                        double dc[3] = {ck[0] - m[0], ck[1] - m[1], ck[2] - m[2]};
+                        term = s.pwt[i] * (gauss_mult(detp) * exp(-0.5 * quadform3(Pinv, dc)));
+                    }
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, hit);
+                while (mask) {
+                    int l = __ffs(mask) - 1;
+                    sum += __shfl_sync(0xffffffffu, term, l);
+                    mask &= mask - 1;
+                }
+            }
+            if (lane == 0 && sum >= c.explore_thr) sm.kflag[k] = 1;
+        }
+        __syncthreads();
+
+        // A5: births in measurement order (PHD:806-816)
+        for (int k = tid; k < M; k += kBlock) sm.kidx[k] = sm.kflag[k] ? 0 : 1;
+        __syncthreads();
+        B = block_scan_array(sm.sh, sm.kidx, M);
+        if (N + B > capp) { B = capp - N; if (tid == 0) sm.ctx.status |= ST_OVER_COMPONENTS; }
+        for (int k = tid; k < M; k += kBlock) {
+            if (!sm.kflag[k]) {
+                int b = sm.kidx[k];
+                if (b < B) {
+                    int i = N + b;
+                    s.pm[i] = sm.cs[3 * k]; s.pm[capp + i] = sm.cs[3 * k + 1]; s.pm[2 * capp + i] = sm.cs[3 * k + 2];
+                    s.pwt[i] = c.birth_w;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { sm.ctx.B = B; sm.ctx.Npred = N + B; }
+    __syncthreads();
+    const int Npred = N + B;
+
+    // A6/A7: births as predicted components: miss-detection weight, gate lookup, pairs
+    for (int i = N + tid; i < Npred; i += kBlock) {
+        double m[3] = {s.pm[i], s.pm[capp + i], s.pm[2 * capp + i]};
+        double diff[3], mp[3];
+        Quat local;
+        to_local(pose, m, diff, local);
+        measure_from_local(c, diff, local, mp);
+        double pdi = detection_probability(c, mp);
+        s.ppd[i] = pdi;
+        s.pwmd[i] = (1 - pdi) * c.birth_w;
+        if (do_correct) gate_append(p, sm, s, i, m, local);
+    }
+    __syncthreads();
+    if (tid == 0 && sm.ctx.npairs > p.lay.cap_pairs) { sm.ctx.npairs = p.lay.cap_pairs; sm.ctx.status |= ST_OVER_PAIRS; }
+    __syncthreads();
+    for (int j = sm.ctx.npairs_prior + tid; j < sm.ctx.npairs; j += kBlock) eval_pair(p, sm, s, in, j);
+    __syncthreads();
+
+    // A8: order the pairs by (measurement, component): the reference's output order (PHD:881-903)
+    const int np = sm.ctx.npairs;
+    const int np2 = next_pow2(np > 1 ? np : 1);
+    unsigned long long* skey = (np2 <= (int)p.smem_sort_cap) ? sm.skey : s.skey;
+    unsigned int* sval = (np2 <= (int)p.smem_sort_cap) ? sm.sval : s.sval;
+    for (int j = tid; j < np2; j += kBlock) {
+        skey[j] = (j < np) ? s.pkey[j] : ~0ull;
+        sval[j] = (j < np) ? (unsigned)j : ~0u;
+    }
+    block_bitonic_sort(skey, sval, np2);
+
+    // A9: per measurement: weightsum in component order, then the detection weights (PHD:886-902)
+    for (int k = tid; k < M; k += kBlock) {
+        int b = lower_bound_u64(skey, np, (unsigned long long)k << 32);
+        int e = lower_bound_u64(skey, np, (unsigned long long)(k + 1) << 32);
+        double ws = 0;
+        for (int t = b; t < e; t++) ws += s.pt[sval[t]];
+        for (int t = b; t < e; t++) {
+            double wv = s.pt[sval[t]] / (c.clutter + ws);
+            if (wv != wv) wv = 0;   // GAUSS:154
+            s.pwgt[t] = wv;
+        }
+    }
+    __syncthreads();
+    // keep the permutation (sorted position -> pair slot) in the slab for the later phases
+    for (int j = tid; j < np; j += kBlock) s.bidx[j] = (int)sval[j];
+    __syncthreads();
+    if (tid == 0) sm.ctx.L = Npred + np;
+    __syncthreads();
+    (void)particle;
+}
+
+// entry e of the corrected (pre-prune) list: e < Npred the miss-detected copy, else a detection
+__device__ __forceinline__ void load_corrected(const KParams& p, const Smem& sm, const Slab& s, const double* in,
+                                               int e, double& w, double* m, double* P)
+{
+    const int Npred = sm.ctx.Npred;
+    if (e < Npred) {
+        double w0;
+        load_pred(p, s, in, sm.ctx.N, e, w0, m, P);
+        w = s.pwmd[e];
+    }
+    else {
+        const int t = e - Npred, j = s.bidx[t], capq = p.lay.cap_pairs;
+        w = s.pwgt[t];
+        m[0] = s.pmean[j]; m[1] = s.pmean[capq + j]; m[2] = s.pmean[2 * capq + j];
+#pragma unroll
+        for (int a = 0; a < 9; a++) P[a] = s.pcov[(size_t)a * capq + j];
+    }
+}
+
+// visit the ranks r' != r whose mean lies within radius rho of (x,y,z); f(r') is called for each
+template <class F>
+__device__ __forceinline__ void for_neighbours(const Smem& sm, const Slab& s, int npts, const double* px,
+                                               const double* py, const double* pz, double x, double y, double z,
+                                               double rho, F f)
+{
+    const CellGrid& g = sm.ctx.grid;
+    int lo[3], hi[3];
+    bool brute = !(rho == rho) || isinf(rho);
+    if (!brute) {
+        if (!grid_range(g, x, y, z, rho, lo, hi)) return;
+        long cells = (long)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
+        if (cells > 128) brute = true;
+    }
+    if (brute) {
+        for (int r = 0; r < npts; r++) f(r);
+        return;
+    }
+    for (int cz = lo[2]; cz <= hi[2]; cz++)
+        for (int cy = lo[1]; cy <= hi[1]; cy++) {
+            int rowc = (cz * g.dim[1] + cy) * g.dim[0];
+            int b = sm.gstart[rowc + lo[0]], e = sm.gstart[rowc + hi[0] + 1];
+            for (int t = b; t < e; t++) {
+                int r = s.gitems[t];
+                double dx = px[r] - x, dy = py[r] - y, dz = pz[r] - z;
+                if (fabs(dx) <= rho && fabs(dy) <= rho && fabs(dz) <= rho) f(r);
+            }
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase B: PruneModel (PHD:913-948): stable weight-descending order, MinWeight / MaxQuantity cut,
+// greedy Mahalanobis clustering, moment-matched merge (GAUSS:243-246, 297-347)
+// ------------------------------------------------------------------------------------------------
+__device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const double* in, double* out)
+{
+    const DevCfg& c = p.cfg;
+    const int tid = threadIdx.x;
+    const int L = sm.ctx.L, Npred = sm.ctx.Npred;
+    const int capw = p.lay.cap_top;
+
+    // B1: entries that survive the MinWeight test, sorted by (weight desc, list position asc)
+    if (tid == 0) sm.ctx.ncand = 0;
+    __syncthreads();
+    for (int e = tid; e < L; e += kBlock) {
+        double w = (e < Npred) ? s.pwmd[e] : s.pwgt[e - Npred];
+        if (!(w < c.min_w)) {
+            int idx = atomicAdd(&sm.ctx.ncand, 1);
+            s.skey[idx] = weight_desc_key(w);
+            s.sval[idx] = (unsigned)e;
+        }
+    }
+    __syncthreads();
+    const int nc = sm.ctx.ncand;
+    const int nc2 = next_pow2(nc > 1 ? nc : 1);
+    unsigned long long* skey = s.skey;
+    unsigned int* sval = s.sval;
+    if (nc2 <= (int)p.smem_sort_cap) {
+        for (int j = tid; j < nc2; j += kBlock) {
+            sm.skey[j] = (j < nc) ? s.skey[j] : ~0ull;
+            sm.sval[j] = (j < nc) ? s.sval[j] : ~0u;
+        }
+        skey = sm.skey; sval = sm.sval;
+    }
+    else {
+        for (int j = nc + tid; j < nc2; j += kBlock) { s.skey[j] = ~0ull; s.sval[j] = ~0u; }
+    }
+    block_bitonic_sort(skey, sval, nc2);
+    const int W0 = min(min(c.maxq, nc), capw);
+    if (tid == 0) { sm.ctx.W0 = W0; if (min(c.maxq, nc) > capw) sm.ctx.status |= ST_OVER_COMPONENTS; }
+
+    // B2: materialise the W0 heaviest entries in rank order; merge radius bound per candidate:
+    // d2 = D^T P^-1 D >= |D|^2 / trace(P), so d2 < t^2 needs |D|^2 < t^2 trace(P)
+    double rsum = 0;
+    for (int r = tid; r < W0; r += kBlock) {
+        double w, m[3], P[9];
+        load_corrected(p, sm, s, in, (int)sval[r], w, m, P);
+        s.tw[r] = w;
+        s.tm[r] = m[0]; s.tm[capw + r] = m[1]; s.tm[2 * capw + r] = m[2];
+#pragma unroll
+        for (int a = 0; a < 9; a++) s.tP[(size_t)a * capw + r] = P[a];
+        double tr = P[0] + P[4] + P[8];
+        double rho = c.merge_t * sqrt(tr) * (1.0 + 1e-9);
+        if (!(tr > 0) || !(rho == rho)) rho = INFINITY;
+        s.rho[r] = rho;
+        if (!isinf(rho)) rsum += rho;
+    }
+    double rmean = block_sum(sm.sh, rsum) / (W0 > 0 ? W0 : 1);
+    __syncthreads();
+
+    // B3: cell grid over the W0 means; out-edges r -> r' (r' > r, close w.r.t. candidate r's covariance)
+    const double* tx = s.tm; const double* ty = s.tm + capw; const double* tz = s.tm + 2 * capw;
+    double mincell = 2.0 * rmean;
+    grid_build(sm.sh, sm.ctx.grid, sm.gstart, s.gitems, tx, ty, tz, W0, mincell, mincell, mincell);
+    const double t2 = c.merge_t * c.merge_t;
+    for (int pass = 0; pass < 2; pass++) {
+        for (int r = tid; r < W0; r += kBlock) {
+            double P[9], Pinv[9];
+#pragma unroll
+            for (int a = 0; a < 9; a++) P[a] = s.tP[(size_t)a * capw + r];
+            mat3_inv(P, Pinv);
+            const double x = tx[r], y = ty[r], z = tz[r];
+            int cnt = 0;
+            const int off = (pass == 1) ? s.ecnt[r] : 0;
+            const int cape = p.lay.cap_edges;
+            for_neighbours(sm, s, W0, tx, ty, tz, x, y, z, s.rho[r], [&](int r2) {
+                if (r2 <= r) return;
+                double d[3] = {x - tx[r2], y - ty[r2], z - tz[r2]};   // a.Mean - b.Mean (GAUSS:367)
+                if (quadform3(Pinv, d) < t2) {
+                    if (pass == 1 && off + cnt < cape) s.edst[off + cnt] = r2;
+                    cnt++;
+                }
+            });
+            if (pass == 0) s.ecnt[r] = cnt;
+            else {
+                int e = min(off + cnt, cape);
+                for (int a = off + 1; a < e; a++) {   // ascending r' (= list order of the reference's inner loop)
+                    int v = s.edst[a], b = a - 1;
+                    while (b >= off && s.edst[b] > v) { s.edst[b + 1] = s.edst[b]; b--; }
+                    s.edst[b + 1] = v;
+                }
+            }
+        }
+        __syncthreads();
+        if (pass == 0) {
+            if (tid == 0) s.ecnt[W0] = 0;
+            __syncthreads();
+            int ne = block_scan_array(sm.sh, s.ecnt, W0 + 1);
+            if (tid == 0) { sm.ctx.nedges = ne; if (ne > p.lay.cap_edges) sm.ctx.status |= ST_OVER_EDGES; }
+            __syncthreads();
+        }
+    }
+
+    // B4: which candidates survive.  A component is absorbed iff some surviving earlier candidate is
+    // close to it; resolve in rounds (the lowest undecided rank is always decidable).
+    for (int r = tid; r < W0; r += kBlock) { s.nstate[r] = 0; s.nflag[r] = 0; s.nowner[r] = 0x7fffffff; }
+    __syncthreads();
+    const int cape = p.lay.cap_edges;
+    for (int round = 0; round <= W0; round++) {
+        for (int r = tid; r < W0; r += kBlock) {
+            int st = s.nstate[r];
+            if (st == 2) continue;
+            int b = min(s.ecnt[r], cape), e = min(s.ecnt[r + 1], cape);
+            for (int a = b; a < e; a++) {
+                int d = s.edst[a];
+                if (s.nstate[d] == 0) atomicOr(&s.nflag[d], (st == 1) ? 2 : 1);
+            }
+        }
+        __syncthreads();
+        int und = 0;
+        for (int r = tid; r < W0; r += kBlock) {
+            if (s.nstate[r] == 0) {
+                int f = s.nflag[r];
+                if (f & 2) s.nstate[r] = 2;
+                else if (!(f & 1)) s.nstate[r] = 1;
+                else und++;
+                s.nflag[r] = 0;
+            }
+        }
+        int tot = block_sum_int(sm.sh, und);
+        __syncthreads();
+        if (tot == 0) break;
+    }
+    // B5: owner of each absorbed component = the first surviving candidate that is close to it
+    for (int r = tid; r < W0; r += kBlock) {
+        if (s.nstate[r] != 1) continue;
+        int b = min(s.ecnt[r], cape), e = min(s.ecnt[r + 1], cape);
+        for (int a = b; a < e; a++) atomicMin(&s.nowner[s.edst[a]], r);
+    }
+    __syncthreads();
+    // B6: output slot of each survivor, then the merge (GAUSS:329-346) in list order
+    for (int r = tid; r < W0; r += kBlock) s.nflag[r] = (s.nstate[r] == 1) ? 1 : 0;
+    __syncthreads();
+    int nout = block_scan_array(sm.sh, s.nflag, W0);
+    if (nout > p.cap) { nout = p.cap; if (tid == 0) sm.ctx.status |= ST_OVER_COMPONENTS; }
+    for (int r = tid; r < W0; r += kBlock) {
+        if (s.nstate[r] != 1) continue;
+        int o = s.nflag[r];
+        if (o >= nout) continue;
+        double weight = 0.0, mean[3] = {0, 0, 0}, cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        int b = min(s.ecnt[r], cape), e = min(s.ecnt[r + 1], cape);
+        int a = b - 1;
+        int member = r;
+        while (true) {
+            double w = s.tw[member];
+            double m[3] = {tx[member], ty[member], tz[member]};
+            weight += w;
+#pragma unroll
+            for (int i = 0; i < 3; i++) mean[i] = mean[i] + w * m[i];
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    cov[i * 3 + k] = cov[i * 3 + k] + w * (s.tP[(size_t)(i * 3 + k) * capw + member] + m[i] * m[k]);
+            // next member owned by r
+            a++;
+            while (a < e && s.nowner[s.edst[a]] != r) a++;
+            if (a >= e) break;
+            member = s.edst[a];
+        }
+        double ow, om[3], oP[9];
+        if (weight < 1e-15) {
+            ow = 0.0;
+            om[0] = tx[r]; om[1] = ty[r]; om[2] = tz[r];
+#pragma unroll
+            for (int i = 0; i < 9; i++) oP[i] = (i % 4 == 0) ? 1e12 : 0.0;
+        }
+        else {
+#pragma unroll
+            for (int i = 0; i < 3; i++) om[i] = mean[i] / weight;
+            double rw = 1 / weight;
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int k = 0; k < 3; k++) oP[i * 3 + k] = rw * cov[i * 3 + k] - om[i] * om[k];
+            ow = weight;
+            if (ow != ow) ow = 0;
+        }
+        mfield(out, p.cap, 0)[o] = ow;
+        mfield(out, p.cap, 1)[o] = om[0]; mfield(out, p.cap, 2)[o] = om[1]; mfield(out, p.cap, 3)[o] = om[2];
+#pragma unroll
+        for (int i = 0; i < 9; i++) mfield(out, p.cap, 4 + i)[o] = oP[i];
+    }
+    if (tid == 0) sm.ctx.nout = nout;
+    __syncthreads();
+}
+
+// implemented in rbphd_weight.cuh (included below): WeightAlpha (PHD:373-393)
+__device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const double* predcov, int npriorcov,
+                               const double* corr, int ncorr, double* parts);
+__device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab& s, int J);
+
+}  // namespace rbphd
+
+#include "rbphd_weight.cuh"
+
+namespace rbphd {
+
+// dump helper for the stage entry points: write component (w,m,P) at position o of the dump buffer
+__device__ __forceinline__ void dump_comp(const KParams& p, int o, double w, const double* m, const double* P)
+{
+    if (o >= p.dump_cap) return;
+    double* d = p.dump;
+    const int dc = p.dump_cap;
+    d[o] = w;
+    d[(size_t)1 * dc + o] = m[0]; d[(size_t)2 * dc + o] = m[1]; d[(size_t)3 * dc + o] = m[2];
+    for (int a = 0; a < 9; a++) d[(size_t)(4 + a) * dc + o] = P[a];
+}
+
+__device__ __forceinline__ void carve_smem(unsigned char* raw, const KParams& p, Smem*& smp)
+{
+    smp = reinterpret_cast<Smem*>(raw);
+    size_t off = (sizeof(Smem) + 15) & ~size_t(15);
+    const int Mc = (p.M + 1) & ~1;
+    smp->zs = reinterpret_cast<double*>(raw + off); off += sizeof(double) * 3 * (Mc > 0 ? Mc : 2);
+    smp->cs = reinterpret_cast<double*>(raw + off); off += sizeof(double) * 3 * (Mc > 0 ? Mc : 2);
+    smp->skey = reinterpret_cast<unsigned long long*>(raw + off); off += sizeof(unsigned long long) * p.smem_sort_cap;
+    smp->sval = reinterpret_cast<unsigned int*>(raw + off); off += sizeof(unsigned int) * p.smem_sort_cap;
+    smp->kflag = reinterpret_cast<int*>(raw + off); off += sizeof(int) * (Mc + 2);
+    smp->kidx = reinterpret_cast<int*>(raw + off); off += sizeof(int) * (Mc + 2);
+    smp->gstart = reinterpret_cast<int*>(raw + off);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused per-particle kernel (persistent: CTA b processes particles b, b+grid, ...)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock, 2) k_particle_update(const __grid_constant__ KParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    if (threadIdx.x == 0) { Smem* smp; carve_smem(smem_raw, p, smp); }
+    __syncthreads();
+    const int tid = threadIdx.x;
+    const Slab s = make_slab(p.scratch + (size_t)blockIdx.x * p.lay.bytes, p.lay);
+    const int cur = p.st->cur;
+
+    // measurements -> shared memory once per CTA, by the TMA engine (1-D bulk copy, mbarrier completion)
+    {
+        __shared__ __align__(8) unsigned long long bar;
+        const unsigned bytes = (unsigned)(sizeof(double) * 3 * p.M);
+        const bool bulk_ok = (bytes % 16 == 0) && bytes > 0 && ((reinterpret_cast<uintptr_t>(p.z) & 15) == 0);
+        if (bulk_ok) {
+            if (tid == 0) {
+                unsigned bar_a = (unsigned)__cvta_generic_to_shared(&bar);
+                unsigned dst_a = (unsigned)__cvta_generic_to_shared(sm.zs);
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a),
+                    "l"(p.z), "r"(bytes), "r"(bar_a)
+                    : "memory");
+            }
+            __syncthreads();
+            unsigned bar_a = (unsigned)__cvta_generic_to_shared(&bar);
+            unsigned done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done)
+                    : "r"(bar_a), "r"(0u)
+                    : "memory");
+            }
+        }
+        else {
+            for (int t = tid; t < 3 * p.M; t += kBlock) sm.zs[t] = p.z[t];
+        }
+        __syncthreads();
+    }
+
+    for (int particle = p.first + blockIdx.x; particle < p.first + p.P; particle += gridDim.x) {
+        const double* in = p.maps[cur] + (size_t)particle * kFields * p.cap;
+        double* out = p.maps[1 - cur] + (size_t)particle * kFields * p.cap;
+        if (tid == 0) {
+            Ctx& c = sm.ctx;
+            c.N = min(p.counts[cur][particle], p.cap);
+            c.B = 0; c.Npred = c.N; c.npairs = 0; c.npairs_prior = 0; c.L = c.N; c.ncand = 0; c.W0 = 0;
+            c.nedges = 0; c.nout = 0; c.nF = 0; c.status = 0;
+            for (int a = 0; a < 7; a++) c.pose[a] = p.poses[(size_t)particle * 7 + a];
+        }
+        __syncthreads();
+
+        if (p.mode == MODE_STAGE_PRUNE) {
+            // the given map IS the list to prune
+            const int N = sm.ctx.N, capp = p.lay.cap_pred;
+            for (int i = tid; i < N; i += kBlock) {
+                s.pwt[i] = mfield(in, p.cap, 0)[i];
+                s.pwmd[i] = s.pwt[i];
+                s.pm[i] = mfield(in, p.cap, 1)[i]; s.pm[capp + i] = mfield(in, p.cap, 2)[i];
+                s.pm[2 * capp + i] = mfield(in, p.cap, 3)[i];
+            }
+            __syncthreads();
+        }
+        else if (p.mode == MODE_STAGE_WEIGHT || p.mode == MODE_STAGE_SETLL) {
+            const int N = sm.ctx.N, capp = p.lay.cap_pred;
+            for (int i = tid; i < N; i += kBlock) {
+                s.pwt[i] = mfield(in, p.cap, 0)[i];
+                s.pm[i] = mfield(in, p.cap, 1)[i]; s.pm[capp + i] = mfield(in, p.cap, 2)[i];
+                s.pm[2 * capp + i] = mfield(in, p.cap, 3)[i];
+            }
+            __syncthreads();
+        }
+        else {
+            phase_predict_correct(p, sm, s, in, particle);
+        }
+
+        if (p.mode == MODE_STAGE_PREDICT) {
+            const int Npred = sm.ctx.Npred;
+            for (int i = tid; i < Npred; i += kBlock) {
+                double w, m[3], P[9];
+                load_pred(p, s, in, sm.ctx.N, i, w, m, P);
+                dump_comp(p, i, w, m, P);
+            }
+            if (tid == 0) *p.dump_count = Npred;
+        }
+        else if (p.mode == MODE_STAGE_CORRECT) {
+            const int L = sm.ctx.L;
+            for (int e = tid; e < L; e += kBlock) {
+                double w, m[3], P[9];
+                load_corrected(p, sm, s, in, e, w, m, P);
+                dump_comp(p, e, w, m, P);
+            }
+            if (tid == 0) *p.dump_count = L;
+        }
+        else if (p.mode == MODE_FRAME || p.mode == MODE_STAGE_PRUNE) {
+            phase_prune(p, sm, s, in, out);
+            if (tid == 0) p.counts[1 - cur][particle] = sm.ctx.nout;
+            if (p.mode == MODE_FRAME && !p.only_mapping) {
+                double parts[8];
+                double alpha = phase_weight(p, sm, s, in, sm.ctx.N, out, sm.ctx.nout, parts);
+                if (tid == 0) {
+                    p.alphas[particle] = alpha;
+                    p.weights[particle] *= alpha;
+                    if (p.alpha_parts)
+                        for (int a = 0; a < 8; a++) p.alpha_parts[(size_t)particle * 8 + a] = parts[a];
+                }
+            }
+        }
+        else if (p.mode == MODE_STAGE_WEIGHT) {
+            // buffer cur = predicted map, buffer 1-cur = corrected (pruned) map of the same particle slot
+            double parts[8];
+            int nc = min(p.counts[1 - cur][particle], p.cap);
+            double alpha = phase_weight(p, sm, s, in, sm.ctx.N, out, nc, parts);
+            if (tid == 0) {
+                p.alphas[particle] = alpha;
+                if (p.alpha_parts)
+                    for (int a = 0; a < 8; a++) p.alpha_parts[(size_t)particle * 8 + a] = parts[a];
+            }
+        }
+        else if (p.mode == MODE_STAGE_SETLL) {
+            // landmark list = the means of the map in buffer cur
+            const int J = sm.ctx.N, capj = p.lay.cap_j, capp = p.lay.cap_pred;
+            for (int t = tid; t < J && t < capj; t += kBlock) {
+                s.jm[t] = s.pm[t]; s.jm[capj + t] = s.pm[capp + t]; s.jm[2 * capj + t] = s.pm[2 * capp + t];
+            }
+            __syncthreads();
+            double ll = phase_set_loglikelihood(p, sm, s, min(J, capj));
+            if (tid == 0) p.alphas[particle] = ll;
+        }
+        __syncthreads();
+        if (tid == 0 && sm.ctx.status) atomicOr(&p.st->status, sm.ctx.status);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// particle prediction (PHD:295-314): pose <- pose (+) reading, then (+) dt * C g   (TRK:89-102)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_predict_pose(DevCfg cfg, int P, double* poses, Reading6 reading, double dt,
+                               const double* gauss, int perfect_still)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    double rd[6];
+    bool zero = true;
+    for (int a = 0; a < 6; a++) { rd[a] = reading.v[a]; if (rd[a] != 0) zero = false; }
+    Pose pose = add_odometry(pose_load(poses + (size_t)i * 7), rd);
+    if (!(perfect_still && zero)) {
+        double noise[6];
+        for (int a = 0; a < 6; a++) {
+            double sum = 0;
+            for (int k = 0; k < 6; k++) sum += cfg.chol[a * 6 + k] * gauss[(size_t)i * 6 + k];
+            noise[a] = dt * (0.0 + sum);
+        }
+        pose = add_odometry(pose, noise);
+    }
+    pose_store(pose, poses + (size_t)i * 7);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-frame grids over the measurements (particle independent):
+//   vgrid: back-projected points alpha*(px,py,f) in the CAMERA frame (rigid image of MeasureToMap),
+//          cell >= gate radius, used to find the measurements within 0.5 m of a component
+//   zgrid: the measurements themselves in (px,py,range) space, cell >= 5 sigma per axis, used by the
+//          d < 5 Mahalanobis gate of SetLogLikeMatrix (PHD:435-436)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_frame_prep(DevCfg cfg, const double* z, int M, FrameGrid* vg,
+                                                       int* vitems, FrameGrid* zg, int* zitems, double* pts)
+{
+    __shared__ BlockShared sh;
+    const int Mc = M > 0 ? M : 1;
+    for (int k = threadIdx.x; k < M; k += kBlock) {
+        double v[3];
+        measure_to_camera(cfg, z + 3 * k, v);
+        pts[k] = v[0]; pts[Mc + k] = v[1]; pts[2 * Mc + k] = v[2];
+        pts[3 * Mc + k] = z[3 * k]; pts[4 * Mc + k] = z[3 * k + 1]; pts[5 * Mc + k] = z[3 * k + 2];
+    }
+    __syncthreads();
+    double gr = cfg.gate_r;
+    if (!(gr > 0) || isinf(gr)) gr = 0.5;
+    grid_build(sh, vg->g, vg->start, vitems, pts, pts + Mc, pts + 2 * Mc, M, gr, gr, gr);
+    grid_build(sh, zg->g, zg->start, zitems, pts + 3 * Mc, pts + 4 * Mc, pts + 5 * Mc, M,
+               5.0 * sqrt(cfg.R[0]), 5.0 * sqrt(cfg.R[4]), 5.0 * sqrt(cfg.R[8]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight normalisation, best particle, ESS test, systematic wheel (PHD:343-358, 724-777).
+// One CTA.  The reference's sums and the wheel are running floating-point recurrences; they are
+// replayed serially by thread 0 (tiles staged through shared memory) so that ancestors are bit-exact.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTile = 4096;
+
+__global__ void __launch_bounds__(kBlock) k_normalize_resample(DevCfg cfg, int P, double* weights, double u,
+                                                              int force, int* ancestors, DeviceState* st)
+{
+    __shared__ double tile[kTile];
+    __shared__ double s_sum, s_cum;
+    __shared__ int s_best, s_dep;
+    __shared__ double s_maxw[kWarps];
+    __shared__ int s_maxi[kWarps];
+    const int tid = threadIdx.x;
+
+    if (force != 2) {
+        // sum (serial order)
+        if (tid == 0) s_sum = 0;
+        for (int base = 0; base < P; base += kTile) {
+            int n = min(kTile, P - base);
+            for (int i = tid; i < n; i += kBlock) tile[i] = weights[base + i];
+            __syncthreads();
+            if (tid == 0) { double sacc = s_sum; for (int i = 0; i < n; i++) sacc += tile[i]; s_sum = sacc; }
+            __syncthreads();
+        }
+        double sum = s_sum;
+        sum = (sum == 0) ? 1 : sum;
+        // normalise, first-maximum argmax (strict >, starting from 0: PHD:347-354)
+        double bw = 0; int bi = 0x7fffffff;
+        for (int i = tid; i < P; i += kBlock) {
+            double w = weights[i] / sum;
+            weights[i] = w;
+            if (w > bw) { bw = w; bi = i; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            double ow = __shfl_down_sync(0xffffffffu, bw, o);
+            int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (ow > bw || (ow == bw && oi < bi)) { bw = ow; bi = oi; }
+        }
+        if ((tid & 31) == 0) { s_maxw[tid >> 5] = bw; s_maxi[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < kWarps; w++)
+                if (s_maxw[w] > bw || (s_maxw[w] == bw && s_maxi[w] < bi)) { bw = s_maxw[w]; bi = s_maxi[w]; }
+            s_best = (bw > 0 && bi != 0x7fffffff) ? bi : st->best;
+            s_cum = 0;
+        }
+        __syncthreads();
+        // ESS (PHD:768-777)
+        for (int base = 0; base < P; base += kTile) {
+            int n = min(kTile, P - base);
+            for (int i = tid; i < n; i += kBlock) tile[i] = weights[base + i];
+            __syncthreads();
+            if (tid == 0) { double cacc = s_cum; for (int i = 0; i < n; i++) cacc += tile[i] * tile[i]; s_cum = cacc; }
+            __syncthreads();
+        }
+        if (tid == 0) s_dep = ((1.0 / s_cum < cfg.min_eff * P) || force) ? 1 : 0;
+        __syncthreads();
+    }
+    else {
+        if (tid == 0) { s_best = st->best; s_dep = 1; }
+        __syncthreads();
+    }
+    const int dep = s_dep;
+    if (!dep) {
+        for (int i = tid; i < P; i += kBlock) ancestors[i] = i;
+        if (tid == 0) { st->best = s_best; st->resampled = 0; st->depleted = 0; st->cur = 1 - st->cur; }
+        return;
+    }
+    // systematic wheel (PHD:724-760), serial
+    __shared__ double s_random, s_maxweight;
+    __shared__ int s_k, s_i, s_newbest, s_tilebase;
+    if (tid == 0) { s_random = u / P; s_maxweight = 0; s_k = 0; s_i = 0; s_newbest = s_best; }
+    __syncthreads();
+    // walk the weight tiles; for each tile thread 0 advances the wheel as far as the tile allows
+    for (int base = 0; base < P; base += kTile) {
+        int n = min(kTile, P - base);
+        for (int i = tid; i < n; i += kBlock) tile[i] = weights[base + i];
+        __syncthreads();
+        if (tid == 0) {
+            double random = s_random, maxweight = s_maxweight;
+            int k = s_k, i = s_i, nb = s_newbest;
+            const double invP = 1.0 / P;
+            const bool last_tile = (base + n >= P);
+            while (i < P) {
+                // inner loop of PHD:736: consume weights while random > 0
+                while (random > 0 && k < base + n) { random -= tile[k - base]; k++; }
+                if (random > 0 && k < P && !last_tile) break;   // need the next tile
+                int a = (k == 0) ? 0 : k - 1;
+                ancestors[i] = a;
+                double wa = (a >= base) ? tile[a - base] : weights[a];
+                random += invP;
+                if (wa > maxweight) { maxweight = wa; nb = i; }
+                i++;
+            }
+            s_random = random; s_maxweight = maxweight; s_k = k; s_i = i; s_newbest = nb;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    for (int i = tid; i < P; i += kBlock) weights[i] = 1.0 / P;
+    if (tid == 0) { st->best = s_newbest; st->resampled = 1; st->depleted = 1; }
+    (void)s_tilebase;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-side particle copy after resampling (PHD:740-742): new particle i <- ancestor's map and pose.
+// Runs every SLAM frame; exits at once when the frame did not resample.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_copy_particles(int P, int cap, double* map0, double* map1, int* cnt0,
+                                                          int* cnt1, const double* poses, double* poses_tmp,
+                                                          const int* ancestors, const DeviceState* st)
+{
+    if (!st->resampled) return;
+    const int cur = st->cur;
+    const double* src_maps = cur ? map0 : map1;   // posterior was written to buffer 1-cur
+    double* dst_maps = cur ? map1 : map0;
+    const int* src_cnt = cur ? cnt0 : cnt1;
+    int* dst_cnt = cur ? cnt1 : cnt0;
+    for (int i = blockIdx.x; i < P; i += gridDim.x) {
+        const int a = ancestors[i];
+        const int n = src_cnt[a];
+        const double* src = src_maps + (size_t)a * kFields * cap;
+        double* dst = dst_maps + (size_t)i * kFields * cap;
+        for (int f = 0; f < kFields; f++) {
+            const double2* s2 = reinterpret_cast<const double2*>(src + (size_t)f * cap);
+            double2* d2 = reinterpret_cast<double2*>(dst + (size_t)f * cap);
+            for (int t = threadIdx.x; t < (n + 1) / 2; t += kBlock) d2[t] = s2[t];
+        }
+        if (threadIdx.x == 0) dst_cnt[i] = n;
+        if (threadIdx.x < 7) poses_tmp[(size_t)i * 7 + threadIdx.x] = poses[(size_t)a * 7 + threadIdx.x];
+    }
+}
+
+__global__ void k_commit_poses(int P, double* poses, const double* poses_tmp, const DeviceState* st)
+{
+    if (!st->resampled) return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P * 7) poses[i] = poses_tmp[i];
+}
+
+__global__ void k_flip(DeviceState* st) { st->cur = 1 - st->cur; st->resampled = 0; }
+
+// ------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------
+void launch_predict_pose(cudaStream_t s, const DevCfg& cfg, int P, double* poses, Reading6 reading, double dt,
+                         const double* gauss, int perfect_still)
+{
+    k_predict_pose<<<(P + 127) / 128, 128, 0, s>>>(cfg, P, poses, reading, dt, gauss, perfect_still);
+}
+
+void launch_frame_prep(cudaStream_t s, const DevCfg& cfg, const double* z, int M, FrameGrid* vg, int* vitems,
+                       FrameGrid* zg, int* zitems, double* pts)
+{
+    k_frame_prep<<<1, kBlock, 0, s>>>(cfg, z, M, vg, vitems, zg, zitems, pts);
+}
+
+size_t particle_update_smem(int max_measurements, size_t* sort_cap)
+{
+    const int Mc = (max_measurements + 1) & ~1;
+    size_t cap = 4096;
+    if (sort_cap) *sort_cap = cap;
+    size_t off = (sizeof(Smem) + 15) & ~size_t(15);
+    off += sizeof(double) * 3 * (Mc > 0 ? Mc : 2) * 2;
+    off += (sizeof(unsigned long long) + sizeof(unsigned int)) * cap;
+    off += sizeof(int) * (Mc + 2) * 2;
+    off += sizeof(int) * (kGridMaxCells + 1);
+    return (off + 15) & ~size_t(15);
+}
+
+int particle_update_max_ctas_per_sm(size_t smem)
+{
+    cudaFuncSetAttribute(k_particle_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_particle_update, kBlock, smem);
+    return n;
+}
+
+void launch_particle_update(cudaStream_t s, const KParams& prm, int grid, size_t smem)
+{
+    k_particle_update<<<grid, kBlock, smem, s>>>(prm);
+}
+
+void launch_normalize_resample(cudaStream_t s, const DevCfg& cfg, int P, double* weights, double u, int force,
+                               int* ancestors, DeviceState* st)
+{
+    k_normalize_resample<<<1, kBlock, 0, s>>>(cfg, P, weights, u, force, ancestors, st);
+}
+
+void launch_copy_particles(cudaStream_t s, int P, int cap, double* const maps[2], int* const counts[2],
+                           double* poses, double* poses_tmp, const int* ancestors, DeviceState* st)
+{
+    int grid = P < 148 * 8 ? P : 148 * 8;
+    if (grid < 1) grid = 1;
+    k_copy_particles<<<grid, kBlock, 0, s>>>(P, cap, maps[0], maps[1], counts[0], counts[1], poses, poses_tmp,
+                                             ancestors, st);
+    k_commit_poses<<<(P * 7 + 255) / 256, 256, 0, s>>>(P, poses, poses_tmp, st);
+}
+
+void launch_flip(cudaStream_t s, DeviceState* st) { k_flip<<<1, 1, 0, s>>>(st); }
+
+}  // namespace rbphd

@@ -1,0 +1,392 @@
+// rbphd_weight.cuh -- WeightAlpha (PHD:373-393) for one particle, CTA-wide:
+//   BestMapEstimate (MAP:119-142), Map.Evaluate over the predicted and corrected maps (MAP:192-202),
+//   SetLogLikeMatrix / SetLogLikelihood (PHD:415-515) with connected components (GC:358-425),
+//   exhaustive lexicographic pairing (GC:280-350) and log-sum-exp (MX:361-389).
+// Included by rbphd_kernels.cu (needs Smem / Slab / KParams).
+#pragma once
+
+namespace rbphd {
+
+// Terms of Map.Evaluate with Mahalanobis distance^2 above this are < 2e-22 of the component's peak and
+// are skipped (the reference sums them; the parity bar for weights is 1e-9 relative).
+constexpr double kEvalD2 = 100.0;
+constexpr double kTightRadius = 0.6;
+constexpr double kFatRadius = 2.0;
+
+struct CompSrc {
+    const double* w;
+    const double* mx; const double* my; const double* mz;
+    const double* cov;     // field-major covariance (a * covstride + i), valid for i < ncov
+    size_t covstride;
+    int ncov;
+    const double* defcov;  // covariance of components i >= ncov (births)
+    int n;
+};
+
+__device__ __forceinline__ void comp_cov(const CompSrc& c, int i, double* P)
+{
+    if (i < c.ncov) {
+#pragma unroll
+        for (int a = 0; a < 9; a++) P[a] = c.cov[(size_t)a * c.covstride + i];
+    }
+    else {
+#pragma unroll
+        for (int a = 0; a < 9; a++) P[a] = c.defcov[a];
+    }
+}
+
+__device__ __forceinline__ double eval_term(const KParams& p, const Slab& s, const CompSrc& c, int i, double x,
+                                            double y, double z)
+{
+    const int st = p.lay.cap_pred;
+    double Pinv[9];
+#pragma unroll
+    for (int a = 0; a < 9; a++) Pinv[a] = s.cinv[(size_t)a * st + i];
+    double d[3] = {x - c.mx[i], y - c.my[i], z - c.mz[i]};
+    return c.w[i] * (s.cnorm[i] * exp(-0.5 * quadform3(Pinv, d)));
+}
+
+// v[t] = sum_i w_i N(jm_t; m_i, P_i) for the J points in s.jm.  Returns sum_t log v[t].
+__device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, const CompSrc& c, int J)
+{
+    const int tid = threadIdx.x, st = p.lay.cap_pred, capj = p.lay.cap_j;
+    // per-component cache: inverse covariance, multiplier, squared influence radius, class
+    for (int i = tid; i < c.n; i += kBlock) {
+        double P[9], Pinv[9];
+        comp_cov(c, i, P);
+        double det = mat3_inv(P, Pinv);
+#pragma unroll
+        for (int a = 0; a < 9; a++) s.cinv[(size_t)a * st + i] = Pinv[a];
+        s.cnorm[i] = gauss_mult(det);
+        double tr = P[0] + P[4] + P[8];
+        double r2 = kEvalD2 * tr * (1.0 + 1e-9);
+        if (!(r2 >= 0)) r2 = INFINITY;   // NaN / negative trace: never cull
+        s.crad[i] = r2;
+        s.fat[i] = (r2 <= kTightRadius * kTightRadius) ? 0 : ((r2 <= kFatRadius * kFatRadius) ? 1 : 2);
+    }
+    for (int t = tid; t < J; t += kBlock) s.vsum[t] = 0.0;
+    __syncthreads();
+
+    const double* jx = s.jm; const double* jy = s.jm + capj; const double* jz = s.jm + 2 * capj;
+    for (int cls = 0; cls < 3; cls++) {
+        // index-ordered list of this class
+        for (int i = tid; i < c.n; i += kBlock) s.nflag[i] = (s.fat[i] == cls) ? 1 : 0;
+        __syncthreads();
+        int ncl = block_scan_array(sm.sh, s.nflag, c.n);
+        for (int i = tid; i < c.n; i += kBlock) {
+            if (s.fat[i] == cls) {
+                int o = s.nflag[i];
+                s.clist[o] = i;
+                s.gx[o] = c.mx[i]; s.gx[st + o] = c.my[i]; s.gx[2 * st + o] = c.mz[i];
+            }
+        }
+        __syncthreads();
+        if (ncl == 0) continue;
+        if (cls < 2) {
+            const double cell = (cls == 0) ? kTightRadius : kFatRadius;
+            grid_build(sm.sh, sm.ctx.grid, sm.gstart, s.gitems, s.gx, s.gx + st, s.gx + 2 * st, ncl, cell, cell, cell);
+            const CellGrid& g = sm.ctx.grid;
+            for (int t = tid; t < J; t += kBlock) {
+                const double x = jx[t], y = jy[t], z = jz[t];
+                int lo[3], hi[3];
+                if (!grid_range(g, x, y, z, cell, lo, hi)) continue;
+                double v = s.vsum[t];
+                for (int cz = lo[2]; cz <= hi[2]; cz++)
+                    for (int cy = lo[1]; cy <= hi[1]; cy++) {
+                        int rowc = (cz * g.dim[1] + cy) * g.dim[0];
+                        int b = sm.gstart[rowc + lo[0]], e = sm.gstart[rowc + hi[0] + 1];
+                        for (int q = b; q < e; q++) {
+                            int i = s.clist[s.gitems[q]];
+                            double dx = x - c.mx[i], dy = y - c.my[i], dz = z - c.mz[i];
+                            if (dx * dx + dy * dy + dz * dz <= s.crad[i]) v += eval_term(p, s, c, i, x, y, z);
+                        }
+                    }
+                s.vsum[t] = v;
+            }
+        }
+        else {
+            for (int t = tid; t < J; t += kBlock) {
+                const double x = jx[t], y = jy[t], z = jz[t];
+                double v = s.vsum[t];
+                for (int q = 0; q < ncl; q++) {
+                    int i = s.clist[q];
+                    double dx = x - c.mx[i], dy = y - c.my[i], dz = z - c.mz[i];
+                    if (dx * dx + dy * dy + dz * dz <= s.crad[i]) v += eval_term(p, s, c, i, x, y, z);
+                }
+                s.vsum[t] = v;
+            }
+        }
+        __syncthreads();
+    }
+    // nothing nearby at all: the reference's full sum decides between a denormal and log(0) = -inf
+    double lsum = 0;
+    for (int t = tid; t < J; t += kBlock) {
+        double v = s.vsum[t];
+        if (!(v > 0)) {
+            v = 0;
+            for (int i = 0; i < c.n; i++) v += eval_term(p, s, c, i, jx[t], jy[t], jz[t]);
+        }
+        lsum += log(v);
+    }
+    double tot = block_sum(sm.sh, lsum);
+    __syncthreads();
+    return tot;
+}
+
+// MX:361-389
+__device__ __forceinline__ double log_sum_exp(const double* v, int n)
+{
+    double mx = -INFINITY, value = 0;
+    for (int i = 0; i < n; i++) mx = fmax(mx, v[i]);
+    if (isinf(mx) && mx < 0) return -INFINITY;
+    for (int i = 0; i < n; i++) value += exp(v[i] - mx);
+    return mx + log(value);
+}
+
+// GC:280-350 on a dense n x n block (n <= 5), values pushed to vals (at most 200: PHD:469,503)
+__device__ inline int lexicographical_values(const double* Mx, int n, int modelsize, double* vals)
+{
+    int perm[5];
+    for (int i = 0; i < n; i++) perm[i] = i;
+    int ms = n;
+    for (int i = 0; i < n; i++) if (perm[i] >= modelsize) { ms = i; break; }
+    auto reverse = [&](int from, int to) {   // [from, to)
+        for (int a = from, b = to - 1; a < b; a++, b--) { int t = perm[a]; perm[a] = perm[b]; perm[b] = t; }
+    };
+    auto value = [&]() {
+        double total = 0;
+        for (int i = 0; i < n; i++) total += Mx[i * 5 + perm[i]];
+        return total;
+    };
+    auto last = [&]() {
+        for (int i = 1; i < n; i++) if (perm[i - 1] < perm[i]) return false;
+        return true;
+    };
+    int m = 0;
+    reverse(ms, n);
+    vals[m++] = value();
+    while (!last() && m < 200) {
+        int a, b;
+        for (a = n - 2; a > 0; a--) if (perm[a] < perm[a + 1]) break;
+        for (b = n - 1; b > a; b--) if (perm[a] < perm[b]) break;
+        int t = perm[a]; perm[a] = perm[b]; perm[b] = t;
+        reverse(a + 1, n);
+        reverse(ms, n);
+        vals[m++] = value();
+    }
+    return m;
+}
+
+__device__ __forceinline__ bool grid_range3(const CellGrid& g, const double* q, const double* r, int* lo, int* hi)
+{
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        if (!(q[a] + r[a] >= g.org[a]) || !(q[a] - r[a] <= g.hi[a])) return false;
+        lo[a] = grid_coord(g, a, q[a] - r[a]);
+        hi[a] = grid_coord(g, a, q[a] + r[a]);
+    }
+    return true;
+}
+
+// SetLogLikelihood (PHD:462-515) for the J landmarks in s.jm
+__device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab& s, int J)
+{
+    const DevCfg& c = p.cfg;
+    const int tid = threadIdx.x, M = p.M, capj = p.lay.cap_j, capll = p.lay.cap_ll;
+    const Pose pose = pose_load(sm.ctx.pose);
+    const double* jx = s.jm; const double* jy = s.jm + capj; const double* jz = s.jm + 2 * capj;
+    int* deg = s.bcnt;           // J + M
+    int* label = s.uf;           // J + M
+    __shared__ int s_nll, s_changed;
+    if (tid == 0) s_nll = 0;
+    for (int t = tid; t < J + M; t += kBlock) { deg[t] = 0; label[t] = t; }
+    __syncthreads();
+
+    // PHD:426-442: predicted measurement and detection probability per landmark, then the d < 5 gate
+    const CellGrid& zg = p.zgrid->g;
+    const double rad[3] = {5.0 * sqrt(c.R[0]) * (1 + 1e-9), 5.0 * sqrt(c.R[4]) * (1 + 1e-9),
+                           5.0 * sqrt(c.R[8]) * (1 + 1e-9)};
+    for (int t = tid; t < J; t += kBlock) {
+        double m[3] = {jx[t], jy[t], jz[t]}, diff[3], mp[3];
+        Quat local;
+        to_local(pose, m, diff, local);
+        measure_from_local(c, diff, local, mp);
+        double pdt = detection_probability(c, mp);
+        s.jpd[t] = pdt;
+        s.jmp[t] = mp[0]; s.jmp[capj + t] = mp[1]; s.jmp[2 * capj + t] = mp[2];
+        int lo[3], hi[3];
+        if (M == 0 || !(mp[0] == mp[0]) || !grid_range3(zg, mp, rad, lo, hi)) continue;
+        const double lw = log(pdt);
+        for (int cz = lo[2]; cz <= hi[2]; cz++)
+            for (int cy = lo[1]; cy <= hi[1]; cy++) {
+                int rowc = (cz * zg.dim[1] + cy) * zg.dim[0];
+                int b = __ldg(&p.zgrid->start[rowc + lo[0]]), e = __ldg(&p.zgrid->start[rowc + hi[0] + 1]);
+                for (int q = b; q < e; q++) {
+                    int k = __ldg(&p.zitems[q]);
+                    double d3[3] = {mp[0] - sm.zs[3 * k], mp[1] - sm.zs[3 * k + 1], mp[2] - sm.zs[3 * k + 2]};
+                    double d = sqrt(quadform3(c.Rinv, d3));
+                    if (d < 5) {
+                        int idx = atomicAdd(&s_nll, 1);
+                        if (idx < capll) {
+                            s.llkey[idx] = ((unsigned long long)t << 32) | (unsigned)k;
+                            s.llval[idx] = lw + c.logmultR - 0.5 * d * d;
+                        }
+                        atomicAdd(&deg[t], 1);
+                        atomicAdd(&deg[J + k], 1);
+                    }
+                }
+            }
+    }
+    __syncthreads();
+    if (tid == 0 && s_nll > capll) { s_nll = capll; sm.ctx.status |= ST_OVER_LL; }
+    __syncthreads();
+    const int nll = s_nll;
+
+    // GC:358-425: connected components by min-label propagation over the detection edges
+    for (int it = 0; it < J + M + 1; it++) {
+        if (tid == 0) s_changed = 0;
+        __syncthreads();
+        for (int e = tid; e < nll; e += kBlock) {
+            int t = (int)(s.llkey[e] >> 32), k = (int)(s.llkey[e] & 0xffffffffu);
+            int a = label[t], b = label[J + k];
+            if (a < b) { atomicMin(&label[J + k], a); s_changed = 1; }
+            else if (b < a) { atomicMin(&label[t], b); s_changed = 1; }
+        }
+        __syncthreads();
+        int ch = s_changed;
+        __syncthreads();
+        if (!ch) break;
+    }
+
+    // edges ordered by (component label, landmark, measurement)
+    const int n2 = next_pow2(nll > 1 ? nll : 1);
+    unsigned long long* skey = (n2 <= (int)p.smem_sort_cap) ? sm.skey : s.skey;
+    unsigned int* sval = (n2 <= (int)p.smem_sort_cap) ? sm.sval : s.sval;
+    for (int e = tid; e < n2; e += kBlock) {
+        if (e < nll) {
+            unsigned long long t = s.llkey[e] >> 32, k = s.llkey[e] & 0xffffffffu;
+            skey[e] = ((unsigned long long)label[t] << 40) | (t << 20) | k;
+            sval[e] = (unsigned)e;
+        }
+        else { skey[e] = ~0ull; sval[e] = ~0u; }
+    }
+    block_bitonic_sort(skey, sval, n2);
+
+    double contrib = 0;
+    // blocks with at least one detection edge: one thread per block (head = first edge of the label)
+    for (int e = tid; e < nll; e += kBlock) {
+        unsigned long long lab = skey[e] >> 40;
+        if (e > 0 && (skey[e - 1] >> 40) == lab) continue;
+        int end = e + 1;
+        while (end < nll && (skey[end] >> 40) == lab) end++;
+        int ts[5], ks[5], a = 0, b = 0;
+        bool big = false;
+        for (int q = e; q < end && !big; q++) {
+            int t = (int)((skey[q] >> 20) & 0xfffff), k = (int)(skey[q] & 0xfffff);
+            bool ft = false, fk = false;
+            for (int i = 0; i < a; i++) ft |= (ts[i] == t);
+            for (int i = 0; i < b; i++) fk |= (ks[i] == k);
+            if (!ft) { if (a + b >= 5) big = true; else ts[a++] = t; }
+            if (!fk && !big) {
+                if (a + b >= 5) big = true;
+                else { int i = b++; while (i > 0 && ks[i - 1] > k) { ks[i] = ks[i - 1]; i--; } ks[i] = k; }
+            }
+        }
+        if (big) { atomicOr(&sm.ctx.status, ST_OVER_BLOCK); continue; }
+        const int n = a + b;
+        double Mx[25], vals[200];
+        for (int r = 0; r < n; r++)
+            for (int cc = 0; cc < n; cc++) {
+                double v;
+                if (r < a) v = (cc >= b && cc - b == r) ? log(1 - s.jpd[ts[r]]) : -INFINITY;
+                else       v = (cc < b) ? ((cc == r - a) ? c.logclutter : -INFINITY) : 0.0;
+                Mx[r * 5 + cc] = v;
+            }
+        for (int q = e; q < end; q++) {
+            int t = (int)((skey[q] >> 20) & 0xfffff), k = (int)(skey[q] & 0xfffff);
+            int r = 0, cc = 0;
+            while (ts[r] != t) r++;
+            while (ks[cc] != k) cc++;
+            Mx[r * 5 + cc] = s.llval[sval[q]];
+        }
+        int m = lexicographical_values(Mx, n, J, vals);
+        contrib += log_sum_exp(vals, m);
+    }
+    // isolated landmarks (1x1 block: ln(1 - PD)) and isolated measurements (1x1 block: ln clutter)
+    for (int t = tid; t < J; t += kBlock) if (deg[t] == 0) contrib += log(1 - s.jpd[t]);
+    for (int k = tid; k < M; k += kBlock) if (deg[J + k] == 0) contrib += c.logclutter;
+    double total = block_sum(sm.sh, contrib);
+    __syncthreads();
+    return total;
+}
+
+__device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const double* predmap, int npriorcov,
+                               const double* corr, int ncorr, double* parts)
+{
+    const int tid = threadIdx.x, capp = p.lay.cap_pred, capj = p.lay.cap_j;
+    const int Npred = sm.ctx.Npred;
+
+    // MAP:61-71 ExpectedSize of both maps
+    double a = 0, b = 0;
+    for (int i = tid; i < Npred; i += kBlock) a += s.pwt[i];
+    for (int i = tid; i < ncorr; i += kBlock) b += mfield(corr, p.cap, 0)[i];
+    const double pcount = block_sum(sm.sh, a);
+    const double ccount = block_sum(sm.sh, b);
+    int size = (ccount > 0) ? ((ccount < 2.0e9) ? (int)ccount : 2000000000) : 0;
+
+    // MAP:119-142 BestMapEstimate: the `size` largest values of the multiset {w_i - j : j = 0,1,..},
+    // ties ordered (generation, index) -- what the reference's append-and-stable-re-sort produces
+    for (int i = tid; i < ncorr; i += kBlock) {
+        double w = mfield(corr, p.cap, 0)[i];
+        int g = 0;
+        if (w > 0) { double cw = ceil(w); g = (cw < (double)size) ? (int)cw : size; }
+        s.nflag[i] = g;
+    }
+    __syncthreads();
+    int total = block_scan_array(sm.sh, s.nflag, ncorr);
+    if (total > p.lay.cap_sort) { if (tid == 0) sm.ctx.status |= ST_OVER_JMAP; }
+    const int n2 = next_pow2(total > 1 ? total : 1);
+    unsigned long long* skey = (n2 <= (int)p.smem_sort_cap) ? sm.skey : s.skey;
+    unsigned int* sval = (n2 <= (int)p.smem_sort_cap) ? sm.sval : s.sval;
+    const int sortcap = (n2 <= (int)p.smem_sort_cap) ? (int)p.smem_sort_cap : p.lay.cap_sort;
+    for (int j = total + tid; j < n2 && j < sortcap; j += kBlock) { skey[j] = ~0ull; sval[j] = ~0u; }
+    for (int i = tid; i < ncorr; i += kBlock) {
+        double w = mfield(corr, p.cap, 0)[i];
+        int off = s.nflag[i];
+        int g = ((i + 1 < ncorr) ? s.nflag[i + 1] : total) - off;
+        for (int j = 0; j < g; j++) {
+            if (off + j < sortcap) {
+                skey[off + j] = weight_desc_key(w - (double)j);
+                sval[off + j] = (unsigned)j * (unsigned)p.cap + (unsigned)i;
+            }
+        }
+    }
+    if (n2 <= sortcap) block_bitonic_sort(skey, sval, n2);
+    else __syncthreads();
+    int J = min(size, total);
+    if (J > capj) { J = capj; if (tid == 0) sm.ctx.status |= ST_OVER_JMAP; }
+    for (int t = tid; t < J; t += kBlock) {
+        int i = (int)(sval[t] % (unsigned)p.cap);
+        s.jidx[t] = i;
+        s.jm[t] = mfield(corr, p.cap, 1)[i]; s.jm[capj + t] = mfield(corr, p.cap, 2)[i];
+        s.jm[2 * capj + t] = mfield(corr, p.cap, 3)[i];
+    }
+    __syncthreads();
+
+    // PHD:381-384: sum_j ln v_pred(m_j), sum_j ln v_corr(m_j)
+    CompSrc pred{s.pwt, s.pm, s.pm + capp, s.pm + 2 * capp, mfield(predmap, p.cap, 4), (size_t)p.cap, npriorcov,
+                 p.cfg.birth_cov, Npred};
+    const double plog = eval_map_at_points(p, sm, s, pred, J);
+    CompSrc cor{mfield(corr, p.cap, 0), mfield(corr, p.cap, 1), mfield(corr, p.cap, 2), mfield(corr, p.cap, 3),
+                mfield(corr, p.cap, 4), (size_t)p.cap, ncorr, p.cfg.birth_cov, ncorr};
+    const double clog = eval_map_at_points(p, sm, s, cor, J);
+
+    const double setll = phase_set_loglikelihood(p, sm, s, J);
+    const double ratio = (plog - pcount) - (clog - ccount);
+    const double alpha = exp(setll + ratio);
+    parts[0] = alpha; parts[1] = setll; parts[2] = plog; parts[3] = clog; parts[4] = pcount; parts[5] = ccount;
+    parts[6] = (double)J; parts[7] = 0;
+    return alpha;
+}
+
+}  // namespace rbphd

@@ -1140,21 +1140,22 @@ void parallel_particles(orc_nav* nav, int first, int last, int M, const double* 
 int normalize_resample(const orc_config* c, int P, double* w, double u, int* best, int* ancestors,
                        int force)
 {
-    double sum = 0;
-    for (int i = 0; i < P; i++) sum += w[i];
-    sum = (sum == 0) ? 1 : sum;
-    for (int i = 0; i < P; i++) w[i] = w[i] / sum;
-
-    double maxweight = 0;
     int b = *best;
-    for (int i = 0; i < P; i++) if (w[i] > maxweight) { maxweight = w[i]; b = i; }
-
-    double cum = 0;
-    for (int i = 0; i < P; i++) cum += w[i] * w[i];
-    bool depleted = (1.0 / cum < c->min_effective_particle * P);
-
+    double maxweight = 0;
     for (int i = 0; i < P; i++) ancestors[i] = i;
-    if (!(depleted || force)) { *best = b; return 0; }
+    if (force != 2) {   /* force == 2: ResampleParticles() alone, weights taken as they are */
+        double sum = 0;
+        for (int i = 0; i < P; i++) sum += w[i];
+        sum = (sum == 0) ? 1 : sum;
+        for (int i = 0; i < P; i++) w[i] = w[i] / sum;
+
+        for (int i = 0; i < P; i++) if (w[i] > maxweight) { maxweight = w[i]; b = i; }
+
+        double cum = 0;
+        for (int i = 0; i < P; i++) cum += w[i] * w[i];
+        bool depleted = (1.0 / cum < c->min_effective_particle * P);
+        if (!(depleted || force)) { *best = b; return 0; }
+    }
 
     /* PHD:724-760 */
     double random = u / P;

@@ -1,0 +1,395 @@
+"""Parity of the CUDA path (through the C ABI of librbphd.so) against the CPU oracle.
+
+Bar: component counts, ancestors, best index and resampling decisions bit-exact;
+means / covariances / weights within 1e-9 relative (relative to the vector / matrix norm).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def capi():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from monorfs_b200 import capi as _capi
+    _capi.load()
+    return _capi
+
+
+@pytest.fixture(scope="module")
+def synth():
+    from monorfs_b200 import synth as _s
+    return _s
+
+
+def close_rel(a, b, rtol=RTOL):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    if a.shape != b.shape:
+        return False
+    scale = max(np.max(np.abs(b)) if b.size else 0.0, 1e-300)
+    both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
+    diff = np.where(both_inf, 0.0, np.abs(a - b))
+    return bool(np.all(diff <= rtol * scale))
+
+
+def assert_maps_equal(got, exp, what=""):
+    gw, gm, gP = got
+    ew, em, eP = exp
+    assert len(gw) == len(ew), f"{what}: component count {len(gw)} != {len(ew)}"
+    assert close_rel(gw, ew), f"{what}: weights differ, max abs {np.max(np.abs(gw - ew)):.3e}"
+    for i in range(len(ew)):
+        assert close_rel(gm[i], em[i]), f"{what}: mean {i}: {gm[i]} vs {em[i]}"
+        assert close_rel(gP[i], eP[i]), f"{what}: cov {i}"
+
+
+def small_scene(synth, P=8, N=40, M=16, seed=3, **over):
+    return synth.make_scene(P, N, M, seed=seed, **over)
+
+
+@pytest.fixture(scope="module")
+def ctx(capi, orc, synth):
+    sc = small_scene(synth)
+    h = capi.Handle(sc.params, max_particles=64, max_components=256, max_measurements=64, max_pairs=4096)
+    yield dict(h=h, sc=sc, ocfg=orc.make_config(sc.params))
+    h.close()
+
+
+# ------------------------------------------------------------------ per-particle stages
+def test_stage_predict(ctx, orc):
+    h, sc, ocfg = ctx["h"], ctx["sc"], ctx["ocfg"]
+    fr = sc.next_frame()
+    pose = sc.poses[1]
+    exp = orc.predict(ocfg, pose, sc.map_w, sc.map_m, sc.map_P, fr.z)
+    got = h.stage_predict(pose, sc.map_w, sc.map_m, sc.map_P, fr.z)
+    assert exp[3] > 0, "scene must produce births"
+    assert_maps_equal(got, exp[:3], "predict")
+
+
+def test_stage_predict_empty_map(ctx, orc):
+    """PHDNavigatorTest.PredictInitial (PHDNavigatorTest.cs:85-104) on the pixel-range model."""
+    h, sc, ocfg = ctx["h"], ctx["sc"], ctx["ocfg"]
+    pose = [0.1, -0.2, 0.05, 1, 0, 0, 0]
+    z = [[10.0, -20.0, 2.5]]
+    got = h.stage_predict(pose, np.zeros(0), np.zeros((0, 3)), np.zeros((0, 3, 3)), z)
+    exp = orc.predict(ocfg, pose, np.zeros(0), np.zeros((0, 3)), np.zeros((0, 3, 3)), z)
+    assert len(got[0]) == 1
+    assert_maps_equal(got, exp[:3], "predict-empty")
+    assert close_rel(got[1][0], orc.measure_to_map(ocfg, pose, z[0]))
+    assert np.allclose(got[2][0], np.eye(3) * 1e-2) and got[0][0] == 0.05
+
+
+def test_stage_predict_known(ctx, orc):
+    """PHDNavigatorTest.PredictKnown (PHDNavigatorTest.cs:106-126): an explored point gives no birth."""
+    h, ocfg = ctx["h"], ctx["ocfg"]
+    pose = [0, 0, 0, 1, 0, 0, 0]
+    z = [[10.0, -20.0, 2.5]]
+    c = orc.measure_to_map(ocfg, pose, z[0])
+    got = h.stage_predict(pose, [1.0], [c], [np.eye(3)], z)
+    assert len(got[0]) == 1 and got[0][0] == 1.0
+
+
+def test_stage_correct_gated_and_ungated(ctx, orc):
+    h, sc, ocfg = ctx["h"], ctx["sc"], ctx["ocfg"]
+    fr = sc.next_frame()
+    pose = sc.poses[2]
+    pw, pm, pP, _ = orc.predict(ocfg, pose, sc.map_w, sc.map_m, sc.map_P, fr.z)
+    exp = orc.correct(ocfg, pose, pw, pm, pP, fr.z)
+    got = h.stage_correct(pose, pw, pm, pP, fr.z)
+    assert len(exp[0]) > len(pw), "scene must produce detections"
+    assert_maps_equal(got, exp, "correct-gated")
+    # ungated form = what PHDNavigatorTest.Correct pins (PHDNavigatorTest.cs:128-193); small sizes
+    exp = orc.correct(ocfg, pose, pw[:6], pm[:6], pP[:6], fr.z[:5], gate_radius=-1.0)
+    got = h.stage_correct(pose, pw[:6], pm[:6], pP[:6], fr.z[:5], gate_radius=-1.0)
+    assert len(got[0]) == 6 + 6 * 5
+    assert_maps_equal(got, exp, "correct-ungated")
+
+
+def test_stage_prune_reference_case(ctx, orc):
+    """PHDNavigatorTest.Prune (PHDNavigatorTest.cs:195-265): 13 components -> 5."""
+    h, ocfg = ctx["h"], ctx["ocfg"]
+    I = np.eye(3)
+    mw, md = 1e-3, 0.3
+    comps = [([-12, -24, -54], I, 23.0), ([-80, -22, -12], 4.0 * I, 1.0), ([-63, -11, -95], 0.1 * I, 6.0),
+             ([12, 24, 54], I, 0.3 * mw), ([80, 22, 12], 4.0 * I, 0.8 * mw), ([63, 11, 95], 0.1 * I, 0.99 * mw),
+             ([23, 19, 73], I, 0.0),
+             ([0, 0, 0], I, 1.0), ([0, md, 0], I, 0.6), ([0, md / 2, 0], I, 1.2),
+             ([99 - md / 6, 99, 99], I, 0.9), ([99, 99 - md / 6, 99], I, 0.5), ([99, 99, 99 - md / 6], I, 1.1)]
+    w = [c[2] for c in comps]
+    m = [c[0] for c in comps]
+    P = [c[1] for c in comps]
+    exp = orc.prune(ocfg, w, m, P)
+    got = h.stage_prune(w, m, P)
+    assert len(got[0]) == 5
+    assert_maps_equal(got, exp, "prune-reference")
+
+
+def test_stage_prune_scene(ctx, orc):
+    h, sc, ocfg = ctx["h"], ctx["sc"], ctx["ocfg"]
+    fr = sc.next_frame()
+    pose = sc.poses[3]
+    pw, pm, pP, _ = orc.predict(ocfg, pose, sc.map_w, sc.map_m, sc.map_P, fr.z)
+    cw, cm, cP = orc.correct(ocfg, pose, pw, pm, pP, fr.z)
+    exp = orc.prune(ocfg, cw, cm, cP)
+    got = h.stage_prune(cw, cm, cP)
+    assert_maps_equal(got, exp, "prune-scene")
+    # idempotence on a pruned map whose components are not mutually close
+    again = h.stage_prune(*got)
+    exp2 = orc.prune(ocfg, *exp)
+    assert_maps_equal(again, exp2, "prune-twice")
+
+
+def test_stage_prune_ties_and_chains(ctx, orc):
+    """Equal weights (stable order) and a chain a~b~c where b is absorbed by a and c survives."""
+    h, ocfg = ctx["h"], ctx["ocfg"]
+    I = np.eye(3) * 1e-2
+    t = 0.3 * 0.1   # merge radius for cov 1e-2 I
+    m = [[0, 0, 0], [0.9 * t, 0, 0], [1.8 * t, 0, 0], [5, 5, 5], [5, 5, 5 + 0.5 * t], [9, 9, 9]]
+    w = [0.5, 0.5, 0.5, 0.2, 0.2, 0.2]
+    P = [I] * 6
+    exp = orc.prune(ocfg, w, m, P)
+    got = h.stage_prune(w, m, P)
+    assert_maps_equal(got, exp, "prune-ties")
+
+
+def test_stage_set_loglikelihood(ctx, orc):
+    h, sc, ocfg = ctx["h"], ctx["sc"], ctx["ocfg"]
+    fr = sc.next_frame()
+    pose = sc.poses[0]
+    for J in (0, 1, 7, len(sc.map_m)):
+        jm = sc.map_m[:J]
+        exp = orc.set_loglikelihood(ocfg, pose, jm, fr.z)
+        got = h.stage_set_loglikelihood(pose, jm, fr.z)
+        assert close_rel(got, exp), (J, got, exp)
+
+
+def test_stage_set_loglikelihood_shared_measurements(ctx, orc):
+    """Two landmarks competing for the same measurements: 4x4 blocks through the lexicographic lane."""
+    h, ocfg = ctx["h"], ctx["ocfg"]
+    pose = [0, 0, 0, 1, 0, 0, 0]
+    lm = np.array([[0.2, 0.1, 3.0], [0.21, 0.1, 3.0], [-1.0, 0.5, 5.0]])
+    z = np.array([orc.measure_perfect(ocfg, pose, l) for l in lm])
+    z = np.concatenate([z + [0.5, -0.5, 0.01], [[100.0, 100.0, 4.0]]])
+    exp = orc.set_loglikelihood(ocfg, pose, lm, z)
+    got = h.stage_set_loglikelihood(pose, lm, z)
+    assert close_rel(got, exp), (got, exp)
+
+
+def test_stage_weight_alpha(ctx, orc):
+    h, sc, ocfg = ctx["h"], ctx["sc"], ctx["ocfg"]
+    fr = sc.next_frame()
+    for pi in (0, 5):
+        pose = sc.poses[pi]
+        pw, pm, pP, _ = orc.predict(ocfg, pose, sc.map_w, sc.map_m, sc.map_P, fr.z)
+        cw, cm, cP = orc.correct(ocfg, pose, pw, pm, pP, fr.z)
+        qw, qm, qP = orc.prune(ocfg, cw, cm, cP)
+        exp = orc.weight_alpha(ocfg, pose, fr.z, (pw, pm, pP), (qw, qm, qP))
+        got = h.stage_weight_alpha(pose, fr.z, (pw, pm, pP), (qw, qm, qP))
+        assert got["J"] == exp["J"]
+        for k in ("pcount", "ccount", "ploglik", "cloglik", "setloglik"):
+            assert close_rel(got[k], exp[k]), (k, got[k], exp[k])
+        assert close_rel(np.log(got["alpha"]), np.log(exp["alpha"]), 1e-9), (got["alpha"], exp["alpha"])
+
+
+def test_best_map_estimate_heavy_weights(ctx, orc):
+    """Weights above 1 are picked repeatedly (MAP:131-138)."""
+    h, sc, ocfg = ctx["h"], ctx["sc"], ctx["ocfg"]
+    fr = sc.next_frame()
+    pose = sc.poses[0]
+    n = 12
+    w = np.array([2.5, 0.4, 1.5, 1.5, 0.9, 3.2, 0.05, 1.0, 0.3, 0.7, 2.5, 0.6])
+    pred = (w, sc.map_m[:n], sc.map_P[:n])
+    exp = orc.weight_alpha(ocfg, pose, fr.z, pred, pred)
+    got = h.stage_weight_alpha(pose, fr.z, pred, pred)
+    assert got["J"] == exp["J"] == int(w.sum())
+    for k in ("ploglik", "cloglik", "setloglik"):
+        assert close_rel(got[k], exp[k]), (k, got[k], exp[k])
+
+
+# ------------------------------------------------------------------ particle set
+def test_pose_update(ctx, orc):
+    h, sc = ctx["h"], ctx["sc"]
+    P = sc.P
+    h.reset(P, sc.poses[0], sc.map_w, sc.map_m, sc.map_P)
+    h.set_poses(sc.poses)
+    nav = orc.Navigator(ctx["ocfg"], P, sc.poses[0])
+    for i in range(P):
+        nav.set_pose(i, sc.poses[i])
+    rng = np.random.default_rng(5)
+    for _ in range(3):
+        g = rng.normal(size=(P, 6))
+        reading = [0.01, -0.02, 0.03, 0.004, -0.002, 0.001]
+        h.update(reading, 1 / 30.0, g)
+        nav.update(reading, 1 / 30.0, g)
+        assert np.allclose(h.get_poses(), nav.get_poses(), rtol=0, atol=1e-13)
+    # PerfectStill with a zero reading: no noise (TRK:94)
+    before = h.get_poses()
+    h.update([0] * 6, 1 / 30.0, rng.normal(size=(P, 6)), perfect_still=True)
+    nav.update([0] * 6, 1 / 30.0, rng.normal(size=(P, 6)), perfect_still=True)
+    assert np.allclose(h.get_poses(), nav.get_poses(), rtol=0, atol=1e-13)
+    assert np.allclose(h.get_poses(), before, rtol=0, atol=1e-12)
+
+
+def test_resample_reference_invariants(ctx, orc):
+    """SimulationTest.resample (SimulationTest.cs:225-270) through rbphd_resample."""
+    h, sc, ocfg = ctx["h"], ctx["sc"], ctx["ocfg"]
+    rng = np.random.default_rng(11)
+    seen0 = seen3 = 0
+    iters = 60
+    for it in range(iters):
+        h.reset(5, sc.poses[0], sc.map_w[:3], sc.map_m[:3], sc.map_P[:3])
+        poses = np.tile(np.array([0, 0, 0, 1, 0, 0, 0], float), (5, 1))
+        poses[:, 0] = np.arange(5)
+        h.set_poses(poses)
+        for i in range(5):
+            h.set_map(i, sc.map_w[:i + 1], sc.map_m[:i + 1], sc.map_P[:i + 1])
+        wts = [0.11, 0.28, 0.31, 0.01, 0.29]
+        h.set_weights(wts)
+        u = float(np.float32(rng.random()))
+        h.resample(u)
+        anc = h.get_ancestors()
+        _, ebest, eanc, _ = orc.normalize_resample(ocfg, wts, u, force=2)
+        assert anc.tolist() == eanc.tolist()
+        assert h.get_best() == ebest and anc[h.get_best()] == 2
+        assert {1, 2, 4} <= set(anc.tolist())
+        assert np.allclose(h.get_weights(), 0.2)
+        assert h.get_poses()[:, 0].tolist() == anc.astype(float).tolist()
+        assert h.get_map_counts().tolist() == (anc + 1).tolist()
+        seen0 += 0 in anc
+        seen3 += 3 in anc
+    assert seen0 < iters and seen3 < iters
+
+
+def run_both(capi, orc, synth, P, N, M, frames, seed, only_mapping=False, **over):
+    sc = synth.make_scene(P, N, M, seed=seed, **over)
+    ocfg = orc.make_config(sc.params)
+    h = capi.Handle(sc.params, max_particles=P, max_components=max(2 * N, 64), max_measurements=M,
+                    max_pairs=max(8 * M, 256))
+    nav = orc.Navigator(ocfg, P, sc.poses[0], only_mapping=only_mapping)
+    h.reset(P, sc.poses[0], sc.map_w, sc.map_m, sc.map_P)
+    h.set_poses(sc.poses)
+    for i in range(P):
+        nav.set_pose(i, sc.poses[i])
+        nav.set_map(i, sc.map_w, sc.map_m, sc.map_P)
+    nres = 0
+    for f in range(frames):
+        fr = sc.next_frame()
+        if only_mapping:
+            for i in range(P):
+                h.set_pose(i, fr.true_pose)
+                nav.set_pose(i, fr.true_pose)
+        else:
+            h.update(fr.reading, synth.DT, fr.gauss)
+            nav.update(fr.reading, synth.DT, fr.gauss)
+        gbest, gres = h.slam_update(fr.z, fr.u, only_mapping=only_mapping)
+        obest, ores, oanc = nav.slam_update(fr.z, fr.u)
+        tag = f"frame {f}"
+        assert gres == ores, tag
+        if not only_mapping:
+            with np.errstate(divide="ignore"):
+                assert close_rel(np.log(h.get_alphas()), np.log(nav.get_alphas()), 1e-9), tag
+            assert h.get_ancestors().tolist() == oanc.tolist(), tag
+            assert gbest == obest, tag
+            assert close_rel(h.get_weights(), nav.get_weights()), tag
+        assert np.allclose(h.get_poses(), nav.get_poses(), rtol=0, atol=1e-12), tag
+        counts = h.get_map_counts()
+        for i in range(P):
+            assert_maps_equal(h.get_map(i), nav.get_map(i), f"{tag} particle {i}")
+            assert counts[i] == len(nav.get_map(i)[0])
+        nres += int(gres)
+    h.close()
+    return nres
+
+
+def test_slam_frames_small(capi, orc, synth):
+    nres = run_both(capi, orc, synth, P=12, N=40, M=16, frames=8, seed=21)
+    assert nres >= 1, "the run must exercise resampling"
+
+
+def test_slam_frames_medium(capi, orc, synth):
+    run_both(capi, orc, synth, P=24, N=150, M=48, frames=5, seed=22, min_effective_particle=0.3)
+
+
+def test_mapping_only_frames(capi, orc, synth):
+    run_both(capi, orc, synth, P=3, N=80, M=30, frames=6, seed=23, only_mapping=True)
+
+
+def test_squared_gate_metric(capi, orc, synth):
+    """The Accord squared-Euclidean KD-tree hypothesis as a switch."""
+    run_both(capi, orc, synth, P=6, N=50, M=20, frames=3, seed=24, gate_metric=1)
+
+
+def test_empty_inputs(capi, orc, synth):
+    sc = small_scene(synth)
+    h = capi.Handle(sc.params, max_particles=4, max_components=128, max_measurements=32)
+    h.reset(4, sc.poses[0], np.zeros(0), np.zeros((0, 3)), np.zeros((0, 3, 3)))
+    best, res = h.slam_update(np.zeros((0, 3)), 0.5)          # empty map, no measurements
+    assert h.get_map_counts().tolist() == [0, 0, 0, 0]
+    fr = sc.next_frame()
+    h.slam_update(fr.z, 0.5)                                   # empty map, births only
+    nav = orc.Navigator(orc.make_config(sc.params), 4, sc.poses[0])
+    nav.slam_update(np.zeros((0, 3)), 0.5)
+    nav.slam_update(fr.z, 0.5)
+    for i in range(4):
+        assert_maps_equal(h.get_map(i), nav.get_map(i), f"empty particle {i}")
+    h.close()
+
+
+def test_capacity_error_is_loud(capi, synth):
+    sc = small_scene(synth, N=40)
+    h = capi.Handle(sc.params, max_particles=2, max_components=64, max_measurements=16, max_pairs=4)
+    h.reset(2, sc.poses[0], sc.map_w, sc.map_m, sc.map_P)
+    fr = sc.next_frame()
+    with pytest.raises(capi.RbphdError) as e:
+        h.slam_update(fr.z, 0.5)
+    assert e.value.code == capi.ERR_CAPACITY
+    h.close()
+
+
+def test_c2_shape_sampled_parity(capi, orc, synth):
+    """BASELINE config 2 shape (2000 particles x 500 components x 100 measurements): the map update of
+    the first particles against the oracle, WeightAlpha of one particle at that size, and
+    size-independent properties over all particles."""
+    P, N, M = 2000, 500, 100
+    sc = synth.make_scene(P, N, M, seed=31)
+    h = capi.Handle(sc.params, max_particles=P, max_components=2 * N, max_measurements=M)
+    h.reset(P, sc.poses[0], sc.map_w, sc.map_m, sc.map_P)
+    h.set_poses(sc.poses)
+    S = 5
+    ocfg = orc.make_config(sc.params)
+    nav = orc.Navigator(ocfg, S, sc.poses[0], only_mapping=True)
+    for i in range(S):
+        nav.set_pose(i, sc.poses[i])
+        nav.set_map(i, sc.map_w, sc.map_m, sc.map_P)
+    fr = sc.next_frame()
+    h.slam_update(fr.z, fr.u, only_mapping=True)
+    nav.slam_update(fr.z, fr.u)
+    counts = h.get_map_counts()
+    assert counts.min() > 0 and counts.max() <= sc.params["max_quantity"]
+    for i in range(S):
+        assert_maps_equal(h.get_map(i), nav.get_map(i), f"c2 particle {i}")
+    # WeightAlpha at this size through the stage entry point
+    pose = sc.poses[0]
+    pred = orc.predict(ocfg, pose, sc.map_w, sc.map_m, sc.map_P, fr.z)[:3]
+    corr = nav.get_map(0)
+    exp = orc.weight_alpha(ocfg, pose, fr.z, pred, corr)
+    got = h.stage_weight_alpha(pose, fr.z, pred, corr)
+    assert got["J"] == exp["J"] and exp["J"] > 100
+    for k in ("pcount", "ccount", "ploglik", "cloglik", "setloglik"):
+        assert close_rel(got[k], exp[k]), (k, got[k], exp[k])
+    # a full SLAM frame over all particles: weights normalised, ancestors a valid non-decreasing wheel
+    h.update(fr.reading, synth.DT, fr.gauss)
+    fr2 = sc.next_frame()
+    best, res = h.slam_update(fr2.z, fr2.u)
+    w = h.get_weights()
+    assert np.all(np.isfinite(w)) and abs(w.sum() - 1.0) < 1e-9
+    anc = h.get_ancestors()
+    assert np.all(np.diff(anc) >= 0) and 0 <= anc.min() and anc.max() < P
+    assert 0 <= best < P
+    if res:
+        assert np.allclose(w, 1.0 / P)
+    h.close()
