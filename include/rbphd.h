@@ -64,7 +64,8 @@ typedef struct rbphd_limits {
     int32_t max_components;      /* per-particle map capacity; default max(max_quantity, 64) rounded up */
     int32_t max_measurements;    /* per-frame measurement capacity; default 1024 */
     int32_t max_pairs;           /* gated (component, measurement) pairs per particle; default 4*max_measurements */
-    int32_t reserved[3];
+    int32_t resident_frames;     /* device slots for per-frame inputs (gauss, z); default 1 */
+    int32_t reserved[2];
 } rbphd_limits;
 
 typedef struct rbphd_navigator rbphd_navigator;
@@ -99,11 +100,15 @@ int rbphd_get_poses(rbphd_navigator* nav, const double** poses, int* particles);
  * best / resampled may be NULL. */
 int rbphd_slam_update(rbphd_navigator* nav, const double* z, int m, int only_mapping, double u_resample,
                       int* best, int* resampled);
-/* Same, but asynchronous: nothing is copied back and the host is not synchronised (device-resident
- * frame loop).  z_dev / gauss_dev are DEVICE pointers or NULL to reuse what was uploaded last. */
-int rbphd_frame_async(rbphd_navigator* nav, const double* reading6, double dt, int perfect_still,
+/* Device-resident frame loop: Update + SlamUpdate enqueued on the handle's stream with nothing copied
+ * back and no host synchronisation.  The frame's inputs (gauss: particles x 6, z: m x 3) are uploaded
+ * beforehand into input slot `slot` (0 <= slot < resident_frames); either pointer may be NULL to keep
+ * what the slot holds.  rbphd_synchronize() waits and reports deferred capacity errors. */
+int rbphd_upload_frame_inputs(rbphd_navigator* nav, int slot, const double* gauss, const double* z, int m);
+int rbphd_frame_async(rbphd_navigator* nav, int slot, const double* reading6, double dt, int perfect_still,
                       int m, int only_mapping, double u_resample);
-int rbphd_upload_frame_inputs(rbphd_navigator* nav, const double* gauss, const double* z, int m);
+/* Update alone, enqueued without synchronisation (gauss from input slot `slot`) */
+int rbphd_update_async(rbphd_navigator* nav, int slot, const double* reading6, double dt, int perfect_still);
 int rbphd_synchronize(rbphd_navigator* nav);
 
 /* ResampleParticles (PHD:724-760) / ParticleDepleted (PHD:768-777) as public methods */
@@ -145,8 +150,9 @@ int rbphd_stage_set_loglikelihood(rbphd_navigator* nav, const double* pose7, int
 
 /* ---- multi-GPU plumbing (particles sharded by rank).  The data-path
  * collectives themselves are issued by the host runtime on these DEVICE buffers. ---- */
-/* SlamUpdate split at the coupling point PHD:343: phase 1 = the Parallel.For body + w *= alpha */
-int rbphd_slam_update_local(rbphd_navigator* nav, int m, int only_mapping);
+/* SlamUpdate split at the coupling point PHD:343: phase 1 = the Parallel.For body + w *= alpha
+ * (inputs from slot `slot`, enqueued without synchronisation) */
+int rbphd_slam_update_local(rbphd_navigator* nav, int slot, int m, int only_mapping);
 /* device pointer to this rank's un-normalised weights (particles doubles) for the allgather */
 int rbphd_device_weights(rbphd_navigator* nav, void** dev_ptr, int* particles);
 /* phase 2: normalise / best / ESS / wheel over the GLOBAL weight vector (device pointer, all ranks'
@@ -154,7 +160,8 @@ int rbphd_device_weights(rbphd_navigator* nav, void** dev_ptr, int* particles);
 int rbphd_resample_global(rbphd_navigator* nav, const void* dev_global_weights, int global_particles,
                           int rank_offset, double u_resample, int* best_global, int* resampled,
                           const int** ancestors_global);
-/* pack / unpack one particle (pose + map) to a flat device record for migration */
+/* pack / unpack particles (pose + map) to flat device records of rbphd_particle_record_bytes() each */
+int64_t rbphd_particle_record_bytes(const rbphd_navigator* nav);
 int rbphd_pack_particles(rbphd_navigator* nav, const int* local_indices, int count, void** dev_buf,
                          int64_t* bytes);
 int rbphd_unpack_particles(rbphd_navigator* nav, const void* dev_buf, const int* slots, int count);
@@ -163,8 +170,18 @@ int rbphd_commit_resample_local(rbphd_navigator* nav, const int* local_sources, 
 /* ---- instrumentation ---- */
 /* number of kernel launches issued on this handle since creation */
 int64_t rbphd_kernel_launches(const rbphd_navigator* nav);
-/* device time (ms, CUDA events on the handle's stream) of each stage of the last frame */
-int rbphd_last_stage_ms(rbphd_navigator* nav, double* ms, int n);
+/* Per-stage device times: after rbphd_profile_enable(nav, max_frames) every rbphd_frame_async records
+ * CUDA events on the handle's stream around its kernels; rbphd_profile_read() (after a synchronise)
+ * returns, per recorded frame, RBPHD_STAGES durations in ms: pose, prep, particle_update,
+ * normalize_resample, copy_particles. */
+#define RBPHD_STAGES 5
+int rbphd_profile_enable(rbphd_navigator* nav, int max_frames);
+int rbphd_profile_read(rbphd_navigator* nav, double* ms, int max_frames, int* frames);
+/* device-side work counters since the last reset: prior components read, pruned components written,
+ * gated (component, measurement) pairs evaluated, particle-frames processed */
+int rbphd_get_counters(rbphd_navigator* nav, int64_t out4[4], int reset);
+/* SM cycles per internal phase of the fused kernel, summed over CTAs (diagnostic; 16 entries) */
+int rbphd_get_phase_cycles(rbphd_navigator* nav, int64_t out16[16]);
 void* rbphd_stream(rbphd_navigator* nav);   /* cudaStream_t of the handle, for event timing by the host */
 
 #ifdef __cplusplus

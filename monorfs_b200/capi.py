@@ -31,7 +31,8 @@ class RbphdConfig(C.Structure):
 class RbphdLimits(C.Structure):
     _fields_ = [
         ("device", C.c_int32), ("max_particles", C.c_int32), ("max_components", C.c_int32),
-        ("max_measurements", C.c_int32), ("max_pairs", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("max_measurements", C.c_int32), ("max_pairs", C.c_int32), ("resident_frames", C.c_int32),
+        ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -39,13 +40,13 @@ class RbphdLimits(C.Structure):
 EXPORTS = [
     "rbphd_new", "rbphd_delete", "rbphd_last_error", "rbphd_reset", "rbphd_clear_maps", "rbphd_particle_count",
     "rbphd_update", "rbphd_set_pose", "rbphd_set_poses", "rbphd_get_poses", "rbphd_slam_update",
-    "rbphd_frame_async", "rbphd_upload_frame_inputs", "rbphd_synchronize", "rbphd_resample",
+    "rbphd_frame_async", "rbphd_upload_frame_inputs", "rbphd_update_async", "rbphd_synchronize", "rbphd_resample",
     "rbphd_particle_depleted", "rbphd_get_weights", "rbphd_set_weights", "rbphd_get_alphas", "rbphd_get_best",
     "rbphd_get_ancestors", "rbphd_get_map_counts", "rbphd_get_map", "rbphd_set_map", "rbphd_stage_predict",
     "rbphd_stage_correct", "rbphd_stage_prune", "rbphd_stage_weight_alpha", "rbphd_stage_set_loglikelihood",
     "rbphd_slam_update_local", "rbphd_device_weights", "rbphd_resample_global", "rbphd_pack_particles",
-    "rbphd_unpack_particles", "rbphd_commit_resample_local", "rbphd_kernel_launches", "rbphd_last_stage_ms",
-    "rbphd_stream",
+    "rbphd_particle_record_bytes", "rbphd_unpack_particles", "rbphd_commit_resample_local", "rbphd_kernel_launches", "rbphd_profile_enable",
+    "rbphd_profile_read", "rbphd_get_counters", "rbphd_get_phase_cycles", "rbphd_stream",
 ]
 
 _lib = None
@@ -73,6 +74,8 @@ def load():
         lib.rbphd_last_error.argtypes = [C.c_void_p]
         lib.rbphd_kernel_launches.restype = C.c_int64
         lib.rbphd_kernel_launches.argtypes = [C.c_void_p]
+        lib.rbphd_particle_record_bytes.restype = C.c_int64
+        lib.rbphd_particle_record_bytes.argtypes = [C.c_void_p]
         lib.rbphd_stream.restype = C.c_void_p
         lib.rbphd_stream.argtypes = [C.c_void_p]
         _lib = lib
@@ -111,7 +114,8 @@ def _view(ptr, n, dtype=np.float64):
 class Handle:
     """Thin RAII wrapper over rbphd_navigator* (mirrors the HandleRef + Dispose pattern of ISAM2Navigator.cs:446-452)."""
 
-    def __init__(self, params, max_particles, max_components=0, max_measurements=0, max_pairs=0, device=0):
+    def __init__(self, params, max_particles, max_components=0, max_measurements=0, max_pairs=0, device=0,
+                 resident_frames=1):
         self.lib = load()
         self.cfg = make_config(params)
         lim = RbphdLimits()
@@ -120,6 +124,7 @@ class Handle:
         lim.max_components = int(max_components)
         lim.max_measurements = int(max_measurements)
         lim.max_pairs = int(max_pairs)
+        lim.resident_frames = int(resident_frames)
         self._h = self.lib.rbphd_new(C.byref(self.cfg), C.byref(lim))
         if not self._h:
             raise RbphdError(ERR_NO_DEVICE, self.lib.rbphd_last_error(None).decode())
@@ -221,17 +226,20 @@ class Handle:
                                             C.byref(best), C.byref(res)))
         return best.value, bool(res.value)
 
-    def upload_frame_inputs(self, gauss, z):
+    def upload_frame_inputs(self, gauss, z, slot=0):
         g = _d(gauss).reshape(-1, 6) if gauss is not None else None
         zz = _d(z).reshape(-1, 3) if z is not None else None
-        self._ck(self.lib.rbphd_upload_frame_inputs(self._h, _p(g) if g is not None else None,
+        self._ck(self.lib.rbphd_upload_frame_inputs(self._h, int(slot), _p(g) if g is not None else None,
                                                     _p(zz) if zz is not None else None,
                                                     len(zz) if zz is not None else 0))
 
-    def frame_async(self, reading, dt, m, u, only_mapping=False, perfect_still=False):
-        self._ck(self.lib.rbphd_frame_async(self._h, _p(_d(reading)) if reading is not None else None,
+    def frame_async(self, reading, dt, m, u, only_mapping=False, perfect_still=False, slot=0):
+        self._ck(self.lib.rbphd_frame_async(self._h, int(slot), _p(_d(reading)) if reading is not None else None,
                                             C.c_double(dt), int(perfect_still), int(m), int(only_mapping),
                                             C.c_double(u)))
+
+    def update_async(self, reading, dt, slot=0, perfect_still=False):
+        self._ck(self.lib.rbphd_update_async(self._h, int(slot), _p(_d(reading)), C.c_double(dt), int(perfect_still)))
 
     def synchronize(self):
         self._ck(self.lib.rbphd_synchronize(self._h))
@@ -287,8 +295,8 @@ class Handle:
         return out.value
 
     # ---- multi-GPU plumbing
-    def slam_update_local(self, m, only_mapping=False):
-        self._ck(self.lib.rbphd_slam_update_local(self._h, int(m), int(only_mapping)))
+    def slam_update_local(self, m, only_mapping=False, slot=0):
+        self._ck(self.lib.rbphd_slam_update_local(self._h, int(slot), int(m), int(only_mapping)))
 
     def device_weights(self):
         ptr, n = C.c_void_p(), C.c_int()
@@ -309,6 +317,9 @@ class Handle:
                                                C.byref(nbytes)))
         return ptr.value, nbytes.value
 
+    def record_doubles(self):
+        return int(self.lib.rbphd_particle_record_bytes(self._h)) // 8
+
     def unpack_particles(self, dev_ptr, slots):
         slots = np.ascontiguousarray(slots, dtype=np.int32)
         self._ck(self.lib.rbphd_unpack_particles(self._h, C.c_void_p(dev_ptr), slots.ctypes.data_as(c_int_p),
@@ -319,6 +330,32 @@ class Handle:
         self._ck(self.lib.rbphd_commit_resample_local(self._h, sources.ctypes.data_as(c_int_p), len(sources)))
 
     # ---- instrumentation
+    STAGES = ("pose", "prep", "particle_update", "normalize_resample", "copy_particles")
+
+    def profile_enable(self, max_frames):
+        self._ck(self.lib.rbphd_profile_enable(self._h, int(max_frames)))
+
+    def profile_read(self, max_frames):
+        ms = np.zeros((max_frames, 5))
+        n = C.c_int()
+        self._ck(self.lib.rbphd_profile_read(self._h, _p(ms), int(max_frames), C.byref(n)))
+        return ms[:n.value]
+
+    def counters(self, reset=False):
+        out = (C.c_int64 * 4)()
+        self._ck(self.lib.rbphd_get_counters(self._h, out, int(reset)))
+        return dict(comps_in=out[0], comps_out=out[1], pairs=out[2], particle_frames=out[3])
+
+    PHASES = ("A1 meas->map", "A2 prior comps+gate", "A3 prior pairs", "A4-5 explore+births", "A6-7 birth comps+pairs",
+              "A8-9 pair sort+weights", "B1 candidate sort", "B2 materialise", "B3 grid+edges", "B4-5 resolve",
+              "B6 merge+write", "C1-3 map estimate", "C4 eval predicted", "C4 eval corrected", "C5 set likelihood",
+              "tail")
+
+    def phase_cycles(self):
+        out = (C.c_int64 * 16)()
+        self._ck(self.lib.rbphd_get_phase_cycles(self._h, out))
+        return {k: int(out[i]) for i, k in enumerate(self.PHASES)}
+
     @property
     def kernel_launches(self):
         return int(self.lib.rbphd_kernel_launches(self._h))

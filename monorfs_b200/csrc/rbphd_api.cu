@@ -69,6 +69,11 @@ struct rbphd_navigator {
     int nslab = 0;
     size_t smem = 0, sort_cap = 0;
     int M_last = 0;
+    int slots = 1;
+    size_t zstride = 0, gstride = 0;   // doubles per input slot
+    // profiling: 6 events per frame
+    std::vector<cudaEvent_t> pev;
+    int prof_frames = 0, prof_max = 0;
     // host mirrors (library-owned outputs)
     PinnedBuf h_in, h_out, h_state, h_map;
     std::vector<double> o_w, o_m, o_P;
@@ -76,9 +81,6 @@ struct rbphd_navigator {
     int64_t launches = 0;
     std::string error;
     rbphd_navigator* stage = nullptr;   // lazily created 2-slot navigator for the stage entry points
-    cudaEvent_t ev[8] = {};
-    bool ev_ok = false;
-    double stage_ms[8] = {};
 };
 
 namespace {
@@ -212,7 +214,7 @@ void make_layout(ScratchLayout& l, int cap, int Mcap, int cap_pairs, int maxq)
     take(l.fat, I * l.cap_nodes);    take(l.clist, I * l.cap_nodes); take(l.gx, 3 * D * l.cap_pred);
     take(l.llkey, U * l.cap_ll);     take(l.llval, D * l.cap_ll);
     take(l.uf, I * (l.cap_j + Mcap + 2)); take(l.bcnt, I * (l.cap_j + Mcap + 2));
-    take(l.bsum, 16); take(l.bmin, 16); take(l.mslots, 16);
+    take(l.bsum, 16); take(l.bmin, 16); take(l.mslots, murty_workspace_bytes());
     l.bytes = align_up(off, 256);
 }
 
@@ -226,7 +228,7 @@ void free_device(rbphd_navigator* nav)
     cudaFree(nav->vitems); cudaFree(nav->zitems); cudaFree(nav->scratch); cudaFree(nav->dump);
     cudaFree(nav->dump_count); cudaFree(nav->gweights); cudaFree(nav->ganc); cudaFree(nav->packbuf);
     cudaFree(nav->idxbuf);
-    if (nav->ev_ok) for (auto& e : nav->ev) cudaEventDestroy(e);
+    for (auto& e : nav->pev) cudaEventDestroy(e);
     if (nav->stream) cudaStreamDestroy(nav->stream);
 }
 
@@ -236,7 +238,7 @@ int set_device(rbphd_navigator* nav)
     return RBPHD_OK;
 }
 
-KParams base_params(rbphd_navigator* nav, int mode, int M, int only_mapping)
+KParams base_params(rbphd_navigator* nav, int mode, int M, int only_mapping, int slot = 0)
 {
     KParams k;
     std::memset(&k, 0, sizeof k);
@@ -254,7 +256,7 @@ KParams base_params(rbphd_navigator* nav, int mode, int M, int only_mapping)
     k.weights = nav->weights;
     k.alphas = nav->alphas;
     k.alpha_parts = nav->alpha_parts;
-    k.z = nav->z;
+    k.z = nav->z + nav->zstride * (size_t)slot;
     k.vgrid = nav->vgrid;  k.vitems = nav->vitems;
     k.zgrid = nav->zgrid;  k.zitems = nav->zitems;
     k.scratch = nav->scratch;
@@ -274,12 +276,15 @@ int check_async(rbphd_navigator* nav, const char* what)
 }
 
 // prep + fused per-particle kernel
-int enqueue_map_update(rbphd_navigator* nav, int M, int only_mapping, int mode)
+int enqueue_map_update(rbphd_navigator* nav, int M, int only_mapping, int mode, int slot = 0,
+                       cudaEvent_t* ev = nullptr)
 {
-    launch_frame_prep(nav->stream, nav->dcfg, nav->z, M, nav->vgrid, nav->vitems, nav->zgrid, nav->zitems, nav->pts);
-    KParams k = base_params(nav, mode, M, only_mapping);
+    KParams k = base_params(nav, mode, M, only_mapping, slot);
+    launch_frame_prep(nav->stream, nav->dcfg, k.z, M, nav->vgrid, nav->vitems, nav->zgrid, nav->zitems, nav->pts);
+    if (ev) cudaEventRecord(ev[0], nav->stream);
     int grid = std::min(nav->nslab, std::max(1, nav->P));
     launch_particle_update(nav->stream, k, grid, nav->smem);
+    if (ev) cudaEventRecord(ev[1], nav->stream);
     nav->launches += 2;
     nav->M_last = M;
     return check_async(nav, "particle update launch");
@@ -304,7 +309,8 @@ int status_to_error(rbphd_navigator* nav, int status)
     if (status & ST_OVER_EDGES) msg += " merge-edges";
     if (status & ST_OVER_JMAP) msg += " map-estimate-size";
     if (status & ST_OVER_LL) msg += " likelihood-edges";
-    if (status & ST_OVER_BLOCK) msg += " association-block>5-rows(Murty lane not available)";
+    if (status & ST_OVER_BLOCK) msg += " association-block-rows(>24)";
+    if (status & ST_OVER_MURTY) msg += " murty-node-pool";
     return fail(nav, RBPHD_ERR_CAPACITY, msg);
 }
 
@@ -403,7 +409,9 @@ rbphd_navigator* rbphd_new(const rbphd_config* config, const rbphd_limits* limit
     if (lim.max_measurements <= 0) lim.max_measurements = 1024;
     lim.max_measurements = (lim.max_measurements + 1) & ~1;
     if (lim.max_pairs <= 0) lim.max_pairs = 4 * lim.max_measurements;
+    if (lim.resident_frames <= 0) lim.resident_frames = 1;
     nav->lim = lim;
+    nav->slots = lim.resident_frames;
     nav->maxP = lim.max_particles;
     nav->cap = lim.max_components;
     nav->Mcap = lim.max_measurements;
@@ -440,14 +448,16 @@ rbphd_navigator* rbphd_new(const rbphd_config* config, const rbphd_limits* limit
     CKN(cudaMalloc(&nav->weights, sizeof(double) * nav->maxP));
     CKN(cudaMalloc(&nav->alphas, sizeof(double) * nav->maxP));
     CKN(cudaMalloc(&nav->alpha_parts, sizeof(double) * 8 * nav->maxP));
-    CKN(cudaMalloc(&nav->z, sizeof(double) * 3 * nav->Mcap + 64));
-    CKN(cudaMalloc(&nav->gauss, sizeof(double) * 6 * nav->maxP));
+    nav->zstride = 3 * (size_t)nav->Mcap;
+    nav->gstride = 6 * (size_t)nav->maxP + (6 * (size_t)nav->maxP) % 2;
+    CKN(cudaMalloc(&nav->z, sizeof(double) * nav->zstride * nav->slots + 64));
+    CKN(cudaMalloc(&nav->gauss, sizeof(double) * nav->gstride * nav->slots));
     CKN(cudaMalloc(&nav->pts, sizeof(double) * 6 * nav->Mcap + 64));
     CKN(cudaMalloc(&nav->ancestors, sizeof(int) * nav->maxP));
     CKN(cudaMalloc(&nav->st, sizeof(DeviceState)));
     CKN(cudaMemsetAsync(nav->st, 0, sizeof(DeviceState), nav->stream));
     CKN(cudaMemsetAsync(nav->alphas, 0, sizeof(double) * nav->maxP, nav->stream));
-    CKN(cudaMemsetAsync(nav->gauss, 0, sizeof(double) * 6 * nav->maxP, nav->stream));
+    CKN(cudaMemsetAsync(nav->gauss, 0, sizeof(double) * nav->gstride * nav->slots, nav->stream));
     CKN(cudaMalloc(&nav->vgrid, sizeof(FrameGrid)));
     CKN(cudaMalloc(&nav->zgrid, sizeof(FrameGrid)));
     CKN(cudaMalloc(&nav->vitems, sizeof(int) * (nav->Mcap + 2)));
@@ -463,8 +473,6 @@ rbphd_navigator* rbphd_new(const rbphd_config* config, const rbphd_limits* limit
     if (per_sm < 1) return bail("k_particle_update cannot be resident (shared memory / registers)");
     nav->nslab = std::max(1, std::min(prop.multiProcessorCount * per_sm, nav->maxP));
     CKN(cudaMalloc(&nav->scratch, nav->lay.bytes * (size_t)nav->nslab));
-    for (auto& ev : nav->ev) CKN(cudaEventCreate(&ev));
-    nav->ev_ok = true;
     CKN(cudaStreamSynchronize(nav->stream));
 #undef CKN
     nav->P = 0;
@@ -526,17 +534,18 @@ int rbphd_clear_maps(rbphd_navigator* nav)
     return RBPHD_OK;
 }
 
-int rbphd_upload_frame_inputs(rbphd_navigator* nav, const double* gauss, const double* z, int m)
+int rbphd_upload_frame_inputs(rbphd_navigator* nav, int slot, const double* gauss, const double* z, int m)
 {
     if (!nav) return RBPHD_ERR_ARGUMENT;
     if (m < 0 || m > nav->Mcap) return fail(nav, RBPHD_ERR_ARGUMENT, "m > max_measurements");
+    if (slot < 0 || slot >= nav->slots) return fail(nav, RBPHD_ERR_ARGUMENT, "input slot out of range");
     if (int r = set_device(nav)) return r;
     size_t gb = gauss ? sizeof(double) * 6 * (size_t)nav->P : 0;
     size_t zb = z ? sizeof(double) * 3 * (size_t)m : 0;
     // the pinned staging buffer may still be in flight from the previous frame
     CK(cudaStreamSynchronize(nav->stream));
-    if (gauss) if (int r = upload(nav, nav->gauss, gauss, gb, 0)) return r;
-    if (z) if (int r = upload(nav, nav->z, z, zb, gb)) return r;
+    if (gauss) if (int r = upload(nav, nav->gauss + nav->gstride * (size_t)slot, gauss, gb, 0)) return r;
+    if (z) if (int r = upload(nav, nav->z + nav->zstride * (size_t)slot, z, zb, gb)) return r;
     return RBPHD_OK;
 }
 
@@ -545,7 +554,7 @@ int rbphd_update(rbphd_navigator* nav, const double* reading6, double dt, const 
     if (!nav || !reading6) return RBPHD_ERR_ARGUMENT;
     if (nav->P < 1) return fail(nav, RBPHD_ERR_ARGUMENT, "navigator not reset");
     if (int r = set_device(nav)) return r;
-    if (gauss) if (int r = rbphd_upload_frame_inputs(nav, gauss, nullptr, 0)) return r;
+    if (gauss) if (int r = rbphd_upload_frame_inputs(nav, 0, gauss, nullptr, 0)) return r;
     Reading6 rd;
     std::memcpy(rd.v, reading6, sizeof rd.v);
     launch_predict_pose(nav->stream, nav->dcfg, nav->P, nav->poses, rd, dt, nav->gauss, perfect_still);
@@ -553,6 +562,20 @@ int rbphd_update(rbphd_navigator* nav, const double* reading6, double dt, const 
     if (int r = check_async(nav, "predict_pose launch")) return r;
     CK(cudaStreamSynchronize(nav->stream));
     return RBPHD_OK;
+}
+
+int rbphd_update_async(rbphd_navigator* nav, int slot, const double* reading6, double dt, int perfect_still)
+{
+    if (!nav || !reading6) return RBPHD_ERR_ARGUMENT;
+    if (nav->P < 1) return fail(nav, RBPHD_ERR_ARGUMENT, "navigator not reset");
+    if (slot < 0 || slot >= nav->slots) return fail(nav, RBPHD_ERR_ARGUMENT, "input slot out of range");
+    if (int r = set_device(nav)) return r;
+    Reading6 rd;
+    std::memcpy(rd.v, reading6, sizeof rd.v);
+    launch_predict_pose(nav->stream, nav->dcfg, nav->P, nav->poses, rd, dt, nav->gauss + nav->gstride * (size_t)slot,
+                        perfect_still);
+    nav->launches += 1;
+    return check_async(nav, "predict_pose launch");
 }
 
 int rbphd_set_pose(rbphd_navigator* nav, int particle, const double* pose7)
@@ -709,36 +732,46 @@ int rbphd_synchronize(rbphd_navigator* nav)
     return RBPHD_OK;
 }
 
-static int enqueue_slam_tail(rbphd_navigator* nav, int only_mapping, double u, int force)
+static int enqueue_slam_tail(rbphd_navigator* nav, int only_mapping, double u, int force,
+                             cudaEvent_t* ev = nullptr)
 {
     if (only_mapping) {
         launch_flip(nav->stream, nav->st);
         nav->launches += 1;
+        if (ev) { cudaEventRecord(ev[0], nav->stream); cudaEventRecord(ev[1], nav->stream); }
     }
     else {
         launch_normalize_resample(nav->stream, nav->dcfg, nav->P, nav->weights, u, force, nav->ancestors, nav->st);
+        if (ev) cudaEventRecord(ev[0], nav->stream);
         launch_copy_particles(nav->stream, nav->P, nav->cap, nav->maps, nav->counts, nav->poses, nav->poses_tmp,
                               nav->ancestors, nav->st);
+        if (ev) cudaEventRecord(ev[1], nav->stream);
         nav->launches += 3;
     }
     return check_async(nav, "slam tail launch");
 }
 
-int rbphd_frame_async(rbphd_navigator* nav, const double* reading6, double dt, int perfect_still, int m,
+int rbphd_frame_async(rbphd_navigator* nav, int slot, const double* reading6, double dt, int perfect_still, int m,
                       int only_mapping, double u_resample)
 {
     if (!nav) return RBPHD_ERR_ARGUMENT;
     if (nav->P < 1) return fail(nav, RBPHD_ERR_ARGUMENT, "navigator not reset");
     if (m < 0 || m > nav->Mcap) return fail(nav, RBPHD_ERR_ARGUMENT, "m > max_measurements");
+    if (slot < 0 || slot >= nav->slots) return fail(nav, RBPHD_ERR_ARGUMENT, "input slot out of range");
     if (int r = set_device(nav)) return r;
+    cudaEvent_t* ev = nullptr;
+    if (nav->prof_frames < nav->prof_max) ev = &nav->pev[6 * (size_t)nav->prof_frames++];
+    if (ev) cudaEventRecord(ev[0], nav->stream);
     if (reading6 && !only_mapping) {
         Reading6 rd;
         std::memcpy(rd.v, reading6, sizeof rd.v);
-        launch_predict_pose(nav->stream, nav->dcfg, nav->P, nav->poses, rd, dt, nav->gauss, perfect_still);
+        launch_predict_pose(nav->stream, nav->dcfg, nav->P, nav->poses, rd, dt,
+                            nav->gauss + nav->gstride * (size_t)slot, perfect_still);
         nav->launches += 1;
     }
-    if (int r = enqueue_map_update(nav, m, only_mapping, MODE_FRAME)) return r;
-    return enqueue_slam_tail(nav, only_mapping, u_resample, 0);
+    if (ev) cudaEventRecord(ev[1], nav->stream);
+    if (int r = enqueue_map_update(nav, m, only_mapping, MODE_FRAME, slot, ev ? ev + 2 : nullptr)) return r;
+    return enqueue_slam_tail(nav, only_mapping, u_resample, 0, ev ? ev + 4 : nullptr);
 }
 
 int rbphd_slam_update(rbphd_navigator* nav, const double* z, int m, int only_mapping, double u_resample, int* best,
@@ -749,7 +782,7 @@ int rbphd_slam_update(rbphd_navigator* nav, const double* z, int m, int only_map
     if (m < 0 || m > nav->Mcap) return fail(nav, RBPHD_ERR_ARGUMENT, "m > max_measurements");
     if (m > 0 && !z) return RBPHD_ERR_ARGUMENT;
     if (int r = set_device(nav)) return r;
-    if (int r = rbphd_upload_frame_inputs(nav, nullptr, z, m)) return r;
+    if (int r = rbphd_upload_frame_inputs(nav, 0, nullptr, z, m)) return r;
     if (int r = enqueue_map_update(nav, m, only_mapping, MODE_FRAME)) return r;
     if (int r = enqueue_slam_tail(nav, only_mapping, u_resample, 0)) return r;
     DeviceState st;
@@ -804,7 +837,7 @@ static int stage_run(rbphd_navigator* nav, rbphd_navigator** sp, const double* p
     static const double ident[7] = {0, 0, 0, 1, 0, 0, 0};
     if (int r = rbphd_reset(s, 1, pose7 ? pose7 : ident, n, w, mean, cov)) return fail(nav, r, s->error);
     if (m > s->Mcap) return fail(nav, RBPHD_ERR_ARGUMENT, "m > max_measurements");
-    if (int r = rbphd_upload_frame_inputs(s, nullptr, z, m)) return fail(nav, r, s->error);
+    if (int r = rbphd_upload_frame_inputs(s, 0, nullptr, z, m)) return fail(nav, r, s->error);
     return RBPHD_OK;
 }
 
@@ -933,13 +966,14 @@ int rbphd_stage_set_loglikelihood(rbphd_navigator* nav, const double* pose7, int
 }
 
 // ------------------------------------------------------------------ multi-GPU plumbing
-int rbphd_slam_update_local(rbphd_navigator* nav, int m, int only_mapping)
+int rbphd_slam_update_local(rbphd_navigator* nav, int slot, int m, int only_mapping)
 {
     if (!nav) return RBPHD_ERR_ARGUMENT;
     if (nav->P < 1) return fail(nav, RBPHD_ERR_ARGUMENT, "navigator not reset");
     if (m < 0 || m > nav->Mcap) return fail(nav, RBPHD_ERR_ARGUMENT, "m > max_measurements");
+    if (slot < 0 || slot >= nav->slots) return fail(nav, RBPHD_ERR_ARGUMENT, "input slot out of range");
     if (int r = set_device(nav)) return r;
-    if (int r = enqueue_map_update(nav, m, only_mapping, MODE_FRAME)) return r;
+    if (int r = enqueue_map_update(nav, m, only_mapping, MODE_FRAME, slot)) return r;
     if (only_mapping) { launch_flip(nav->stream, nav->st); nav->launches += 1; }
     return check_async(nav, "local slam update");
 }
@@ -997,6 +1031,11 @@ int rbphd_resample_global(rbphd_navigator* nav, const void* dev_global_weights, 
 
 // One migration record = [count as double][pose 7][13 * cap map slab], 8 + 13*cap doubles.
 static size_t record_doubles(const rbphd_navigator* nav) { return 8 + (size_t)kFields * nav->cap; }
+
+int64_t rbphd_particle_record_bytes(const rbphd_navigator* nav)
+{
+    return nav ? (int64_t)(record_doubles(nav) * sizeof(double)) : 0;
+}
 
 int rbphd_pack_particles(rbphd_navigator* nav, const int* local_indices, int count, void** dev_buf, int64_t* bytes)
 {
@@ -1086,12 +1125,61 @@ int rbphd_commit_resample_local(rbphd_navigator* nav, const int* local_sources, 
     return RBPHD_OK;
 }
 
+int rbphd_get_phase_cycles(rbphd_navigator* nav, int64_t out16[16])
+{
+    if (!nav || !out16) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    DeviceState st;
+    if (int r = read_state(nav, &st)) return r;
+    for (int a = 0; a < 16; a++) out16[a] = (int64_t)st.phase_cycles[a];
+    return RBPHD_OK;
+}
+
 int64_t rbphd_kernel_launches(const rbphd_navigator* nav) { return nav ? nav->launches : 0; }
 
-int rbphd_last_stage_ms(rbphd_navigator* nav, double* ms, int n)
+int rbphd_profile_enable(rbphd_navigator* nav, int max_frames)
+{
+    if (!nav || max_frames < 0) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    while ((int)nav->pev.size() < 6 * max_frames) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        nav->pev.push_back(e);
+    }
+    nav->prof_max = max_frames;
+    nav->prof_frames = 0;
+    return RBPHD_OK;
+}
+
+int rbphd_profile_read(rbphd_navigator* nav, double* ms, int max_frames, int* frames)
 {
     if (!nav || !ms) return RBPHD_ERR_ARGUMENT;
-    for (int i = 0; i < n && i < 8; i++) ms[i] = nav->stage_ms[i];
+    if (int r = set_device(nav)) return r;
+    CK(cudaStreamSynchronize(nav->stream));
+    int n = std::min(nav->prof_frames, max_frames);
+    for (int f = 0; f < n; f++)
+        for (int st = 0; st < RBPHD_STAGES; st++) {
+            float t = 0;
+            CK(cudaEventElapsedTime(&t, nav->pev[6 * (size_t)f + st], nav->pev[6 * (size_t)f + st + 1]));
+            ms[(size_t)f * RBPHD_STAGES + st] = t;
+        }
+    if (frames) *frames = n;
+    nav->prof_frames = 0;
+    return RBPHD_OK;
+}
+
+int rbphd_get_counters(rbphd_navigator* nav, int64_t out4[4], int reset)
+{
+    if (!nav || !out4) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    DeviceState st;
+    if (int r = read_state(nav, &st)) return r;
+    out4[0] = (int64_t)st.comps_in; out4[1] = (int64_t)st.comps_out;
+    out4[2] = (int64_t)st.pairs; out4[3] = (int64_t)st.particle_frames;
+    if (reset) {
+        CK(cudaMemsetAsync(&nav->st->comps_in, 0, 20 * sizeof(unsigned long long), nav->stream));
+        CK(cudaStreamSynchronize(nav->stream));
+    }
     return RBPHD_OK;
 }
 

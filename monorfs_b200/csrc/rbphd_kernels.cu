@@ -24,7 +24,20 @@ struct Ctx {
     int status;
     double pose[7];
     CellGrid grid;
+    long long tlast;
+    unsigned long long tphase[16];
 };
+
+// phase timer: thread 0 attributes the cycles since the previous mark to phase `ph`
+#define PHASE_MARK(sm, ph)                                                   \
+    do {                                                                     \
+        if (threadIdx.x == 0) {                                              \
+            long long now__ = clock64();                                     \
+            (sm).ctx.tphase[ph] += (unsigned long long)(now__ - (sm).ctx.tlast); \
+            (sm).ctx.tlast = now__;                                          \
+        }                                                                    \
+    } while (0)
+
 
 struct Smem {
     BlockShared sh;
@@ -213,6 +226,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
     }
     __syncthreads();
 
+    PHASE_MARK(sm, 0);
     // A2: prior components: miss-detection weight (PHD:837-840), gate lookup, frustum flag
     const CellGrid& vg = p.vgrid->g;
     for (int i = tid; i < N; i += kBlock) {
@@ -238,9 +252,11 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
     }
     __syncthreads();
 
+    PHASE_MARK(sm, 1);
     // A3: gated pairs of prior components
     for (int j = tid; j < sm.ctx.npairs_prior; j += kBlock) eval_pair(p, sm, s, in, j);
     __syncthreads();
+    PHASE_MARK(sm, 2);
 
     int B = 0;
     if (do_births) {
@@ -307,6 +323,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
     }
     if (tid == 0) { sm.ctx.B = B; sm.ctx.Npred = N + B; }
     __syncthreads();
+    PHASE_MARK(sm, 3);
     const int Npred = N + B;
 
     // A6/A7: births as predicted components: miss-detection weight, gate lookup, pairs
@@ -327,6 +344,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
     for (int j = sm.ctx.npairs_prior + tid; j < sm.ctx.npairs; j += kBlock) eval_pair(p, sm, s, in, j);
     __syncthreads();
 
+    PHASE_MARK(sm, 4);
     // A8: order the pairs by (measurement, component): the reference's output order (PHD:881-903)
     const int np = sm.ctx.npairs;
     const int np2 = next_pow2(np > 1 ? np : 1);
@@ -356,6 +374,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
     __syncthreads();
     if (tid == 0) sm.ctx.L = Npred + np;
     __syncthreads();
+    PHASE_MARK(sm, 5);
     (void)particle;
 }
 
@@ -446,6 +465,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
         for (int j = nc + tid; j < nc2; j += kBlock) { s.skey[j] = ~0ull; s.sval[j] = ~0u; }
     }
     block_bitonic_sort(skey, sval, nc2);
+    PHASE_MARK(sm, 6);
     const int W0 = min(min(c.maxq, nc), capw);
     if (tid == 0) { sm.ctx.W0 = W0; if (min(c.maxq, nc) > capw) sm.ctx.status |= ST_OVER_COMPONENTS; }
 
@@ -468,6 +488,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
     double rmean = block_sum(sm.sh, rsum) / (W0 > 0 ? W0 : 1);
     __syncthreads();
 
+    PHASE_MARK(sm, 7);
     // B3: cell grid over the W0 means; out-edges r -> r' (r' > r, close w.r.t. candidate r's covariance)
     const double* tx = s.tm; const double* ty = s.tm + capw; const double* tz = s.tm + 2 * capw;
     double mincell = 2.0 * rmean;
@@ -511,6 +532,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
         }
     }
 
+    PHASE_MARK(sm, 8);
     // B4: which candidates survive.  A component is absorbed iff some surviving earlier candidate is
     // close to it; resolve in rounds (the lowest undecided rank is always decidable).
     for (int r = tid; r < W0; r += kBlock) { s.nstate[r] = 0; s.nflag[r] = 0; s.nowner[r] = 0x7fffffff; }
@@ -548,6 +570,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
         for (int a = b; a < e; a++) atomicMin(&s.nowner[s.edst[a]], r);
     }
     __syncthreads();
+    PHASE_MARK(sm, 9);
     // B6: output slot of each survivor, then the merge (GAUSS:329-346) in list order
     for (int r = tid; r < W0; r += kBlock) s.nflag[r] = (s.nstate[r] == 1) ? 1 : 0;
     __syncthreads();
@@ -603,6 +626,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
     }
     if (tid == 0) sm.ctx.nout = nout;
     __syncthreads();
+    PHASE_MARK(sm, 10);
 }
 
 // implemented in rbphd_weight.cuh (included below): WeightAlpha (PHD:373-393)
@@ -612,6 +636,7 @@ __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab
 
 }  // namespace rbphd
 
+#include "rbphd_murty.cuh"
 #include "rbphd_weight.cuh"
 
 namespace rbphd {
@@ -688,6 +713,8 @@ __global__ void __launch_bounds__(kBlock, 2) k_particle_update(const __grid_cons
         __syncthreads();
     }
 
+    unsigned long long acc_in = 0, acc_out = 0, acc_pairs = 0, acc_pf = 0;   // thread 0 only
+    if (tid == 0) { for (int a = 0; a < 16; a++) sm.ctx.tphase[a] = 0; sm.ctx.tlast = clock64(); }
     for (int particle = p.first + blockIdx.x; particle < p.first + p.P; particle += gridDim.x) {
         const double* in = p.maps[cur] + (size_t)particle * kFields * p.cap;
         double* out = p.maps[1 - cur] + (size_t)particle * kFields * p.cap;
@@ -778,8 +805,18 @@ __global__ void __launch_bounds__(kBlock, 2) k_particle_update(const __grid_cons
             if (tid == 0) p.alphas[particle] = ll;
         }
         __syncthreads();
-        if (tid == 0 && sm.ctx.status) atomicOr(&p.st->status, sm.ctx.status);
+        PHASE_MARK(sm, 15);
+        if (tid == 0) {
+            if (sm.ctx.status) atomicOr(&p.st->status, sm.ctx.status);
+            acc_in += (unsigned long long)sm.ctx.N; acc_out += (unsigned long long)sm.ctx.nout;
+            acc_pairs += (unsigned long long)sm.ctx.npairs; acc_pf += 1;
+        }
         __syncthreads();
+    }
+    if (tid == 0 && p.mode == MODE_FRAME) {
+        atomicAdd(&p.st->comps_in, acc_in); atomicAdd(&p.st->comps_out, acc_out);
+        atomicAdd(&p.st->pairs, acc_pairs); atomicAdd(&p.st->particle_frames, acc_pf);
+        for (int a = 0; a < 16; a++) atomicAdd(&p.st->phase_cycles[a], sm.ctx.tphase[a]);
     }
 }
 
@@ -992,6 +1029,8 @@ void launch_frame_prep(cudaStream_t s, const DevCfg& cfg, const double* z, int M
 {
     k_frame_prep<<<1, kBlock, 0, s>>>(cfg, z, M, vg, vitems, zg, zitems, pts);
 }
+
+size_t murty_workspace_bytes() { return sizeof(MurtyWork); }
 
 size_t particle_update_smem(int max_measurements, size_t* sort_cap)
 {

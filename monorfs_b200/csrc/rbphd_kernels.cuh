@@ -31,6 +31,8 @@ struct DeviceState {
     int status;      // OR of StatusBits
     int depleted;
     int pad[3];
+    unsigned long long comps_in, comps_out, pairs, particle_frames;   // work counters
+    unsigned long long phase_cycles[16];   // SM cycles spent per phase of k_particle_update (thread 0, all CTAs)
 };
 
 struct FrameGrid {
@@ -92,6 +94,7 @@ void launch_copy_particles(cudaStream_t s, int P, int cap, double* const maps[2]
                            double* poses, double* poses_tmp, const int* ancestors, DeviceState* st);
 void launch_flip(cudaStream_t s, DeviceState* st);
 size_t particle_update_smem(int max_measurements, size_t* sort_cap);
+size_t murty_workspace_bytes();
 int particle_update_max_ctas_per_sm(size_t smem);
 
 }  // namespace rbphd

@@ -143,6 +143,128 @@ __device__ __forceinline__ double log_sum_exp(const double* v, int n)
     return mx + log(value);
 }
 
+
+// landmarks (ascending) and measurements (ascending) of the edge group [e, end); -1 if more than maxn rows
+__device__ inline int collect_block(const unsigned long long* skey, int e, int end, int maxn, int* ts, int* ks,
+                                    int* pa, int* pb)
+{
+    int a = 0, b = 0;
+    for (int q = e; q < end; q++) {
+        int t = (int)((skey[q] >> 20) & 0xfffff), k = (int)(skey[q] & 0xfffff);
+        bool ft = false, fk = false;
+        for (int i = 0; i < a; i++) ft |= (ts[i] == t);
+        for (int i = 0; i < b; i++) fk |= (ks[i] == k);
+        if (!ft) { if (a + b >= maxn) return -1; ts[a++] = t; }
+        if (!fk) {
+            if (a + b >= maxn) return -1;
+            int i = b++;
+            while (i > 0 && ks[i - 1] > k) { ks[i] = ks[i - 1]; i--; }
+            ks[i] = k;
+        }
+    }
+    *pa = a; *pb = b;
+    return a + b;
+}
+
+// the compacted block (SPM:592-628): rows = landmarks then clutter rows, columns = measurements then miss
+// columns, detection edges from the gate, clutter x miss quadrant filled with 0 (PHD:480-488)
+__device__ inline void fill_block(const DevCfg& c, const Slab& s, const unsigned long long* skey,
+                                  const unsigned int* sval, int e, int end, const int* ts, const int* ks, int a,
+                                  int b, double* Mx, int ld)
+{
+    const int n = a + b;
+    for (int r = 0; r < n; r++)
+        for (int cc = 0; cc < n; cc++) {
+            double v;
+            if (r < a) v = (cc >= b && cc - b == r) ? log(1 - s.jpd[ts[r]]) : -INFINITY;
+            else       v = (cc < b) ? ((cc == r - a) ? c.logclutter : -INFINITY) : 0.0;
+            Mx[r * ld + cc] = v;
+        }
+    for (int q = e; q < end; q++) {
+        int t = (int)((skey[q] >> 20) & 0xfffff), k = (int)(skey[q] & 0xfffff);
+        int r = 0, cc = 0;
+        while (ts[r] != t) r++;
+        while (ks[cc] != k) cc++;
+        Mx[r * ld + cc] = s.llval[sval[q]];
+    }
+}
+
+__device__ inline int lexicographical_values(const double* Mx, int n, int modelsize, double* vals);
+
+// logcomp[m] as the reference's shared 200-entry buffer holds it when the block starting at edge `head`
+// begins (quirk A9.4): the m-th value of the most recent earlier block that produced more than m values
+// (blocks without detection edges only ever write index 0 and come last), else the initial 0.
+__device__ double stale_value(const KParams& p, const Slab& s, MurtyWork& mw, const unsigned long long* skey,
+                              const unsigned int* sval, int head, int nbig_done, int J, int m)
+{
+    int pos = head;
+    while (pos > 0) {
+        unsigned long long lab = skey[pos - 1] >> 40;
+        int st = pos - 1;
+        while (st > 0 && (skey[st - 1] >> 40) == lab) st--;
+        int bj = -1;
+        for (int q = 0; q < nbig_done; q++) if (mw.bighead[q] == st) bj = q;
+        if (bj >= 0) {
+            if (mw.bigcnt[bj] > m) return mw.bigvals[bj][m];
+        }
+        else {
+            int ts[5], ks[5], a, b;
+            int n = collect_block(skey, st, pos, 5, ts, ks, &a, &b);
+            if (n > 0) {
+                double Mx[25];
+                fill_block(p.cfg, s, skey, sval, st, pos, ts, ks, a, b, Mx, 5);
+                int cnt = lexicographical_values(Mx, n, J, mw.tmpvals);
+                if (cnt > m) return mw.tmpvals[m];
+            }
+        }
+        pos = st;
+    }
+    return 0.0;
+}
+
+// serial Murty lane for the blocks with more than five rows of one particle (thread 0 only)
+__device__ double murty_lane(const KParams& p, Smem& sm, const Slab& s, MurtyWork& mw,
+                             const unsigned long long* skey, const unsigned int* sval, int nll, int J, int nbig)
+{
+    if (nbig > kMurtyBig) { sm.ctx.status |= ST_OVER_MURTY; nbig = kMurtyBig; }
+    for (int a = 1; a < nbig; a++) {   // component order = ascending head
+        int v = mw.bighead[a], b = a - 1;
+        while (b >= 0 && mw.bighead[b] > v) { mw.bighead[b + 1] = mw.bighead[b]; b--; }
+        mw.bighead[b + 1] = v;
+    }
+    double contrib = 0;
+    for (int bi = 0; bi < nbig; bi++) {
+        const int e = mw.bighead[bi];
+        const unsigned long long lab = skey[e] >> 40;
+        int end = e + 1;
+        while (end < nll && (skey[end] >> 40) == lab) end++;
+        int ts[kMurtyN], ks[kMurtyN], a, b;
+        const int n = collect_block(skey, e, end, kMurtyN, ts, ks, &a, &b);
+        mw.bigcnt[bi] = 0;
+        if (n < 0) { sm.ctx.status |= ST_OVER_BLOCK; continue; }
+        fill_block(p.cfg, s, skey, sval, e, end, ts, ks, a, b, mw.profit, kMurtyN);
+        murty_begin(mw, n);
+        double* vals = mw.bigvals[bi];
+        int m = 0;
+        double v;
+        bool have = murty_next(mw, n, &v);
+        while (have) {
+            // PHD:503 (the m = 0 test compares logcomp[0] with itself and never fires)
+            if (m >= 200) break;
+            if (m >= 1 && stale_value(p, s, mw, skey, sval, e, bi, J, m) - vals[0] < -10) break;
+            vals[m++] = v;
+            // the next assignment is only needed if the test for index m lets it through
+            if (m >= 200) break;
+            if (stale_value(p, s, mw, skey, sval, e, bi, J, m) - vals[0] < -10) break;
+            have = murty_next(mw, n, &v);
+        }
+        if (mw.overflow) sm.ctx.status |= ST_OVER_MURTY;
+        mw.bigcnt[bi] = m;
+        contrib += log_sum_exp(vals, m);
+    }
+    return contrib;
+}
+
 // GC:280-350 on a dense n x n block (n <= 5), values pushed to vals (at most 200: PHD:469,503)
 __device__ inline int lexicographical_values(const double* Mx, int n, int modelsize, double* vals)
 {
@@ -273,48 +395,33 @@ __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab
     block_bitonic_sort(skey, sval, n2);
 
     double contrib = 0;
+    __shared__ int s_nbig;
+    if (tid == 0) s_nbig = 0;
+    __syncthreads();
+    MurtyWork& mw = *reinterpret_cast<MurtyWork*>(s.mslots);
     // blocks with at least one detection edge: one thread per block (head = first edge of the label)
     for (int e = tid; e < nll; e += kBlock) {
         unsigned long long lab = skey[e] >> 40;
         if (e > 0 && (skey[e - 1] >> 40) == lab) continue;
         int end = e + 1;
         while (end < nll && (skey[end] >> 40) == lab) end++;
-        int ts[5], ks[5], a = 0, b = 0;
-        bool big = false;
-        for (int q = e; q < end && !big; q++) {
-            int t = (int)((skey[q] >> 20) & 0xfffff), k = (int)(skey[q] & 0xfffff);
-            bool ft = false, fk = false;
-            for (int i = 0; i < a; i++) ft |= (ts[i] == t);
-            for (int i = 0; i < b; i++) fk |= (ks[i] == k);
-            if (!ft) { if (a + b >= 5) big = true; else ts[a++] = t; }
-            if (!fk && !big) {
-                if (a + b >= 5) big = true;
-                else { int i = b++; while (i > 0 && ks[i - 1] > k) { ks[i] = ks[i - 1]; i--; } ks[i] = k; }
-            }
+        int ts[5], ks[5], a, b;
+        const int n = collect_block(skey, e, end, 5, ts, ks, &a, &b);
+        if (n < 0) {   // more than five rows: Murty lane, handled serially below (PHD:496-499)
+            int slot = atomicAdd(&s_nbig, 1);
+            if (slot < kMurtyBig) mw.bighead[slot] = e;
+            continue;
         }
-        if (big) { atomicOr(&sm.ctx.status, ST_OVER_BLOCK); continue; }
-        const int n = a + b;
         double Mx[25], vals[200];
-        for (int r = 0; r < n; r++)
-            for (int cc = 0; cc < n; cc++) {
-                double v;
-                if (r < a) v = (cc >= b && cc - b == r) ? log(1 - s.jpd[ts[r]]) : -INFINITY;
-                else       v = (cc < b) ? ((cc == r - a) ? c.logclutter : -INFINITY) : 0.0;
-                Mx[r * 5 + cc] = v;
-            }
-        for (int q = e; q < end; q++) {
-            int t = (int)((skey[q] >> 20) & 0xfffff), k = (int)(skey[q] & 0xfffff);
-            int r = 0, cc = 0;
-            while (ts[r] != t) r++;
-            while (ks[cc] != k) cc++;
-            Mx[r * 5 + cc] = s.llval[sval[q]];
-        }
+        fill_block(c, s, skey, sval, e, end, ts, ks, a, b, Mx, 5);
         int m = lexicographical_values(Mx, n, J, vals);
         contrib += log_sum_exp(vals, m);
     }
     // isolated landmarks (1x1 block: ln(1 - PD)) and isolated measurements (1x1 block: ln clutter)
     for (int t = tid; t < J; t += kBlock) if (deg[t] == 0) contrib += log(1 - s.jpd[t]);
     for (int k = tid; k < M; k += kBlock) if (deg[J + k] == 0) contrib += c.logclutter;
+    __syncthreads();
+    if (tid == 0 && s_nbig > 0) contrib += murty_lane(p, sm, s, mw, skey, sval, nll, J, s_nbig);
     double total = block_sum(sm.sh, contrib);
     __syncthreads();
     return total;
@@ -373,15 +480,19 @@ __device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const 
     }
     __syncthreads();
 
+    PHASE_MARK(sm, 11);
     // PHD:381-384: sum_j ln v_pred(m_j), sum_j ln v_corr(m_j)
     CompSrc pred{s.pwt, s.pm, s.pm + capp, s.pm + 2 * capp, mfield(predmap, p.cap, 4), (size_t)p.cap, npriorcov,
                  p.cfg.birth_cov, Npred};
     const double plog = eval_map_at_points(p, sm, s, pred, J);
+    PHASE_MARK(sm, 12);
     CompSrc cor{mfield(corr, p.cap, 0), mfield(corr, p.cap, 1), mfield(corr, p.cap, 2), mfield(corr, p.cap, 3),
                 mfield(corr, p.cap, 4), (size_t)p.cap, ncorr, p.cfg.birth_cov, ncorr};
     const double clog = eval_map_at_points(p, sm, s, cor, J);
+    PHASE_MARK(sm, 13);
 
     const double setll = phase_set_loglikelihood(p, sm, s, J);
+    PHASE_MARK(sm, 14);
     const double ratio = (plog - pcount) - (clog - ccount);
     const double alpha = exp(setll + ratio);
     parts[0] = alpha; parts[1] = setll; parts[2] = plog; parts[3] = clog; parts[4] = pcount; parts[5] = ccount;

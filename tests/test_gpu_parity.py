@@ -179,6 +179,61 @@ def test_stage_set_loglikelihood_shared_measurements(ctx, orc):
     assert close_rel(got, exp), (got, exp)
 
 
+def _cluster(orc, ocfg, pose, centre, n_lm, n_z, rng, spread_px=2.5, spread_r=0.04):
+    """n_lm landmarks whose predicted measurements fall within a few pixels / centimetres of each other,
+    and n_z measurements around them: one association block of n_lm + n_z rows (PHD:435-436 gate d < 5)."""
+    z0 = orc.measure_perfect(ocfg, pose, centre)
+    lms, zs = [], []
+    for _ in range(n_lm):
+        zz = z0 + rng.normal(size=3) * [spread_px, spread_px, spread_r]
+        lms.append(orc.measure_to_map(ocfg, pose, zz))
+    for _ in range(n_z):
+        zs.append(z0 + rng.normal(size=3) * [spread_px, spread_px, spread_r])
+    return lms, zs
+
+
+def test_stage_set_loglikelihood_murty_lane(ctx, orc):
+    """Blocks with more than five rows: Hungarian + Murty (GC:64-272) and the stale-buffer early exit
+    (PHD:503) across a mix of 2x2, 3-5 row and large blocks."""
+    h, ocfg = ctx["h"], ctx["ocfg"]
+    pose = [0.05, -0.02, 0.01, 0.999, 0.01, -0.02, 0.015]
+    pose = list(pose[:3]) + list(np.array(pose[3:]) / np.linalg.norm(pose[3:]))
+    checked = 0
+    for seed in range(8):
+        rng = np.random.default_rng(100 + seed)
+        lms, zs = [], []
+        layout = [((0.3, 0.2, 3.0), 1, 1), ((-0.8, 0.4, 4.0), 2, 1), ((1.2, -0.6, 6.0), 3 + seed % 3, 3 + seed % 2),
+                  ((-1.5, -0.9, 7.5), 1, 1), ((0.1, 0.9, 5.0), 4, 5), ((2.0, 1.0, 8.0), 2, 2)]
+        rng.shuffle(layout)
+        for centre, nl, nz in layout:
+            a, b = _cluster(orc, ocfg, pose, np.array(centre), nl, nz, rng)
+            lms += a
+            zs += b
+        zs.append([250.0, -200.0, 3.3])   # isolated clutter
+        lms.append([5.0, 5.0, -3.0])      # landmark behind the camera
+        lms, zs = np.array(lms), np.array(zs)
+        exp = orc.set_loglikelihood(ocfg, pose, lms, zs)
+        got = h.stage_set_loglikelihood(pose, lms, zs)
+        assert np.isfinite(exp)
+        assert close_rel(got, exp), (seed, got, exp)
+        checked += 1
+    assert checked == 8
+
+
+def test_stage_set_loglikelihood_dense_random(ctx, orc):
+    h, ocfg = ctx["h"], ctx["ocfg"]
+    pose = [0, 0, 0, 1, 0, 0, 0]
+    for seed in range(6):
+        rng = np.random.default_rng(200 + seed)
+        J, M = 24, 20
+        zc = np.stack([rng.uniform(-40, 40, J), rng.uniform(-30, 30, J), rng.uniform(2.0, 2.6, J)], axis=1)
+        lms = np.array([orc.measure_to_map(ocfg, pose, z) for z in zc])
+        zs = zc[rng.integers(0, J, M)] + rng.normal(size=(M, 3)) * [1.5, 1.5, 0.03]
+        exp = orc.set_loglikelihood(ocfg, pose, lms, zs)
+        got = h.stage_set_loglikelihood(pose, lms, zs)
+        assert close_rel(got, exp), (seed, got, exp)
+
+
 def test_stage_weight_alpha(ctx, orc):
     h, sc, ocfg = ctx["h"], ctx["sc"], ctx["ocfg"]
     fr = sc.next_frame()
@@ -306,7 +361,7 @@ def run_both(capi, orc, synth, P, N, M, frames, seed, only_mapping=False, **over
 
 
 def test_slam_frames_small(capi, orc, synth):
-    nres = run_both(capi, orc, synth, P=12, N=40, M=16, frames=8, seed=21)
+    nres = run_both(capi, orc, synth, P=12, N=40, M=16, frames=8, seed=21, min_effective_particle=0.6)
     assert nres >= 1, "the run must exercise resampling"
 
 

@@ -265,7 +265,7 @@ def test_resample_invariants(orc):
     iters = 10000
     for _ in range(iters):
         u = float(np.float32(rng.random()))
-        w, best, anc, res = orc.normalize_resample(cfg, [0.11, 0.28, 0.31, 0.01, 0.29], u, force=True)
+        w, best, anc, res = orc.normalize_resample(cfg, [0.11, 0.28, 0.31, 0.01, 0.29], u, force=2)   # ResampleParticles() alone
         assert res and np.allclose(w, 0.2)
         assert anc[best] == 2                       # best estimate is particle 2
         assert {1, 2, 4} <= set(anc.tolist())       # weights > 0.2 always survive
