@@ -193,7 +193,7 @@ void make_layout(ScratchLayout& l, int cap, int Mcap, int cap_pairs, int maxq)
     l.cap_top = std::max(1, std::min(maxq, cap));
     l.cap_edges = 8 * l.cap_top + 64;
     l.cap_ll = std::max(8 * Mcap, 1024);
-    l.cap_nodes = std::max(l.cap_pred, l.cap_top) + 2;
+    l.cap_nodes = std::max(std::max(l.cap_pred, l.cap_top), l.cap_j) + 2;
     size_t off = 0;
     auto take = [&](size_t& field, size_t bytes) { field = off; off = align_up(off + bytes, 16); };
     const size_t D = sizeof(double), I = sizeof(int), U = sizeof(unsigned long long);
@@ -210,8 +210,8 @@ void make_layout(ScratchLayout& l, int cap, int Mcap, int cap_pairs, int maxq)
     take(l.gitems, I * l.cap_nodes);
     take(l.jidx, I * l.cap_j);       take(l.jm, 3 * D * l.cap_j);  take(l.jmp, 3 * D * l.cap_j);
     take(l.jpd, D * l.cap_j);        take(l.vsum, D * l.cap_j);
-    take(l.cinv, 9 * D * l.cap_pred); take(l.cnorm, D * l.cap_pred); take(l.crad, D * l.cap_pred);
-    take(l.fat, I * l.cap_nodes);    take(l.clist, I * l.cap_nodes); take(l.gx, 3 * D * l.cap_pred);
+    take(l.cinv, 16); take(l.cnorm, 16); take(l.crad, 16);   // (unused since the component-major Map.Evaluate)
+    take(l.fat, 16);  take(l.clist, 16); take(l.gx, 16);
     take(l.llkey, U * l.cap_ll);     take(l.llval, D * l.cap_ll);
     take(l.uf, I * (l.cap_j + Mcap + 2)); take(l.bcnt, I * (l.cap_j + Mcap + 2));
     take(l.bsum, 16); take(l.bmin, 16); take(l.mslots, murty_workspace_bytes());

@@ -6,10 +6,10 @@
 
 namespace rbphd {
 
-constexpr int kBlock = 256;          // threads per CTA of the per-particle kernels
+constexpr int kBlock = 512;          // threads per CTA of the per-particle kernels (one CTA per SM)
 constexpr int kWarps = kBlock / 32;
-constexpr int kGridMaxDim = 16;      // per-particle cell grid: at most 16^3 cells, offsets in shared memory
-constexpr int kGridMaxCells = kGridMaxDim * kGridMaxDim * kGridMaxDim;
+constexpr int kGridMaxDim = 64;      // cells per axis of a cell grid
+constexpr int kGridMaxCells = 8192;  // cells of a cell grid; the offsets (kGridMaxCells + 1 ints) live in shared memory
 
 struct BlockShared {                 // small fixed scratch in shared memory
     int    warp_i[kWarps + 1];
@@ -181,15 +181,42 @@ __device__ inline void grid_build(BlockShared& sh, CellGrid& g, int* start, int*
             double l = INFINITY, h = -INFINITY;
             for (int w = 0; w < kWarps; w++) { l = fmin(l, sh.warp_d[w]); h = fmax(h, sh.warp_d[kWarps + w]); }
             if (!(l <= h)) { l = 0; h = 0; }
-            double ext = h - l;
-            double mc = mincell3[a];
-            double dd = (mc > 0) ? ceil(ext / mc) : (double)kGridMaxDim;
+            g.org[a] = l; g.hi[a] = h;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // cell edge per axis = mincell * f with the smallest common f >= 1 that keeps the grid within
+        // kGridMaxCells cells (and kGridMaxDim per axis)
+        double ext[3], mc[3];
+        for (int a = 0; a < 3; a++) {
+            ext[a] = g.hi[a] - g.org[a];
+            mc[a] = (mincell3[a] > 0 && mincell3[a] < INFINITY) ? mincell3[a] : ext[a] / 16.0;
+            if (!(mc[a] > 0)) mc[a] = 1.0;
+        }
+        double f = 1.0;
+        for (int it = 0; it < 200; it++) {
+            long cells = 1;
+            bool ok = true;
+            for (int a = 0; a < 3; a++) {
+                double dd = ceil(ext[a] / (mc[a] * f));
+                if (!(dd >= 1.0)) dd = 1.0;
+                if (dd > (double)kGridMaxDim) { ok = false; dd = (double)kGridMaxDim; }
+                cells *= (long)dd;
+            }
+            if (ok && cells <= kGridMaxCells) break;
+            f *= 1.2;
+        }
+        for (int a = 0; a < 3; a++) {
+            double dd = ceil(ext[a] / (mc[a] * f));
             int d = (dd >= (double)kGridMaxDim) ? kGridMaxDim : ((dd >= 1.0) ? (int)dd : 1);
-            double cs = ext / d;
+            double cs = ext[a] / d;
             if (!(cs > 0)) cs = 1.0;
             cs = cs * (1.0 + 1e-12) + 1e-300;
-            g.org[a] = l; g.hi[a] = h; g.dim[a] = d; g.inv[a] = 1.0 / cs;
+            g.dim[a] = d; g.inv[a] = 1.0 / cs;
         }
+        if ((long)g.dim[0] * g.dim[1] * g.dim[2] > kGridMaxCells) { g.dim[0] = g.dim[1] = g.dim[2] = 16; 
+            for (int a = 0; a < 3; a++) { double cs = ext[a] / 16; if (!(cs > 0)) cs = 1.0; g.inv[a] = 1.0 / (cs * (1.0 + 1e-12) + 1e-300); } }
     }
     __syncthreads();
     if (threadIdx.x == 0) { g.ncell = g.dim[0] * g.dim[1] * g.dim[2]; g.n = n; }

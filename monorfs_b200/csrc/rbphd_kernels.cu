@@ -20,8 +20,9 @@ namespace rbphd {
 // shared-memory context of one CTA of k_particle_update
 // ------------------------------------------------------------------------------------------------
 struct Ctx {
-    int N, B, Npred, npairs, npairs_prior, L, ncand, W0, nedges, nout, nF;
+    int N, B, Npred, npairs, npairs_prior, L, ncand, W0, nedges, nout, nF, nU, nsel;
     int status;
+    unsigned long long selkey;
     double pose[7];
     CellGrid grid;
     long long tlast;
@@ -49,7 +50,13 @@ struct Smem {
     int* gstart;     // kGridMaxCells+1
     unsigned long long* skey;   // sort buffer (smem_sort_cap)
     unsigned int* sval;
+    double* vs;      // kVsCap   per-query accumulators of Map.Evaluate
+    double* dens;    // M        exploration density accumulators
+    int* hist;       // 256      radix-select histogram
 };
+
+constexpr int kSortCap = 8192;   // (key,val) pairs the shared-memory sort buffer holds
+constexpr int kVsCap = 4096;
 
 struct Slab {
     // predicted map = prior components followed by births
@@ -260,47 +267,88 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
 
     int B = 0;
     if (do_births) {
-        // A4: measurements not yet known to be explored: exact gated density sum over the prior map,
-        // in component order (MAP:210-220).  One warp per measurement; only components near the frustum.
-        int nF = block_scan_array(sm.sh, s.flagf, N);   // flagf -> exclusive prefix
-        for (int i = tid; i < N; i += kBlock) {
-            int pos = s.flagf[i];
-            int nxt = (i + 1 < N) ? s.flagf[i + 1] : nF;
-            if (nxt > pos) s.fidx[pos] = i;
-        }
+        // A4: measurements not yet known to be explored: gated density sum over the prior map (MAP:210-220).
+        // All terms are >= 0, so the sum taken in any order differs from the reference's in-order sum by
+        // at most n ulps; it decides unless it lands within 1e-9 of the threshold, in which case the
+        // in-order sum is replayed (one warp per measurement).
+        if (tid == 0) sm.ctx.nU = 0;
         __syncthreads();
-        const int lane = tid & 31, warp = tid >> 5;
-        for (int k = warp; k < M; k += kWarps) {
-            if (sm.kflag[k]) continue;
-            const double ck[3] = {sm.cs[3 * k], sm.cs[3 * k + 1], sm.cs[3 * k + 2]};
-            double sum = 0;
-            for (int base = 0; base < nF; base += 32) {
-                int f = base + lane;
-                bool hit = false;
-                double term = 0;
-                if (f < nF) {
-                    int i = s.fidx[f];
-                    double m[3] = {s.pm[i], s.pm[capp + i], s.pm[2 * capp + i]};
-                    double dx = m[0] - ck[0], dy = m[1] - ck[1], dz = m[2] - ck[2];
-                    double d2 = dx * dx + dy * dy + dz * dz;
+        for (int k = tid; k < M; k += kBlock)
+            if (!sm.kflag[k]) { int u = atomicAdd(&sm.ctx.nU, 1); sm.kidx[u] = k; sm.dens[u] = 0.0; }
+        __syncthreads();
+        const int nU = sm.ctx.nU;
+        if (nU > 0) {
+            for (int i = tid; i < N; i += kBlock) {
+                if (!s.flagf[i]) continue;
+                const double m[3] = {s.pm[i], s.pm[capp + i], s.pm[2 * capp + i]};
+                bool have = false;
+                double Pinv[9], wm = 0;
+                for (int u = 0; u < nU; u++) {
+                    const int k = sm.kidx[u];
+                    const double dx = m[0] - sm.cs[3 * k], dy = m[1] - sm.cs[3 * k + 1], dz = m[2] - sm.cs[3 * k + 2];
+                    const double d2 = dx * dx + dy * dy + dz * dz;
                     if (d2 <= c.explore_r2) {
-                        hit = true;
-                        double P[9], Pinv[9];
+                        if (!have) {
+                            double P[9];
 #pragma unroll
-                        for (int a = 0; a < 9; a++) P[a] = mfield(in, p.cap, 4 + a)[i];
-                        double detp = mat3_inv(P, Pinv);
-                        double dc[3] = {ck[0] - m[0], ck[1] - m[1], ck[2] - m[2]};
-                        term = s.pwt[i] * (gauss_mult(detp) * exp(-0.5 * quadform3(Pinv, dc)));
+                            for (int a = 0; a < 9; a++) P[a] = mfield(in, p.cap, 4 + a)[i];
+                            wm = gauss_mult(mat3_inv(P, Pinv));
+                            have = true;
+                        }
+                        const double dc[3] = {sm.cs[3 * k] - m[0], sm.cs[3 * k + 1] - m[1], sm.cs[3 * k + 2] - m[2]};
+                        atomicAdd(&sm.dens[u], s.pwt[i] * (wm * exp(-0.5 * quadform3(Pinv, dc))));
                     }
                 }
-                unsigned mask = __ballot_sync(0xffffffffu, hit);
-                while (mask) {
-                    int l = __ffs(mask) - 1;
-                    sum += __shfl_sync(0xffffffffu, term, l);
-                    mask &= mask - 1;
-                }
             }
-            if (lane == 0 && sum >= c.explore_thr) sm.kflag[k] = 1;
+            __syncthreads();
+            int ambiguous = 0;
+            for (int u = tid; u < nU; u += kBlock) {
+                const double d = sm.dens[u];
+                const int k = sm.kidx[u];
+                if (d >= c.explore_thr * (1.0 + 1e-9)) sm.kflag[k] = 1;
+                else if (d >= c.explore_thr * (1.0 - 1e-9)) { sm.kflag[k] = 2; ambiguous = 1; }
+            }
+            if (__syncthreads_or(ambiguous)) {
+                for (int i = tid; i < N; i += kBlock) s.fidx[i] = s.flagf[i];
+                __syncthreads();
+                const int nF = block_scan_array(sm.sh, s.fidx, N);
+                for (int i = tid; i < N; i += kBlock) if (s.flagf[i]) s.gitems[s.fidx[i]] = i;
+                __syncthreads();
+                const int lane = tid & 31, warp = tid >> 5;
+                for (int k = warp; k < M; k += kWarps) {
+                    if (sm.kflag[k] != 2) continue;
+                    const double ck[3] = {sm.cs[3 * k], sm.cs[3 * k + 1], sm.cs[3 * k + 2]};
+                    double sum = 0;
+                    for (int base = 0; base < nF; base += 32) {
+                        int f = base + lane;
+                        bool hit = false;
+                        double term = 0;
+                        if (f < nF) {
+                            int i = s.gitems[f];
+                            double m[3] = {s.pm[i], s.pm[capp + i], s.pm[2 * capp + i]};
+                            double dx = m[0] - ck[0], dy = m[1] - ck[1], dz = m[2] - ck[2];
+                            double d2 = dx * dx + dy * dy + dz * dz;
+                            if (d2 <= c.explore_r2) {
+                                hit = true;
+                                double P[9], Pinv[9];
+#pragma unroll
+                                for (int a = 0; a < 9; a++) P[a] = mfield(in, p.cap, 4 + a)[i];
+                                double detp = mat3_inv(P, Pinv);
+                                double dc[3] = {ck[0] - m[0], ck[1] - m[1], ck[2] - m[2]};
+                                term = s.pwt[i] * (gauss_mult(detp) * exp(-0.5 * quadform3(Pinv, dc)));
+                            }
+                        }
+                        unsigned mask = __ballot_sync(0xffffffffu, hit);
+                        while (mask) {
+                            int l = __ffs(mask) - 1;
+                            sum += __shfl_sync(0xffffffffu, term, l);
+                            mask &= mask - 1;
+                        }
+                    }
+                    if (lane == 0) sm.kflag[k] = (sum >= c.explore_thr) ? 1 : 0;
+                }
+                __syncthreads();
+            }
         }
         __syncthreads();
 
@@ -450,11 +498,57 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
         }
     }
     __syncthreads();
-    const int nc = sm.ctx.ncand;
+    int nc = sm.ctx.ncand;
+    const int want = min(c.maxq, nc);
+    if (nc > (int)p.smem_sort_cap && want < nc) {
+        // more candidates than the shared-memory sort holds and only the `want` heaviest are needed:
+        // radix-select the want-th key (8 bits per pass), keep every candidate with key <= it
+        unsigned long long prefix = 0;
+        int remaining = want;
+        for (int pass = 0; pass < 8; pass++) {
+            const int shift = 56 - 8 * pass;
+            for (int b = tid; b < 256; b += kBlock) sm.hist[b] = 0;
+            __syncthreads();
+            for (int e = tid; e < nc; e += kBlock) {
+                const unsigned long long key = s.skey[e];
+                if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8)))
+                    atomicAdd(&sm.hist[(int)((key >> shift) & 255)], 1);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int cum = 0, d = 0;
+                for (; d < 256; d++) { if (cum + sm.hist[d] >= remaining) break; cum += sm.hist[d]; }
+                if (d > 255) d = 255;
+                sm.ctx.nsel = remaining - cum;
+                sm.ctx.selkey = prefix | ((unsigned long long)d << shift);
+            }
+            __syncthreads();
+            remaining = sm.ctx.nsel;
+            prefix = sm.ctx.selkey;
+        }
+        if (tid == 0) sm.ctx.nsel = 0;
+        __syncthreads();
+        for (int e = tid; e < nc; e += kBlock) {
+            if (s.skey[e] <= prefix) {
+                int idx = atomicAdd(&sm.ctx.nsel, 1);
+                if (idx < (int)p.smem_sort_cap) { sm.skey[idx] = s.skey[e]; sm.sval[idx] = s.sval[e]; }
+            }
+        }
+        __syncthreads();
+        if (sm.ctx.nsel <= (int)p.smem_sort_cap) {
+            nc = sm.ctx.nsel;
+            const int n2 = next_pow2(nc > 1 ? nc : 1);
+            for (int j = nc + tid; j < n2; j += kBlock) { sm.skey[j] = ~0ull; sm.sval[j] = ~0u; }
+            block_bitonic_sort(sm.skey, sm.sval, n2);
+            // hand the sorted selection over through the same pointers the general path uses
+        }
+    }
+    const bool selected = (nc != sm.ctx.ncand);
     const int nc2 = next_pow2(nc > 1 ? nc : 1);
     unsigned long long* skey = s.skey;
     unsigned int* sval = s.sval;
-    if (nc2 <= (int)p.smem_sort_cap) {
+    if (selected) { skey = sm.skey; sval = sm.sval; }
+    else if (nc2 <= (int)p.smem_sort_cap) {
         for (int j = tid; j < nc2; j += kBlock) {
             sm.skey[j] = (j < nc) ? s.skey[j] : ~0ull;
             sm.sval[j] = (j < nc) ? s.sval[j] : ~0u;
@@ -464,8 +558,10 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
     else {
         for (int j = nc + tid; j < nc2; j += kBlock) { s.skey[j] = ~0ull; s.sval[j] = ~0u; }
     }
-    block_bitonic_sort(skey, sval, nc2);
+    if (!selected) block_bitonic_sort(skey, sval, nc2);
     PHASE_MARK(sm, 6);
+    nc = min(nc, sm.ctx.ncand);
+
     const int W0 = min(min(c.maxq, nc), capw);
     if (tid == 0) { sm.ctx.W0 = W0; if (min(c.maxq, nc) > capw) sm.ctx.status |= ST_OVER_COMPONENTS; }
 
@@ -652,24 +748,45 @@ __device__ __forceinline__ void dump_comp(const KParams& p, int o, double w, con
     for (int a = 0; a < 9; a++) d[(size_t)(4 + a) * dc + o] = P[a];
 }
 
+__host__ __device__ inline size_t carve_offsets(int M, size_t sort_cap, size_t* off_out)
+{
+    // off_out: zs, cs, skey, sval, vs, dens, kflag, kidx, hist, gstart
+    size_t off = (sizeof(Smem) + 15) & ~size_t(15);
+    const int Mc = ((M + 1) & ~1) > 0 ? ((M + 1) & ~1) : 2;
+    off_out[0] = off; off += sizeof(double) * 3 * Mc;
+    off_out[1] = off; off += sizeof(double) * 3 * Mc;
+    off_out[2] = off; off += sizeof(unsigned long long) * sort_cap;
+    off_out[3] = off; off += sizeof(unsigned int) * sort_cap;
+    off_out[4] = off; off += sizeof(double) * kVsCap;
+    off_out[5] = off; off += sizeof(double) * Mc;
+    off_out[6] = off; off += sizeof(int) * (Mc + 2);
+    off_out[7] = off; off += sizeof(int) * (Mc + 2);
+    off_out[8] = off; off += sizeof(int) * 256;
+    off_out[9] = off; off += sizeof(int) * (kGridMaxCells + 1);
+    return (off + 15) & ~size_t(15);
+}
+
 __device__ __forceinline__ void carve_smem(unsigned char* raw, const KParams& p, Smem*& smp)
 {
     smp = reinterpret_cast<Smem*>(raw);
-    size_t off = (sizeof(Smem) + 15) & ~size_t(15);
-    const int Mc = (p.M + 1) & ~1;
-    smp->zs = reinterpret_cast<double*>(raw + off); off += sizeof(double) * 3 * (Mc > 0 ? Mc : 2);
-    smp->cs = reinterpret_cast<double*>(raw + off); off += sizeof(double) * 3 * (Mc > 0 ? Mc : 2);
-    smp->skey = reinterpret_cast<unsigned long long*>(raw + off); off += sizeof(unsigned long long) * p.smem_sort_cap;
-    smp->sval = reinterpret_cast<unsigned int*>(raw + off); off += sizeof(unsigned int) * p.smem_sort_cap;
-    smp->kflag = reinterpret_cast<int*>(raw + off); off += sizeof(int) * (Mc + 2);
-    smp->kidx = reinterpret_cast<int*>(raw + off); off += sizeof(int) * (Mc + 2);
-    smp->gstart = reinterpret_cast<int*>(raw + off);
+    size_t o[10];
+    carve_offsets(p.M, p.smem_sort_cap, o);
+    smp->zs = reinterpret_cast<double*>(raw + o[0]);
+    smp->cs = reinterpret_cast<double*>(raw + o[1]);
+    smp->skey = reinterpret_cast<unsigned long long*>(raw + o[2]);
+    smp->sval = reinterpret_cast<unsigned int*>(raw + o[3]);
+    smp->vs = reinterpret_cast<double*>(raw + o[4]);
+    smp->dens = reinterpret_cast<double*>(raw + o[5]);
+    smp->kflag = reinterpret_cast<int*>(raw + o[6]);
+    smp->kidx = reinterpret_cast<int*>(raw + o[7]);
+    smp->hist = reinterpret_cast<int*>(raw + o[8]);
+    smp->gstart = reinterpret_cast<int*>(raw + o[9]);
 }
 
 // ------------------------------------------------------------------------------------------------
 // the fused per-particle kernel (persistent: CTA b processes particles b, b+grid, ...)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock, 2) k_particle_update(const __grid_constant__ KParams p)
+__global__ void __launch_bounds__(kBlock, 1) k_particle_update(const __grid_constant__ KParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -1034,15 +1151,9 @@ size_t murty_workspace_bytes() { return sizeof(MurtyWork); }
 
 size_t particle_update_smem(int max_measurements, size_t* sort_cap)
 {
-    const int Mc = (max_measurements + 1) & ~1;
-    size_t cap = 4096;
-    if (sort_cap) *sort_cap = cap;
-    size_t off = (sizeof(Smem) + 15) & ~size_t(15);
-    off += sizeof(double) * 3 * (Mc > 0 ? Mc : 2) * 2;
-    off += (sizeof(unsigned long long) + sizeof(unsigned int)) * cap;
-    off += sizeof(int) * (Mc + 2) * 2;
-    off += sizeof(int) * (kGridMaxCells + 1);
-    return (off + 15) & ~size_t(15);
+    if (sort_cap) *sort_cap = kSortCap;
+    size_t o[10];
+    return carve_offsets(max_measurements, kSortCap, o);
 }
 
 int particle_update_max_ctas_per_sm(size_t smem)

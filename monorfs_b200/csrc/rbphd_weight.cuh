@@ -10,8 +10,7 @@ namespace rbphd {
 // Terms of Map.Evaluate with Mahalanobis distance^2 above this are < 2e-22 of the component's peak and
 // are skipped (the reference sums them; the parity bar for weights is 1e-9 relative).
 constexpr double kEvalD2 = 100.0;
-constexpr double kTightRadius = 0.6;
-constexpr double kFatRadius = 2.0;
+constexpr double kQueryCell = 0.5;   // cell edge of the grid over the map-estimate points
 
 struct CompSrc {
     const double* w;
@@ -35,96 +34,71 @@ __device__ __forceinline__ void comp_cov(const CompSrc& c, int i, double* P)
     }
 }
 
-__device__ __forceinline__ double eval_term(const KParams& p, const Slab& s, const CompSrc& c, int i, double x,
-                                            double y, double z)
+// w_i N(x; m_i, P_i) with the inverse recomputed (only used by the rare all-terms fallback)
+__device__ inline double eval_term_full(const CompSrc& c, int i, double x, double y, double z)
 {
-    const int st = p.lay.cap_pred;
-    double Pinv[9];
-#pragma unroll
-    for (int a = 0; a < 9; a++) Pinv[a] = s.cinv[(size_t)a * st + i];
+    double P[9], Pinv[9];
+    comp_cov(c, i, P);
+    double det = mat3_inv(P, Pinv);
     double d[3] = {x - c.mx[i], y - c.my[i], z - c.mz[i]};
-    return c.w[i] * (s.cnorm[i] * exp(-0.5 * quadform3(Pinv, d)));
+    return c.w[i] * (gauss_mult(det) * exp(-0.5 * quadform3(Pinv, d)));
 }
 
-// v[t] = sum_i w_i N(jm_t; m_i, P_i) for the J points in s.jm.  Returns sum_t log v[t].
-__device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, const CompSrc& c, int J)
+// v[t] = sum_i w_i N(jm_t; m_i, P_i) for the J points in s.jm (MAP:192-202), component-major: each thread
+// owns components, looks up the query points inside the component's influence radius in the cell grid
+// over the J points (sm.ctx.grid / sm.gstart / s.gitems, built by the caller) and accumulates into
+// vs[t] with double atomics.  Returns sum_t ln v[t].
+__device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, const CompSrc& c, int J,
+                                     double* vs)
 {
-    const int tid = threadIdx.x, st = p.lay.cap_pred, capj = p.lay.cap_j;
-    // per-component cache: inverse covariance, multiplier, squared influence radius, class
+    const int tid = threadIdx.x, capj = p.lay.cap_j;
+    const double* jx = s.jm; const double* jy = s.jm + capj; const double* jz = s.jm + 2 * capj;
+    const CellGrid& g = sm.ctx.grid;
+    for (int t = tid; t < J; t += kBlock) vs[t] = 0.0;
+    __syncthreads();
     for (int i = tid; i < c.n; i += kBlock) {
         double P[9], Pinv[9];
         comp_cov(c, i, P);
-        double det = mat3_inv(P, Pinv);
-#pragma unroll
-        for (int a = 0; a < 9; a++) s.cinv[(size_t)a * st + i] = Pinv[a];
-        s.cnorm[i] = gauss_mult(det);
-        double tr = P[0] + P[4] + P[8];
+        const double mult = gauss_mult(mat3_inv(P, Pinv));
+        const double w = c.w[i];
+        const double x = c.mx[i], y = c.my[i], z = c.mz[i];
+        const double tr = P[0] + P[4] + P[8];
         double r2 = kEvalD2 * tr * (1.0 + 1e-9);
-        if (!(r2 >= 0)) r2 = INFINITY;   // NaN / negative trace: never cull
-        s.crad[i] = r2;
-        s.fat[i] = (r2 <= kTightRadius * kTightRadius) ? 0 : ((r2 <= kFatRadius * kFatRadius) ? 1 : 2);
-    }
-    for (int t = tid; t < J; t += kBlock) s.vsum[t] = 0.0;
-    __syncthreads();
-
-    const double* jx = s.jm; const double* jy = s.jm + capj; const double* jz = s.jm + 2 * capj;
-    for (int cls = 0; cls < 3; cls++) {
-        // index-ordered list of this class
-        for (int i = tid; i < c.n; i += kBlock) s.nflag[i] = (s.fat[i] == cls) ? 1 : 0;
-        __syncthreads();
-        int ncl = block_scan_array(sm.sh, s.nflag, c.n);
-        for (int i = tid; i < c.n; i += kBlock) {
-            if (s.fat[i] == cls) {
-                int o = s.nflag[i];
-                s.clist[o] = i;
-                s.gx[o] = c.mx[i]; s.gx[st + o] = c.my[i]; s.gx[2 * st + o] = c.mz[i];
-            }
+        bool brute = !(r2 >= 0) || isinf(r2);   // NaN / negative trace: never cull
+        int lo[3], hi[3];
+        if (!brute) {
+            if (!grid_range(g, x, y, z, sqrt(r2), lo, hi)) continue;
+            long cells = (long)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
+            if (cells > 2048) brute = true;
         }
-        __syncthreads();
-        if (ncl == 0) continue;
-        if (cls < 2) {
-            const double cell = (cls == 0) ? kTightRadius : kFatRadius;
-            grid_build(sm.sh, sm.ctx.grid, sm.gstart, s.gitems, s.gx, s.gx + st, s.gx + 2 * st, ncl, cell, cell, cell);
-            const CellGrid& g = sm.ctx.grid;
-            for (int t = tid; t < J; t += kBlock) {
-                const double x = jx[t], y = jy[t], z = jz[t];
-                int lo[3], hi[3];
-                if (!grid_range(g, x, y, z, cell, lo, hi)) continue;
-                double v = s.vsum[t];
-                for (int cz = lo[2]; cz <= hi[2]; cz++)
-                    for (int cy = lo[1]; cy <= hi[1]; cy++) {
-                        int rowc = (cz * g.dim[1] + cy) * g.dim[0];
-                        int b = sm.gstart[rowc + lo[0]], e = sm.gstart[rowc + hi[0] + 1];
-                        for (int q = b; q < e; q++) {
-                            int i = s.clist[s.gitems[q]];
-                            double dx = x - c.mx[i], dy = y - c.my[i], dz = z - c.mz[i];
-                            if (dx * dx + dy * dy + dz * dz <= s.crad[i]) v += eval_term(p, s, c, i, x, y, z);
-                        }
-                    }
-                s.vsum[t] = v;
+        if (brute) {
+            for (int t = 0; t < J; t++) {
+                const double d[3] = {jx[t] - x, jy[t] - y, jz[t] - z};
+                if (!(r2 >= 0) || d[0] * d[0] + d[1] * d[1] + d[2] * d[2] <= r2)
+                    atomicAdd(&vs[t], w * (mult * exp(-0.5 * quadform3(Pinv, d))));
             }
+            continue;
         }
-        else {
-            for (int t = tid; t < J; t += kBlock) {
-                const double x = jx[t], y = jy[t], z = jz[t];
-                double v = s.vsum[t];
-                for (int q = 0; q < ncl; q++) {
-                    int i = s.clist[q];
-                    double dx = x - c.mx[i], dy = y - c.my[i], dz = z - c.mz[i];
-                    if (dx * dx + dy * dy + dz * dz <= s.crad[i]) v += eval_term(p, s, c, i, x, y, z);
+        for (int cz = lo[2]; cz <= hi[2]; cz++)
+            for (int cy = lo[1]; cy <= hi[1]; cy++) {
+                const int rowc = (cz * g.dim[1] + cy) * g.dim[0];
+                const int b = sm.gstart[rowc + lo[0]], e = sm.gstart[rowc + hi[0] + 1];
+                for (int q = b; q < e; q++) {
+                    const int t = s.gitems[q];
+                    const double d[3] = {jx[t] - x, jy[t] - y, jz[t] - z};   // x - Mean (GAUSS:201)
+                    if (d[0] * d[0] + d[1] * d[1] + d[2] * d[2] <= r2)
+                        atomicAdd(&vs[t], w * (mult * exp(-0.5 * quadform3(Pinv, d))));
                 }
-                s.vsum[t] = v;
             }
-        }
-        __syncthreads();
     }
+    __syncthreads();
     // nothing nearby at all: the reference's full sum decides between a denormal and log(0) = -inf
     double lsum = 0;
     for (int t = tid; t < J; t += kBlock) {
-        double v = s.vsum[t];
+        double v = vs[t];
         if (!(v > 0)) {
             v = 0;
-            for (int i = 0; i < c.n; i++) v += eval_term(p, s, c, i, jx[t], jy[t], jz[t]);
+            for (int i = 0; i < c.n; i++) v += eval_term_full(c, i, jx[t], jy[t], jz[t]);
         }
         lsum += log(v);
     }
@@ -484,11 +458,14 @@ __device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const 
     // PHD:381-384: sum_j ln v_pred(m_j), sum_j ln v_corr(m_j)
     CompSrc pred{s.pwt, s.pm, s.pm + capp, s.pm + 2 * capp, mfield(predmap, p.cap, 4), (size_t)p.cap, npriorcov,
                  p.cfg.birth_cov, Npred};
-    const double plog = eval_map_at_points(p, sm, s, pred, J);
+    double* vs = (J <= kVsCap) ? sm.vs : s.vsum;
+    grid_build(sm.sh, sm.ctx.grid, sm.gstart, s.gitems, s.jm, s.jm + capj, s.jm + 2 * capj, J, kQueryCell, kQueryCell,
+               kQueryCell);
+    const double plog = eval_map_at_points(p, sm, s, pred, J, vs);
     PHASE_MARK(sm, 12);
     CompSrc cor{mfield(corr, p.cap, 0), mfield(corr, p.cap, 1), mfield(corr, p.cap, 2), mfield(corr, p.cap, 3),
                 mfield(corr, p.cap, 4), (size_t)p.cap, ncorr, p.cfg.birth_cov, ncorr};
-    const double clog = eval_map_at_points(p, sm, s, cor, J);
+    const double clog = eval_map_at_points(p, sm, s, cor, J, vs);
     PHASE_MARK(sm, 13);
 
     const double setll = phase_set_loglikelihood(p, sm, s, J);
