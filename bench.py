@@ -146,7 +146,7 @@ def run_reference(args, rank, world):
     wl = synth.WORKLOADS[wl_name]
     cores = os.cpu_count() or 1
     # one step = one frame over a bounded particle sample sized for ~1-3 s per step
-    per_pf = {"c4": 0.6, "c2": 0.05, "c3": 8.0, "tiny": 0.001}.get(wl_name, 0.1)
+    per_pf = {"c4": 0.6, "c4s": 0.6, "c2": 0.05, "c3": 8.0, "tiny": 0.001}.get(wl_name, 0.1)
     S = int(max(cores, min(wl["P"], round(2.0 * cores / per_pf))))
     S = max(cores, (S // cores) * cores)
     from oracle import orc
@@ -189,7 +189,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "tiny"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "tiny", "c4s"])
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="frames of the host-buffer pass (default min(steps, 10))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -279,9 +279,10 @@ def main():
         launches = h.kernel_launches - launches0
         ctr = h.counters()
         phases = h.phase_cycles()
+        dbgc = h.debug_counters()
         prof = h.profile_read(steps) if (do_profile and world == 1) else None
         resampled_frames = None
-        res = dict(P=P, N=N, M=M, phases=phases, ms_total=ms, steps=steps, launches=launches, counters=ctr, prof=prof, clocks=clocks,
+        res = dict(P=P, N=N, M=M, phases=phases, dbg=dbgc, ms_total=ms, steps=steps, launches=launches, counters=ctr, prof=prof, clocks=clocks,
                    mean_components=ctr["comps_out"] / max(1, ctr["particle_frames"]),
                    pairs_per_particle_frame=ctr["pairs"] / max(1, ctr["particle_frames"]))
 
@@ -352,7 +353,11 @@ def main():
                     "traffic": None, "algorithmic_bytes_per_launch": per_launch, "kernel_ms": kms,
                     "stage_ms": {k: float(np.mean(prof[:, i])) for i, k in enumerate(capi.Handle.STAGES)}}
         tot = float(sum(main_res["phases"].values())) or 1.0
-        roofline["phase_share"] = {k: round(v / tot, 4) for k, v in main_res["phases"].items()}
+        roofline["phase_share"] = {k: round(v / tot, 4) for k, v in main_res["phases"].items() if v}
+        roofline["events_per_particle"] = {k: round(v / max(1, ctr["particle_frames"]), 1)
+                                           for k, v in main_res["dbg"].items() if v}
+        roofline["phase_kcycles_per_particle"] = {k: round(v / max(1, ctr["particle_frames"]) / 1e3, 1)
+                                                  for k, v in main_res["phases"].items() if v}
         tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
         if os.path.exists(tpath):
             try:
@@ -384,8 +389,8 @@ def main():
                        "steps": main_res["e2e_steps"], "resampling_frames": main_res["e2e_resamples"]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = {"c4": 16, "c2": 160, "tiny": 64}.get(args.workload, 16)
-        nfr = {"c4": 3, "c2": 4, "tiny": 4}.get(args.workload, 2)
+        sample = {"c4": 16, "c4s": 16, "c2": 160, "tiny": 64}.get(args.workload, 16)
+        nfr = {"c4": 3, "c4s": 3, "c2": 4, "tiny": 4}.get(args.workload, 2)
         line["cpu_baseline"] = cpu_baseline(args.workload, sample, nfr, synth.SEED)
 
     if not args.no_secondary and args.workload == "c4" and world == 1:

@@ -180,8 +180,9 @@ int rbphd_profile_read(rbphd_navigator* nav, double* ms, int max_frames, int* fr
 /* device-side work counters since the last reset: prior components read, pruned components written,
  * gated (component, measurement) pairs evaluated, particle-frames processed */
 int rbphd_get_counters(rbphd_navigator* nav, int64_t out4[4], int reset);
-/* SM cycles per internal phase of the fused kernel, summed over CTAs (diagnostic; 16 entries) */
-int rbphd_get_phase_cycles(rbphd_navigator* nav, int64_t out16[16]);
+/* diagnostics: SM cycles per internal phase of the fused kernel summed over CTAs (32 entries) followed
+ * by 16 event counters */
+int rbphd_get_phase_cycles(rbphd_navigator* nav, int64_t out48[48]);
 void* rbphd_stream(rbphd_navigator* nav);   /* cudaStream_t of the handle, for event timing by the host */
 
 #ifdef __cplusplus

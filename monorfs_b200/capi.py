@@ -349,12 +349,23 @@ class Handle:
     PHASES = ("A1 meas->map", "A2 prior comps+gate", "A3 prior pairs", "A4-5 explore+births", "A6-7 birth comps+pairs",
               "A8-9 pair sort+weights", "B1 candidate sort", "B2 materialise", "B3 grid+edges", "B4-5 resolve",
               "B6 merge+write", "C1-3 map estimate", "C4 eval predicted", "C4 eval corrected", "C5 set likelihood",
-              "tail")
+              "tail", "A4a undecided list", "A4b density accumulate", "A4c decide", "B3a merge grid build",
+              "C4a zero", "C4b accumulate", "C4c log-sum", "C3b query grid build", "C5a gate edges", "C5b components",
+              "C5c edge sort", "x27", "x28", "x29", "x30", "x31")
+
+    DEBUG_COUNTERS = ("undecided measurements", "explore hits", "explore active comps", "merge edges", "W0",
+                      "candidates", "eval candidates", "eval hits", "eval cell rows", "likelihood edges", "J",
+                      "murty blocks", "d12", "d13", "d14", "d15")
 
     def phase_cycles(self):
-        out = (C.c_int64 * 16)()
+        out = (C.c_int64 * 48)()
         self._ck(self.lib.rbphd_get_phase_cycles(self._h, out))
         return {k: int(out[i]) for i, k in enumerate(self.PHASES)}
+
+    def debug_counters(self):
+        out = (C.c_int64 * 48)()
+        self._ck(self.lib.rbphd_get_phase_cycles(self._h, out))
+        return {k: int(out[32 + i]) for i, k in enumerate(self.DEBUG_COUNTERS)}
 
     @property
     def kernel_launches(self):

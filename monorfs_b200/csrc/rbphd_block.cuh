@@ -6,7 +6,7 @@
 
 namespace rbphd {
 
-constexpr int kBlock = 512;          // threads per CTA of the per-particle kernels (one CTA per SM)
+constexpr int kBlock = 1024;         // threads per CTA of the per-particle kernels (one CTA per SM)
 constexpr int kWarps = kBlock / 32;
 constexpr int kGridMaxDim = 64;      // cells per axis of a cell grid
 constexpr int kGridMaxCells = 8192;  // cells of a cell grid; the offsets (kGridMaxCells + 1 ints) live in shared memory
@@ -99,9 +99,9 @@ __device__ inline void block_bitonic_sort(unsigned long long* key, unsigned int*
 {
     __syncthreads();
     for (int k = 2; k <= n; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int j = k >> 1, lj = 31 - __clz(k >> 1); j > 0; j >>= 1, lj--) {
             for (int t = threadIdx.x; t < (n >> 1); t += kBlock) {
-                int i = ((t / j) * (j << 1)) + (t % j);
+                int i = ((t >> lj) << (lj + 1)) + (t & (j - 1));
                 int p = i + j;
                 bool asc = ((i & k) == 0);
                 unsigned long long ki = key[i], kp = key[p];
@@ -115,6 +115,52 @@ __device__ inline void block_bitonic_sort(unsigned long long* key, unsigned int*
             __syncthreads();
         }
     }
+}
+
+// Keep the `want` smallest (key, then val) of n candidates when n exceeds what a later sort can hold:
+// radix-select the want-th key (8 bits per pass, histogram in shared memory) and copy every candidate
+// with key <= it to (okey, oval).  Returns the number copied (>= want; more only on ties), or -1 if it
+// would exceed ocap (nothing useful copied).  hist: 256 ints of shared memory, scratch2: 2 ints.
+__device__ inline int block_select_smallest(const unsigned long long* key, const unsigned int* val, int n,
+                                            int want, unsigned long long* okey, unsigned int* oval, int ocap,
+                                            int* hist, int* scratch2, unsigned long long* selkey)
+{
+    unsigned long long prefix = 0;
+    int remaining = want;
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = 56 - 8 * pass;
+        for (int b = threadIdx.x; b < 256; b += kBlock) hist[b] = 0;
+        __syncthreads();
+        for (int e = threadIdx.x; e < n; e += kBlock) {
+            const unsigned long long kk = key[e];
+            if (pass == 0 || (kk >> (shift + 8)) == (prefix >> (shift + 8)))
+                atomicAdd(&hist[(int)((kk >> shift) & 255)], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int cum = 0, d = 0;
+            for (; d < 256; d++) { if (cum + hist[d] >= remaining) break; cum += hist[d]; }
+            if (d > 255) d = 255;
+            scratch2[0] = remaining - cum;
+            *selkey = prefix | ((unsigned long long)d << shift);
+        }
+        __syncthreads();
+        remaining = scratch2[0];
+        prefix = *selkey;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) scratch2[1] = 0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < n; e += kBlock) {
+        if (key[e] <= prefix) {
+            int idx = atomicAdd(&scratch2[1], 1);
+            if (idx < ocap) { okey[idx] = key[e]; oval[idx] = val[e]; }
+        }
+    }
+    __syncthreads();
+    int cnt = scratch2[1];
+    __syncthreads();
+    return (cnt <= ocap) ? cnt : -1;
 }
 
 // first index in sorted key[0..n) with key >= k
@@ -156,7 +202,7 @@ __device__ __forceinline__ int grid_cell(const CellGrid& g, double x, double y, 
 // kGridMaxCells + 1 ints of shared memory; items n ints.
 __device__ inline void grid_build(BlockShared& sh, CellGrid& g, int* start, int* items, const double* px,
                                   const double* py, const double* pz, int n, double mincell0,
-                                  double mincell1, double mincell2)
+                                  double mincell1, double mincell2, int maxcells = kGridMaxCells)
 {
     const double mincell3[3] = {mincell0, mincell1, mincell2};
     // bounding box
@@ -204,7 +250,7 @@ __device__ inline void grid_build(BlockShared& sh, CellGrid& g, int* start, int*
                 if (dd > (double)kGridMaxDim) { ok = false; dd = (double)kGridMaxDim; }
                 cells *= (long)dd;
             }
-            if (ok && cells <= kGridMaxCells) break;
+            if (ok && cells <= maxcells) break;
             f *= 1.2;
         }
         for (int a = 0; a < 3; a++) {
@@ -215,8 +261,8 @@ __device__ inline void grid_build(BlockShared& sh, CellGrid& g, int* start, int*
             cs = cs * (1.0 + 1e-12) + 1e-300;
             g.dim[a] = d; g.inv[a] = 1.0 / cs;
         }
-        if ((long)g.dim[0] * g.dim[1] * g.dim[2] > kGridMaxCells) { g.dim[0] = g.dim[1] = g.dim[2] = 16; 
-            for (int a = 0; a < 3; a++) { double cs = ext[a] / 16; if (!(cs > 0)) cs = 1.0; g.inv[a] = 1.0 / (cs * (1.0 + 1e-12) + 1e-300); } }
+        if ((long)g.dim[0] * g.dim[1] * g.dim[2] > maxcells) { g.dim[0] = g.dim[1] = g.dim[2] = (maxcells >= 4096) ? 16 : 4; 
+            for (int a = 0; a < 3; a++) { double cs = ext[a] / g.dim[a]; if (!(cs > 0)) cs = 1.0; g.inv[a] = 1.0 / (cs * (1.0 + 1e-12) + 1e-300); } }
     }
     __syncthreads();
     if (threadIdx.x == 0) { g.ncell = g.dim[0] * g.dim[1] * g.dim[2]; g.n = n; }

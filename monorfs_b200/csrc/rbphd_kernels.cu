@@ -20,14 +20,16 @@ namespace rbphd {
 // shared-memory context of one CTA of k_particle_update
 // ------------------------------------------------------------------------------------------------
 struct Ctx {
-    int N, B, Npred, npairs, npairs_prior, L, ncand, W0, nedges, nout, nF, nU, nsel;
+    int N, B, Npred, npairs, npairs_prior, L, ncand, W0, nedges, nout, nF, nU, nsel, nsel2;
     int status;
     unsigned long long selkey;
     double pose[7];
     CellGrid grid;
     long long tlast;
-    unsigned long long tphase[16];
+    unsigned long long tphase[32];
+    unsigned int dbg[16];
 };
+#define DBG_ADD(sm, idx, v) atomicAdd(&(sm).ctx.dbg[idx], (unsigned int)(v))
 
 // phase timer: thread 0 attributes the cycles since the previous mark to phase `ph`
 #define PHASE_MARK(sm, ph)                                                   \
@@ -121,6 +123,35 @@ __device__ __forceinline__ void load_pred(const KParams& p, const Slab& s, const
     else {
 #pragma unroll
         for (int a = 0; a < 9; a++) P[a] = p.cfg.birth_cov[a];
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// enumerate -> compact -> process.  Thread-per-item loops whose inner trip count depends on the data
+// run at a few active lanes per warp; so the enumeration only tests and appends (a, b) pairs to a list in
+// shared memory (the idle sort buffer) and the expensive per-pair arithmetic then runs densely, one
+// thread per pair.  Items are taken kBlock at a time; pairs beyond the list capacity are processed
+// inline by the enumerating thread.
+// ------------------------------------------------------------------------------------------------
+template <class Enum, class Proc>
+__device__ __forceinline__ void enumerate_then_process(Smem& sm, int n_items, uint2* list, int list_cap, Enum enumerate,
+                                                       Proc process)
+{
+    for (int base = 0; base < n_items; base += kBlock) {
+        if (threadIdx.x == 0) sm.ctx.nsel2 = 0;
+        __syncthreads();
+        const int i = base + threadIdx.x;
+        if (i < n_items)
+            enumerate(i, [&](int a, int b) {
+                const int idx = atomicAdd(&sm.ctx.nsel2, 1);
+                if (idx < list_cap) list[idx] = make_uint2((unsigned)a, (unsigned)b);
+                else process(a, b);
+            });
+        __syncthreads();
+        const int cnt = min(sm.ctx.nsel2, list_cap);
+        for (int e = threadIdx.x; e < cnt; e += kBlock) process((int)list[e].x, (int)list[e].y);
+        __syncthreads();
     }
 }
 
@@ -235,7 +266,6 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
 
     PHASE_MARK(sm, 0);
     // A2: prior components: miss-detection weight (PHD:837-840), gate lookup, frustum flag
-    const CellGrid& vg = p.vgrid->g;
     for (int i = tid; i < N; i += kBlock) {
         double w = mfield(in, p.cap, 0)[i];
         double m[3] = {mfield(in, p.cap, 1)[i], mfield(in, p.cap, 2)[i], mfield(in, p.cap, 3)[i]};
@@ -249,8 +279,6 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         s.ppd[i] = pdi;
         s.pwmd[i] = (1 - pdi) * w;
         if (do_correct) gate_append(p, sm, s, i, m, local);
-        int lo[3], hi[3];
-        s.flagf[i] = (do_births && M > 0 && grid_range(vg, local.x, local.y, local.z, c.explore_r + 1e-9, lo, hi)) ? 1 : 0;
     }
     __syncthreads();
     if (tid == 0) {
@@ -274,33 +302,62 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         if (tid == 0) sm.ctx.nU = 0;
         __syncthreads();
         for (int k = tid; k < M; k += kBlock)
-            if (!sm.kflag[k]) { int u = atomicAdd(&sm.ctx.nU, 1); sm.kidx[u] = k; sm.dens[u] = 0.0; }
+            if (!sm.kflag[k]) { int u = atomicAdd(&sm.ctx.nU, 1); sm.kidx[u] = k; }
         __syncthreads();
         const int nU = sm.ctx.nU;
+        if (tid == 0) sm.ctx.dbg[0] += nU;
+        PHASE_MARK(sm, 16);
         if (nU > 0) {
-            for (int i = tid; i < N; i += kBlock) {
-                if (!s.flagf[i]) continue;
-                const double m[3] = {s.pm[i], s.pm[capp + i], s.pm[2 * capp + i]};
-                bool have = false;
-                double Pinv[9], wm = 0;
-                for (int u = 0; u < nU; u++) {
-                    const int k = sm.kidx[u];
-                    const double dx = m[0] - sm.cs[3 * k], dy = m[1] - sm.cs[3 * k + 1], dz = m[2] - sm.cs[3 * k + 2];
-                    const double d2 = dx * dx + dy * dy + dz * dz;
-                    if (d2 <= c.explore_r2) {
-                        if (!have) {
-                            double P[9];
-#pragma unroll
-                            for (int a = 0; a < 9; a++) P[a] = mfield(in, p.cap, 4 + a)[i];
-                            wm = gauss_mult(mat3_inv(P, Pinv));
-                            have = true;
-                        }
-                        const double dc[3] = {sm.cs[3 * k] - m[0], sm.cs[3 * k + 1] - m[1], sm.cs[3 * k + 2] - m[2]};
-                        atomicAdd(&sm.dens[u], s.pwt[i] * (wm * exp(-0.5 * quadform3(Pinv, dc))));
-                    }
-                }
+            // small cell grid over the undecided measurement points (cell = explore radius); every prior
+            // component then visits only the points in its 3x3x3 neighbourhood.  Partial sums go to the
+            // slab with native FP64 global atomics (shared-memory FP64 atomics are CAS loops).
+            double* ux = reinterpret_cast<double*>(sm.skey);
+            double* uy = ux + nU;
+            double* uz = uy + nU;
+            int* uitems = reinterpret_cast<int*>(uz + nU);
+            for (int u = tid; u < nU; u += kBlock) {
+                const int k = sm.kidx[u];
+                ux[u] = sm.cs[3 * k]; uy[u] = sm.cs[3 * k + 1]; uz[u] = sm.cs[3 * k + 2];
+                s.vsum[u] = 0.0;
             }
             __syncthreads();
+            grid_build(sm.sh, sm.ctx.grid, sm.gstart, uitems, ux, uy, uz, nU, c.explore_r, c.explore_r, c.explore_r, 512);
+            const CellGrid& g = sm.ctx.grid;
+            // the point arrays live in the first 28 * nU bytes of the sort buffer; the pair list behind them
+            const int list_off = (28 * nU + 15) / 16 * 2;   // in uint2 units, rounded to 16 bytes
+            uint2* hits = reinterpret_cast<uint2*>(sm.skey) + list_off;
+            const int hits_cap = (int)p.smem_sort_cap - list_off;
+            enumerate_then_process(
+                sm, N, hits, hits_cap,
+                [&](int i, auto emit) {
+                    const double m[3] = {s.pm[i], s.pm[capp + i], s.pm[2 * capp + i]};
+                    int lo[3], hi[3];
+                    if (!grid_range(g, m[0], m[1], m[2], c.explore_r + 1e-9, lo, hi)) return;
+                    for (int cz = lo[2]; cz <= hi[2]; cz++)
+                        for (int cy = lo[1]; cy <= hi[1]; cy++) {
+                            const int rowc = (cz * g.dim[1] + cy) * g.dim[0];
+                            const int qb = sm.gstart[rowc + lo[0]], qe = sm.gstart[rowc + hi[0] + 1];
+                            for (int q = qb; q < qe; q++) {
+                                const int u = uitems[q];
+                                const double dx = m[0] - ux[u], dy = m[1] - uy[u], dz = m[2] - uz[u];
+                                if (dx * dx + dy * dy + dz * dz <= c.explore_r2) emit(i, u);
+                            }
+                        }
+                },
+                [&](int ci, int u) {
+                    const double m[3] = {s.pm[ci], s.pm[capp + ci], s.pm[2 * capp + ci]};
+                    double P[9], Pinv[9];
+#pragma unroll
+                    for (int a = 0; a < 9; a++) P[a] = mfield(in, p.cap, 4 + a)[ci];
+                    const double wm = gauss_mult(mat3_inv(P, Pinv));
+                    const double dc[3] = {ux[u] - m[0], uy[u] - m[1], uz[u] - m[2]};
+                    atomicAdd(&s.vsum[u], s.pwt[ci] * (wm * exp(-0.5 * quadform3(Pinv, dc))));
+                    DBG_ADD(sm, 1, 1);
+                });
+            __syncthreads();
+            for (int u = tid; u < nU; u += kBlock) sm.dens[u] = s.vsum[u];
+            __syncthreads();
+            PHASE_MARK(sm, 17);
             int ambiguous = 0;
             for (int u = tid; u < nU; u += kBlock) {
                 const double d = sm.dens[u];
@@ -309,11 +366,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
                 else if (d >= c.explore_thr * (1.0 - 1e-9)) { sm.kflag[k] = 2; ambiguous = 1; }
             }
             if (__syncthreads_or(ambiguous)) {
-                for (int i = tid; i < N; i += kBlock) s.fidx[i] = s.flagf[i];
-                __syncthreads();
-                const int nF = block_scan_array(sm.sh, s.fidx, N);
-                for (int i = tid; i < N; i += kBlock) if (s.flagf[i]) s.gitems[s.fidx[i]] = i;
-                __syncthreads();
+                const int nF = N;
                 const int lane = tid & 31, warp = tid >> 5;
                 for (int k = warp; k < M; k += kWarps) {
                     if (sm.kflag[k] != 2) continue;
@@ -324,7 +377,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
                         bool hit = false;
                         double term = 0;
                         if (f < nF) {
-                            int i = s.gitems[f];
+                            int i = f;
                             double m[3] = {s.pm[i], s.pm[capp + i], s.pm[2 * capp + i]};
                             double dx = m[0] - ck[0], dy = m[1] - ck[1], dz = m[2] - ck[2];
                             double d2 = dx * dx + dy * dy + dz * dz;
@@ -352,6 +405,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         }
         __syncthreads();
 
+        PHASE_MARK(sm, 18);
         // A5: births in measurement order (PHD:806-816)
         for (int k = tid; k < M; k += kBlock) sm.kidx[k] = sm.kflag[k] ? 0 : 1;
         __syncthreads();
@@ -393,32 +447,64 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
     __syncthreads();
 
     PHASE_MARK(sm, 4);
-    // A8: order the pairs by (measurement, component): the reference's output order (PHD:881-903)
+    // A8: order the pairs by (measurement, component) -- the reference's output order (PHD:881-903):
+    // counting sort by measurement, then each measurement's short segment by component index
     const int np = sm.ctx.npairs;
-    const int np2 = next_pow2(np > 1 ? np : 1);
-    unsigned long long* skey = (np2 <= (int)p.smem_sort_cap) ? sm.skey : s.skey;
-    unsigned int* sval = (np2 <= (int)p.smem_sort_cap) ? sm.sval : s.sval;
-    for (int j = tid; j < np2; j += kBlock) {
-        skey[j] = (j < np) ? s.pkey[j] : ~0ull;
-        sval[j] = (j < np) ? (unsigned)j : ~0u;
+    int* segstart = sm.kidx;   // M + 1 (free after the births)
+    int* cursor = sm.kflag;    // M
+    for (int k = tid; k <= M; k += kBlock) segstart[k] = 0;
+    __syncthreads();
+    for (int j = tid; j < np; j += kBlock) atomicAdd(&segstart[(int)(s.pkey[j] >> 32)], 1);
+    __syncthreads();
+    block_scan_array(sm.sh, segstart, M + 1);
+    for (int k = tid; k < M; k += kBlock) cursor[k] = segstart[k];
+    __syncthreads();
+    for (int j = tid; j < np; j += kBlock) {
+        int pos = atomicAdd(&cursor[(int)(s.pkey[j] >> 32)], 1);
+        s.bidx[pos] = j;
     }
-    block_bitonic_sort(skey, sval, np2);
-
-    // A9: per measurement: weightsum in component order, then the detection weights (PHD:886-902)
+    __syncthreads();
+    // A9: per measurement: component order, weightsum, then the detection weights (PHD:886-902).
+    // The segments are sorted on a shared-memory copy (component index, pair slot).
+    unsigned int* scomp = reinterpret_cast<unsigned int*>(sm.skey);   // np <= 2 * kSortCap entries
+    unsigned int* sslot = sm.sval;
+    const bool in_smem = np <= (int)p.smem_sort_cap;
+    if (in_smem) {
+        for (int t = tid; t < np; t += kBlock) {
+            const int j = s.bidx[t];
+            scomp[t] = (unsigned)(s.pkey[j] & 0xffffffffu);
+            sslot[t] = (unsigned)j;
+        }
+        __syncthreads();
+    }
     for (int k = tid; k < M; k += kBlock) {
-        int b = lower_bound_u64(skey, np, (unsigned long long)k << 32);
-        int e = lower_bound_u64(skey, np, (unsigned long long)(k + 1) << 32);
+        const int b = segstart[k], e = segstart[k + 1];
+        if (in_smem) {
+            for (int a = b + 1; a < e; a++) {
+                const unsigned vc = scomp[a], vs = sslot[a];
+                int q = a - 1;
+                while (q >= b && scomp[q] > vc) { scomp[q + 1] = scomp[q]; sslot[q + 1] = sslot[q]; q--; }
+                scomp[q + 1] = vc; sslot[q + 1] = vs;
+            }
+            for (int t = b; t < e; t++) s.bidx[t] = (int)sslot[t];
+        }
+        else {
+            for (int a = b + 1; a < e; a++) {
+                const int v = s.bidx[a];
+                const unsigned vi = (unsigned)(s.pkey[v] & 0xffffffffu);
+                int q = a - 1;
+                while (q >= b && (unsigned)(s.pkey[s.bidx[q]] & 0xffffffffu) > vi) { s.bidx[q + 1] = s.bidx[q]; q--; }
+                s.bidx[q + 1] = v;
+            }
+        }
         double ws = 0;
-        for (int t = b; t < e; t++) ws += s.pt[sval[t]];
+        for (int t = b; t < e; t++) ws += s.pt[s.bidx[t]];
         for (int t = b; t < e; t++) {
-            double wv = s.pt[sval[t]] / (c.clutter + ws);
+            double wv = s.pt[s.bidx[t]] / (c.clutter + ws);
             if (wv != wv) wv = 0;   // GAUSS:154
             s.pwgt[t] = wv;
         }
     }
-    __syncthreads();
-    // keep the permutation (sorted position -> pair slot) in the slab for the later phases
-    for (int j = tid; j < np; j += kBlock) s.bidx[j] = (int)sval[j];
     __syncthreads();
     if (tid == 0) sm.ctx.L = Npred + np;
     __syncthreads();
@@ -501,46 +587,14 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
     int nc = sm.ctx.ncand;
     const int want = min(c.maxq, nc);
     if (nc > (int)p.smem_sort_cap && want < nc) {
-        // more candidates than the shared-memory sort holds and only the `want` heaviest are needed:
-        // radix-select the want-th key (8 bits per pass), keep every candidate with key <= it
-        unsigned long long prefix = 0;
-        int remaining = want;
-        for (int pass = 0; pass < 8; pass++) {
-            const int shift = 56 - 8 * pass;
-            for (int b = tid; b < 256; b += kBlock) sm.hist[b] = 0;
-            __syncthreads();
-            for (int e = tid; e < nc; e += kBlock) {
-                const unsigned long long key = s.skey[e];
-                if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8)))
-                    atomicAdd(&sm.hist[(int)((key >> shift) & 255)], 1);
-            }
-            __syncthreads();
-            if (tid == 0) {
-                int cum = 0, d = 0;
-                for (; d < 256; d++) { if (cum + sm.hist[d] >= remaining) break; cum += sm.hist[d]; }
-                if (d > 255) d = 255;
-                sm.ctx.nsel = remaining - cum;
-                sm.ctx.selkey = prefix | ((unsigned long long)d << shift);
-            }
-            __syncthreads();
-            remaining = sm.ctx.nsel;
-            prefix = sm.ctx.selkey;
-        }
-        if (tid == 0) sm.ctx.nsel = 0;
-        __syncthreads();
-        for (int e = tid; e < nc; e += kBlock) {
-            if (s.skey[e] <= prefix) {
-                int idx = atomicAdd(&sm.ctx.nsel, 1);
-                if (idx < (int)p.smem_sort_cap) { sm.skey[idx] = s.skey[e]; sm.sval[idx] = s.sval[e]; }
-            }
-        }
-        __syncthreads();
-        if (sm.ctx.nsel <= (int)p.smem_sort_cap) {
-            nc = sm.ctx.nsel;
+        // more candidates than the shared-memory sort holds and only the `want` heaviest are needed
+        int cnt = block_select_smallest(s.skey, s.sval, nc, want, sm.skey, sm.sval, (int)p.smem_sort_cap, sm.hist,
+                                        &sm.ctx.nsel, &sm.ctx.selkey);
+        if (cnt >= 0) {
+            nc = cnt;
             const int n2 = next_pow2(nc > 1 ? nc : 1);
             for (int j = nc + tid; j < n2; j += kBlock) { sm.skey[j] = ~0ull; sm.sval[j] = ~0u; }
             block_bitonic_sort(sm.skey, sm.sval, n2);
-            // hand the sorted selection over through the same pointers the general path uses
         }
     }
     const bool selected = (nc != sm.ctx.ncand);
@@ -590,6 +644,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
     double mincell = 2.0 * rmean;
     grid_build(sm.sh, sm.ctx.grid, sm.gstart, s.gitems, tx, ty, tz, W0, mincell, mincell, mincell);
     const double t2 = c.merge_t * c.merge_t;
+    PHASE_MARK(sm, 19);
     for (int pass = 0; pass < 2; pass++) {
         for (int r = tid; r < W0; r += kBlock) {
             double P[9], Pinv[9];
@@ -623,7 +678,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
             if (tid == 0) s.ecnt[W0] = 0;
             __syncthreads();
             int ne = block_scan_array(sm.sh, s.ecnt, W0 + 1);
-            if (tid == 0) { sm.ctx.nedges = ne; if (ne > p.lay.cap_edges) sm.ctx.status |= ST_OVER_EDGES; }
+            if (tid == 0) { sm.ctx.nedges = ne; sm.ctx.dbg[3] += ne; sm.ctx.dbg[4] += W0; sm.ctx.dbg[5] += sm.ctx.ncand; if (ne > p.lay.cap_edges) sm.ctx.status |= ST_OVER_EDGES; }
             __syncthreads();
         }
     }
@@ -831,7 +886,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_particle_update(const __grid_cons
     }
 
     unsigned long long acc_in = 0, acc_out = 0, acc_pairs = 0, acc_pf = 0;   // thread 0 only
-    if (tid == 0) { for (int a = 0; a < 16; a++) sm.ctx.tphase[a] = 0; sm.ctx.tlast = clock64(); }
+    if (tid == 0) { for (int a = 0; a < 32; a++) sm.ctx.tphase[a] = 0; for (int a = 0; a < 16; a++) sm.ctx.dbg[a] = 0; sm.ctx.tlast = clock64(); }
     for (int particle = p.first + blockIdx.x; particle < p.first + p.P; particle += gridDim.x) {
         const double* in = p.maps[cur] + (size_t)particle * kFields * p.cap;
         double* out = p.maps[1 - cur] + (size_t)particle * kFields * p.cap;
@@ -933,7 +988,8 @@ __global__ void __launch_bounds__(kBlock, 1) k_particle_update(const __grid_cons
     if (tid == 0 && p.mode == MODE_FRAME) {
         atomicAdd(&p.st->comps_in, acc_in); atomicAdd(&p.st->comps_out, acc_out);
         atomicAdd(&p.st->pairs, acc_pairs); atomicAdd(&p.st->particle_frames, acc_pf);
-        for (int a = 0; a < 16; a++) atomicAdd(&p.st->phase_cycles[a], sm.ctx.tphase[a]);
+        for (int a = 0; a < 32; a++) atomicAdd(&p.st->phase_cycles[a], sm.ctx.tphase[a]);
+        for (int a = 0; a < 16; a++) atomicAdd(&p.st->dbg[a], (unsigned long long)sm.ctx.dbg[a]);
     }
 }
 

@@ -56,42 +56,51 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
     const CellGrid& g = sm.ctx.grid;
     for (int t = tid; t < J; t += kBlock) vs[t] = 0.0;
     __syncthreads();
-    for (int i = tid; i < c.n; i += kBlock) {
+    PHASE_MARK(sm, 20);
+    auto term_into = [&](int i, int t) {   // w_i N(jm_t; m_i, P_i) -> vs[t]
         double P[9], Pinv[9];
         comp_cov(c, i, P);
         const double mult = gauss_mult(mat3_inv(P, Pinv));
-        const double w = c.w[i];
-        const double x = c.mx[i], y = c.my[i], z = c.mz[i];
-        const double tr = P[0] + P[4] + P[8];
-        double r2 = kEvalD2 * tr * (1.0 + 1e-9);
-        bool brute = !(r2 >= 0) || isinf(r2);   // NaN / negative trace: never cull
-        int lo[3], hi[3];
-        if (!brute) {
-            if (!grid_range(g, x, y, z, sqrt(r2), lo, hi)) continue;
-            long cells = (long)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
-            if (cells > 2048) brute = true;
-        }
-        if (brute) {
-            for (int t = 0; t < J; t++) {
-                const double d[3] = {jx[t] - x, jy[t] - y, jz[t] - z};
-                if (!(r2 >= 0) || d[0] * d[0] + d[1] * d[1] + d[2] * d[2] <= r2)
-                    atomicAdd(&vs[t], w * (mult * exp(-0.5 * quadform3(Pinv, d))));
+        const double d[3] = {jx[t] - c.mx[i], jy[t] - c.my[i], jz[t] - c.mz[i]};   // x - Mean (GAUSS:201)
+        atomicAdd(&vs[t], c.w[i] * (mult * exp(-0.5 * quadform3(Pinv, d))));
+    };
+    enumerate_then_process(
+        sm, c.n, reinterpret_cast<uint2*>(sm.skey), (int)p.smem_sort_cap,
+        [&](int i, auto emit) {
+            const double x = c.mx[i], y = c.my[i], z = c.mz[i];
+            // trace of the covariance without loading the off-diagonal terms
+            const double tr = ((i < c.ncov) ? c.cov[i] : c.defcov[0]) +
+                              ((i < c.ncov) ? c.cov[(size_t)4 * c.covstride + i] : c.defcov[4]) +
+                              ((i < c.ncov) ? c.cov[(size_t)8 * c.covstride + i] : c.defcov[8]);
+            double r2 = kEvalD2 * tr * (1.0 + 1e-9);
+            bool brute = !(r2 >= 0) || isinf(r2);   // NaN / negative trace: never cull
+            int lo[3], hi[3];
+            if (!brute) {
+                if (!grid_range(g, x, y, z, sqrt(r2), lo, hi)) return;
+                long cells = (long)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
+                if (cells > 2048) brute = true;
             }
-            continue;
-        }
-        for (int cz = lo[2]; cz <= hi[2]; cz++)
-            for (int cy = lo[1]; cy <= hi[1]; cy++) {
-                const int rowc = (cz * g.dim[1] + cy) * g.dim[0];
-                const int b = sm.gstart[rowc + lo[0]], e = sm.gstart[rowc + hi[0] + 1];
-                for (int q = b; q < e; q++) {
-                    const int t = s.gitems[q];
-                    const double d[3] = {jx[t] - x, jy[t] - y, jz[t] - z};   // x - Mean (GAUSS:201)
-                    if (d[0] * d[0] + d[1] * d[1] + d[2] * d[2] <= r2)
-                        atomicAdd(&vs[t], w * (mult * exp(-0.5 * quadform3(Pinv, d))));
+            if (brute) {
+                for (int t = 0; t < J; t++) {
+                    const double dx = jx[t] - x, dy = jy[t] - y, dz = jz[t] - z;
+                    if (!(r2 >= 0) || dx * dx + dy * dy + dz * dz <= r2) emit(i, t);
                 }
+                return;
             }
-    }
+            for (int cz = lo[2]; cz <= hi[2]; cz++)
+                for (int cy = lo[1]; cy <= hi[1]; cy++) {
+                    const int rowc = (cz * g.dim[1] + cy) * g.dim[0];
+                    const int b = sm.gstart[rowc + lo[0]], e = sm.gstart[rowc + hi[0] + 1];
+                    for (int q = b; q < e; q++) {
+                        const int t = s.gitems[q];
+                        const double dx = jx[t] - x, dy = jy[t] - y, dz = jz[t] - z;
+                        if (dx * dx + dy * dy + dz * dz <= r2) emit(i, t);
+                    }
+                }
+        },
+        term_into);
     __syncthreads();
+    PHASE_MARK(sm, 21);
     // nothing nearby at all: the reference's full sum decides between a denormal and log(0) = -inf
     double lsum = 0;
     for (int t = tid; t < J; t += kBlock) {
@@ -104,6 +113,7 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
     }
     double tot = block_sum(sm.sh, lsum);
     __syncthreads();
+    PHASE_MARK(sm, 22);
     return tot;
 }
 
@@ -337,7 +347,9 @@ __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab
     if (tid == 0 && s_nll > capll) { s_nll = capll; sm.ctx.status |= ST_OVER_LL; }
     __syncthreads();
     const int nll = s_nll;
+    if (tid == 0) { sm.ctx.dbg[9] += nll; sm.ctx.dbg[10] += J; }
 
+    PHASE_MARK(sm, 24);
     // GC:358-425: connected components by min-label propagation over the detection edges
     for (int it = 0; it < J + M + 1; it++) {
         if (tid == 0) s_changed = 0;
@@ -354,6 +366,7 @@ __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab
         if (!ch) break;
     }
 
+    PHASE_MARK(sm, 25);
     // edges ordered by (component label, landmark, measurement)
     const int n2 = next_pow2(nll > 1 ? nll : 1);
     unsigned long long* skey = (n2 <= (int)p.smem_sort_cap) ? sm.skey : s.skey;
@@ -368,6 +381,7 @@ __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab
     }
     block_bitonic_sort(skey, sval, n2);
 
+    PHASE_MARK(sm, 26);
     double contrib = 0;
     __shared__ int s_nbig;
     if (tid == 0) s_nbig = 0;
@@ -395,6 +409,7 @@ __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab
     for (int t = tid; t < J; t += kBlock) if (deg[t] == 0) contrib += log(1 - s.jpd[t]);
     for (int k = tid; k < M; k += kBlock) if (deg[J + k] == 0) contrib += c.logclutter;
     __syncthreads();
+    if (tid == 0) sm.ctx.dbg[11] += s_nbig;
     if (tid == 0 && s_nbig > 0) contrib += murty_lane(p, sm, s, mw, skey, sval, nll, J, s_nbig);
     double total = block_sum(sm.sh, contrib);
     __syncthreads();
@@ -426,24 +441,42 @@ __device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const 
     __syncthreads();
     int total = block_scan_array(sm.sh, s.nflag, ncorr);
     if (total > p.lay.cap_sort) { if (tid == 0) sm.ctx.status |= ST_OVER_JMAP; }
-    const int n2 = next_pow2(total > 1 ? total : 1);
-    unsigned long long* skey = (n2 <= (int)p.smem_sort_cap) ? sm.skey : s.skey;
-    unsigned int* sval = (n2 <= (int)p.smem_sort_cap) ? sm.sval : s.sval;
-    const int sortcap = (n2 <= (int)p.smem_sort_cap) ? (int)p.smem_sort_cap : p.lay.cap_sort;
-    for (int j = total + tid; j < n2 && j < sortcap; j += kBlock) { skey[j] = ~0ull; sval[j] = ~0u; }
+    // expanded multiset in the slab, then only its `size` largest values are sorted
+    const int gcap = p.lay.cap_sort;
     for (int i = tid; i < ncorr; i += kBlock) {
         double w = mfield(corr, p.cap, 0)[i];
         int off = s.nflag[i];
         int g = ((i + 1 < ncorr) ? s.nflag[i + 1] : total) - off;
         for (int j = 0; j < g; j++) {
-            if (off + j < sortcap) {
-                skey[off + j] = weight_desc_key(w - (double)j);
-                sval[off + j] = (unsigned)j * (unsigned)p.cap + (unsigned)i;
+            if (off + j < gcap) {
+                s.skey[off + j] = weight_desc_key(w - (double)j);
+                s.sval[off + j] = (unsigned)j * (unsigned)p.cap + (unsigned)i;
             }
         }
     }
-    if (n2 <= sortcap) block_bitonic_sort(skey, sval, n2);
-    else __syncthreads();
+    __syncthreads();
+    const int tot = min(total, gcap);
+    const int wantj = min(size, tot);
+    unsigned long long* skey = s.skey;
+    unsigned int* sval = s.sval;
+    int nsort = tot;
+    if (wantj > 0) {
+        int cnt = -1;
+        if (wantj < tot)
+            cnt = block_select_smallest(s.skey, s.sval, tot, wantj, sm.skey, sm.sval, (int)p.smem_sort_cap, sm.hist,
+                                        &sm.ctx.nsel, &sm.ctx.selkey);
+        else if (tot <= (int)p.smem_sort_cap) {
+            for (int j = tid; j < tot; j += kBlock) { sm.skey[j] = s.skey[j]; sm.sval[j] = s.sval[j]; }
+            cnt = tot;
+        }
+        if (cnt >= 0) { skey = sm.skey; sval = sm.sval; nsort = cnt; }
+        const int n2 = next_pow2(nsort > 1 ? nsort : 1);
+        if (skey == sm.skey || n2 <= gcap) {
+            for (int j = nsort + tid; j < n2; j += kBlock) { skey[j] = ~0ull; sval[j] = ~0u; }
+            block_bitonic_sort(skey, sval, n2);
+        }
+    }
+    __syncthreads();
     int J = min(size, total);
     if (J > capj) { J = capj; if (tid == 0) sm.ctx.status |= ST_OVER_JMAP; }
     for (int t = tid; t < J; t += kBlock) {
@@ -454,13 +487,14 @@ __device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const 
     }
     __syncthreads();
 
-    PHASE_MARK(sm, 11);
     // PHD:381-384: sum_j ln v_pred(m_j), sum_j ln v_corr(m_j)
     CompSrc pred{s.pwt, s.pm, s.pm + capp, s.pm + 2 * capp, mfield(predmap, p.cap, 4), (size_t)p.cap, npriorcov,
                  p.cfg.birth_cov, Npred};
-    double* vs = (J <= kVsCap) ? sm.vs : s.vsum;
+    double* vs = s.vsum;   // global: double atomics are native there (shared-memory ones are CAS loops)
+    PHASE_MARK(sm, 11);
     grid_build(sm.sh, sm.ctx.grid, sm.gstart, s.gitems, s.jm, s.jm + capj, s.jm + 2 * capj, J, kQueryCell, kQueryCell,
                kQueryCell);
+    PHASE_MARK(sm, 23);
     const double plog = eval_map_at_points(p, sm, s, pred, J, vs);
     PHASE_MARK(sm, 12);
     CompSrc cor{mfield(corr, p.cap, 0), mfield(corr, p.cap, 1), mfield(corr, p.cap, 2), mfield(corr, p.cap, 3),

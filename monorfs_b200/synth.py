@@ -19,6 +19,7 @@ WORKLOADS = {
     "c3": dict(P=200, N=50000, M=1000),
     "c4": dict(P=20000, N=2000, M=500),
     "tiny": dict(P=64, N=60, M=24),
+    "c4s": dict(P=1480, N=2000, M=500),   # config 4's per-particle shape on 1480 particles (profiling runs)
 }
 
 MEASURER = [575.8156, 0.1, 10.0, -320, -240, 640, 480]   # range clip widened to 10 m (section 8d)
