@@ -164,7 +164,9 @@ int rbphd_resample_global(rbphd_navigator* nav, const void* dev_global_weights, 
 int64_t rbphd_particle_record_bytes(const rbphd_navigator* nav);
 int rbphd_pack_particles(rbphd_navigator* nav, const int* local_indices, int count, void** dev_buf,
                          int64_t* bytes);
-int rbphd_unpack_particles(rbphd_navigator* nav, const void* dev_buf, const int* slots, int count);
+/* record records[j] of dev_buf becomes local particle slots[j] (a record may be used several times) */
+int rbphd_unpack_particles(rbphd_navigator* nav, const void* dev_buf, const int* records, const int* slots,
+                           int count);
 int rbphd_commit_resample_local(rbphd_navigator* nav, const int* local_sources, int count);
 
 /* ---- instrumentation ---- */

@@ -320,10 +320,12 @@ class Handle:
     def record_doubles(self):
         return int(self.lib.rbphd_particle_record_bytes(self._h)) // 8
 
-    def unpack_particles(self, dev_ptr, slots):
+    def unpack_particles(self, dev_ptr, records, slots):
+        records = np.ascontiguousarray(records, dtype=np.int32)
         slots = np.ascontiguousarray(slots, dtype=np.int32)
-        self._ck(self.lib.rbphd_unpack_particles(self._h, C.c_void_p(dev_ptr), slots.ctypes.data_as(c_int_p),
-                                                 len(slots)))
+        assert len(records) == len(slots)
+        self._ck(self.lib.rbphd_unpack_particles(self._h, C.c_void_p(dev_ptr), records.ctypes.data_as(c_int_p),
+                                                 slots.ctypes.data_as(c_int_p), len(slots)))
 
     def commit_resample_local(self, sources):
         sources = np.ascontiguousarray(sources, dtype=np.int32)

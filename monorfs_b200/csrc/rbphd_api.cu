@@ -1037,6 +1037,28 @@ int64_t rbphd_particle_record_bytes(const rbphd_navigator* nav)
     return nav ? (int64_t)(record_doubles(nav) * sizeof(double)) : 0;
 }
 
+static int upload_ints(rbphd_navigator* nav, const int* a, const int* b, int count, int** da, int** db)
+{
+    int need = 2 * std::max(count, 1);
+    if (need > nav->idxcap) {
+        CK(cudaStreamSynchronize(nav->stream));
+        cudaFree(nav->idxbuf);
+        nav->idxbuf = nullptr;
+        CK(cudaMalloc(&nav->idxbuf, sizeof(int) * (size_t)need * 2));
+        nav->idxcap = need * 2;
+    }
+    CK(cudaStreamSynchronize(nav->stream));   // staging buffer reuse
+    int* h = (int*)nav->h_in.get(sizeof(int) * (size_t)need);
+    if (!h) return fail(nav, RBPHD_ERR_CUDA, "pinned allocation failed");
+    std::memcpy(h, a, sizeof(int) * (size_t)count);
+    if (b) std::memcpy(h + count, b, sizeof(int) * (size_t)count);
+    CK(cudaMemcpyAsync(nav->idxbuf, h, sizeof(int) * (size_t)(b ? 2 * count : count), cudaMemcpyHostToDevice,
+                       nav->stream));
+    *da = nav->idxbuf;
+    if (db) *db = nav->idxbuf + count;
+    return RBPHD_OK;
+}
+
 int rbphd_pack_particles(rbphd_navigator* nav, const int* local_indices, int count, void** dev_buf, int64_t* bytes)
 {
     if (!nav || count < 0) return RBPHD_ERR_ARGUMENT;
@@ -1051,21 +1073,15 @@ int rbphd_pack_particles(rbphd_navigator* nav, const int* local_indices, int cou
         CK(cudaMalloc(&nav->packbuf, need));
         nav->packbytes = need;
     }
-    std::vector<int> hc(std::max(nav->P, 1));
-    void* h;
-    if (int r = download(nav, nav->counts[src], sizeof(int) * (size_t)nav->P, &h)) return r;
-    std::memcpy(hc.data(), h, sizeof(int) * (size_t)nav->P);
-    for (int j = 0; j < count; j++) {
-        int i = local_indices[j];
-        if (i < 0 || i >= nav->P) return fail(nav, RBPHD_ERR_ARGUMENT, "pack index out of range");
-        double* rec = nav->packbuf + record_doubles(nav) * (size_t)j;
-        double cnt = hc[i];
-        CK(cudaMemcpyAsync(rec, &cnt, sizeof(double), cudaMemcpyHostToDevice, nav->stream));
-        CK(cudaStreamSynchronize(nav->stream));
-        CK(cudaMemcpyAsync(rec + 1, nav->poses + 7 * (size_t)i, 7 * sizeof(double), cudaMemcpyDeviceToDevice,
-                           nav->stream));
-        CK(cudaMemcpyAsync(rec + 8, nav->maps[src] + (size_t)i * kFields * nav->cap,
-                           sizeof(double) * kFields * (size_t)nav->cap, cudaMemcpyDeviceToDevice, nav->stream));
+    for (int j = 0; j < count; j++)
+        if (local_indices[j] < 0 || local_indices[j] >= nav->P) return fail(nav, RBPHD_ERR_ARGUMENT, "pack index out of range");
+    if (count > 0) {
+        int* didx;
+        if (int r = upload_ints(nav, local_indices, nullptr, count, &didx, nullptr)) return r;
+        launch_pack_particles(nav->stream, nav->cap, nav->maps[src], nav->counts[src], nav->poses, didx, count,
+                              nav->packbuf);
+        nav->launches += 1;
+        if (int r = check_async(nav, "pack launch")) return r;
     }
     CK(cudaStreamSynchronize(nav->stream));
     if (dev_buf) *dev_buf = nav->packbuf;
@@ -1073,29 +1089,22 @@ int rbphd_pack_particles(rbphd_navigator* nav, const int* local_indices, int cou
     return RBPHD_OK;
 }
 
-int rbphd_unpack_particles(rbphd_navigator* nav, const void* dev_buf, const int* slots, int count)
+int rbphd_unpack_particles(rbphd_navigator* nav, const void* dev_buf, const int* records, const int* slots, int count)
 {
     if (!nav || count < 0) return RBPHD_ERR_ARGUMENT;
+    if (count == 0) return RBPHD_OK;
     if (int r = set_device(nav)) return r;
     DeviceState st;
     if (int r = read_state(nav, &st)) return r;
     const int dst = st.cur;   // new particles are assembled in buffer cur (see k_copy_particles)
-    const double* base = (const double*)dev_buf;
-    for (int j = 0; j < count; j++) {
-        int i = slots[j];
-        if (i < 0 || i >= nav->P) return fail(nav, RBPHD_ERR_ARGUMENT, "unpack slot out of range");
-        const double* rec = base + record_doubles(nav) * (size_t)j;
-        double cnt;
-        CK(cudaMemcpyAsync(&cnt, rec, sizeof(double), cudaMemcpyDeviceToHost, nav->stream));
-        CK(cudaStreamSynchronize(nav->stream));
-        int n = (int)cnt;
-        CK(cudaMemcpyAsync(nav->counts[dst] + i, &n, sizeof(int), cudaMemcpyHostToDevice, nav->stream));
-        CK(cudaStreamSynchronize(nav->stream));
-        CK(cudaMemcpyAsync(nav->poses_tmp + 7 * (size_t)i, rec + 1, 7 * sizeof(double), cudaMemcpyDeviceToDevice,
-                           nav->stream));
-        CK(cudaMemcpyAsync(nav->maps[dst] + (size_t)i * kFields * nav->cap, rec + 8,
-                           sizeof(double) * kFields * (size_t)nav->cap, cudaMemcpyDeviceToDevice, nav->stream));
-    }
+    for (int j = 0; j < count; j++)
+        if (slots[j] < 0 || slots[j] >= nav->P) return fail(nav, RBPHD_ERR_ARGUMENT, "unpack slot out of range");
+    int *drec, *dslot;
+    if (int r = upload_ints(nav, records, slots, count, &drec, &dslot)) return r;
+    launch_unpack_particles(nav->stream, nav->cap, (const double*)dev_buf, drec, dslot, count, nav->maps[dst],
+                            nav->counts[dst], nav->poses_tmp);
+    nav->launches += 1;
+    if (int r = check_async(nav, "unpack launch")) return r;
     CK(cudaStreamSynchronize(nav->stream));
     return RBPHD_OK;
 }
@@ -1107,20 +1116,15 @@ int rbphd_commit_resample_local(rbphd_navigator* nav, const int* local_sources, 
     DeviceState st;
     if (int r = read_state(nav, &st)) return r;
     const int src = 1 - st.cur, dst = st.cur;
-    for (int i = 0; i < count; i++) {
-        int a = local_sources[i];
-        if (a < 0) continue;   // filled by rbphd_unpack_particles
-        if (a >= nav->P) return fail(nav, RBPHD_ERR_ARGUMENT, "local source out of range");
-        CK(cudaMemcpyAsync(nav->maps[dst] + (size_t)i * kFields * nav->cap,
-                           nav->maps[src] + (size_t)a * kFields * nav->cap,
-                           sizeof(double) * kFields * (size_t)nav->cap, cudaMemcpyDeviceToDevice, nav->stream));
-        CK(cudaMemcpyAsync(nav->counts[dst] + i, nav->counts[src] + a, sizeof(int), cudaMemcpyDeviceToDevice,
-                           nav->stream));
-        CK(cudaMemcpyAsync(nav->poses_tmp + 7 * (size_t)i, nav->poses + 7 * (size_t)a, 7 * sizeof(double),
-                           cudaMemcpyDeviceToDevice, nav->stream));
-    }
-    CK(cudaMemcpyAsync(nav->poses, nav->poses_tmp, 7 * sizeof(double) * (size_t)nav->P, cudaMemcpyDeviceToDevice,
-                       nav->stream));
+    for (int i = 0; i < count; i++)
+        if (local_sources[i] >= nav->P) return fail(nav, RBPHD_ERR_ARGUMENT, "local source out of range");
+    int* dsrc;
+    if (int r = upload_ints(nav, local_sources, nullptr, count, &dsrc, nullptr)) return r;
+    launch_commit_local(nav->stream, nav->P, nav->cap, nav->maps[src], nav->counts[src], nav->maps[dst],
+                        nav->counts[dst], nav->poses, nav->poses_tmp, dsrc);
+    launch_copy_doubles(nav->stream, 7 * (size_t)nav->P, nav->poses, nav->poses_tmp);
+    nav->launches += 2;
+    if (int r = check_async(nav, "commit launch")) return r;
     CK(cudaStreamSynchronize(nav->stream));
     return RBPHD_OK;
 }

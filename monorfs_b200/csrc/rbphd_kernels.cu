@@ -1186,6 +1186,78 @@ __global__ void k_commit_poses(int P, double* poses, const double* poses_tmp, co
     if (i < P * 7) poses[i] = poses_tmp[i];
 }
 
+// ---- multi-GPU migration: flat particle records [count][pose 7][13 * cap map slab] ----
+__global__ void __launch_bounds__(256) k_pack_particles(int cap, const double* maps, const int* counts,
+                                                        const double* poses, const int* idx, double* rec)
+{
+    const int j = blockIdx.x, i = idx[j];
+    const size_t rd = 8 + (size_t)kFields * cap;
+    double* r = rec + rd * j;
+    const int n = counts[i];
+    if (threadIdx.x == 0) r[0] = (double)n;
+    if (threadIdx.x < 7) r[1 + threadIdx.x] = poses[(size_t)i * 7 + threadIdx.x];
+    const double* src = maps + (size_t)i * kFields * cap;
+    for (int f = 0; f < kFields; f++)
+        for (int t = threadIdx.x; t < n; t += blockDim.x) r[8 + (size_t)f * cap + t] = src[(size_t)f * cap + t];
+}
+
+__global__ void __launch_bounds__(256) k_unpack_particles(int cap, const double* rec, const int* recidx,
+                                                          const int* slots, double* maps, int* counts,
+                                                          double* poses_tmp)
+{
+    const int j = blockIdx.x, i = slots[j];
+    const size_t rd = 8 + (size_t)kFields * cap;
+    const double* r = rec + rd * recidx[j];
+    const int n = (int)r[0];
+    if (threadIdx.x == 0) counts[i] = n;
+    if (threadIdx.x < 7) poses_tmp[(size_t)i * 7 + threadIdx.x] = r[1 + threadIdx.x];
+    double* dst = maps + (size_t)i * kFields * cap;
+    for (int f = 0; f < kFields; f++)
+        for (int t = threadIdx.x; t < n; t += blockDim.x) dst[(size_t)f * cap + t] = r[8 + (size_t)f * cap + t];
+}
+
+// new local particle i <- local ancestor sources[i] (>= 0) from the posterior buffer; -1 = filled by unpack
+__global__ void __launch_bounds__(256) k_commit_local(int cap, const double* src_maps, const int* src_counts,
+                                                      double* dst_maps, int* dst_counts, const double* poses,
+                                                      double* poses_tmp, const int* sources)
+{
+    const int i = blockIdx.x, a = sources[i];
+    if (a < 0) return;
+    const int n = src_counts[a];
+    if (threadIdx.x == 0) dst_counts[i] = n;
+    if (threadIdx.x < 7) poses_tmp[(size_t)i * 7 + threadIdx.x] = poses[(size_t)a * 7 + threadIdx.x];
+    const double* src = src_maps + (size_t)a * kFields * cap;
+    double* dst = dst_maps + (size_t)i * kFields * cap;
+    for (int f = 0; f < kFields; f++)
+        for (int t = threadIdx.x; t < n; t += blockDim.x) dst[(size_t)f * cap + t] = src[(size_t)f * cap + t];
+}
+
+__global__ void k_copy_doubles(size_t n, double* dst, const double* src)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+void launch_pack_particles(cudaStream_t s, int cap, const double* maps, const int* counts, const double* poses,
+                           const int* idx, int count, double* rec)
+{
+    if (count > 0) k_pack_particles<<<count, 256, 0, s>>>(cap, maps, counts, poses, idx, rec);
+}
+void launch_unpack_particles(cudaStream_t s, int cap, const double* rec, const int* recidx, const int* slots,
+                             int count, double* maps, int* counts, double* poses_tmp)
+{
+    if (count > 0) k_unpack_particles<<<count, 256, 0, s>>>(cap, rec, recidx, slots, maps, counts, poses_tmp);
+}
+void launch_commit_local(cudaStream_t s, int P, int cap, const double* src_maps, const int* src_counts,
+                         double* dst_maps, int* dst_counts, double* poses, double* poses_tmp, const int* sources)
+{
+    k_commit_local<<<P, 256, 0, s>>>(cap, src_maps, src_counts, dst_maps, dst_counts, poses, poses_tmp, sources);
+}
+void launch_copy_doubles(cudaStream_t s, size_t n, double* dst, const double* src)
+{
+    if (n > 0) k_copy_doubles<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, dst, src);
+}
+
 __global__ void k_flip(DeviceState* st) { st->cur = 1 - st->cur; st->resampled = 0; }
 
 // ------------------------------------------------------------------------------------------------

@@ -94,6 +94,13 @@ void launch_normalize_resample(cudaStream_t s, const DevCfg& cfg, int P, double*
 void launch_copy_particles(cudaStream_t s, int P, int cap, double* const maps[2], int* const counts[2],
                            double* poses, double* poses_tmp, const int* ancestors, DeviceState* st);
 void launch_flip(cudaStream_t s, DeviceState* st);
+void launch_pack_particles(cudaStream_t s, int cap, const double* maps, const int* counts, const double* poses,
+                           const int* idx, int count, double* rec);
+void launch_unpack_particles(cudaStream_t s, int cap, const double* rec, const int* recidx, const int* slots,
+                             int count, double* maps, int* counts, double* poses_tmp);
+void launch_commit_local(cudaStream_t s, int P, int cap, const double* src_maps, const int* src_counts,
+                         double* dst_maps, int* dst_counts, double* poses, double* poses_tmp, const int* sources);
+void launch_copy_doubles(cudaStream_t s, size_t n, double* dst, const double* src);
 size_t particle_update_smem(int max_measurements, size_t* sort_cap);
 size_t murty_workspace_bytes();
 int particle_update_max_ctas_per_sm(size_t smem);

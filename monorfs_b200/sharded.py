@@ -149,7 +149,7 @@ class ShardedNavigator:
         self._stream.synchronize()
         for src, items in sorted(plan["recv"].items()):
             buf = recv_bufs[src]
-            for k, (_, slots) in enumerate(items):
-                for slot in slots:
-                    self.h.unpack_particles(buf.data_ptr() + 8 * rd * k, [slot])
+            records = [k for k, (_, slots) in enumerate(items) for _ in slots]
+            targets = [slot for _, slots in items for slot in slots]
+            self.h.unpack_particles(buf.data_ptr(), records, targets)
         self.h.commit_resample_local(plan["local_sources"])
