@@ -245,7 +245,7 @@ __device__ inline void grid_build(BlockShared& sh, CellGrid& g, int* start, int*
             long cells = 1;
             bool ok = true;
             for (int a = 0; a < 3; a++) {
-                double dd = ceil(ext[a] / (mc[a] * f));
+                double dd = floor(ext[a] / (mc[a] * f));   // cell edge >= mincell * f
                 if (!(dd >= 1.0)) dd = 1.0;
                 if (dd > (double)kGridMaxDim) { ok = false; dd = (double)kGridMaxDim; }
                 cells *= (long)dd;
@@ -254,7 +254,7 @@ __device__ inline void grid_build(BlockShared& sh, CellGrid& g, int* start, int*
             f *= 1.2;
         }
         for (int a = 0; a < 3; a++) {
-            double dd = ceil(ext[a] / (mc[a] * f));
+            double dd = floor(ext[a] / (mc[a] * f));   // cell edge >= mincell * f
             int d = (dd >= (double)kGridMaxDim) ? kGridMaxDim : ((dd >= 1.0) ? (int)dd : 1);
             double cs = ext[a] / d;
             if (!(cs > 0)) cs = 1.0;

@@ -135,9 +135,11 @@ __device__ __forceinline__ void load_pred(const KParams& p, const Slab& s, const
 // inline by the enumerating thread.
 // ------------------------------------------------------------------------------------------------
 template <class Enum, class Proc>
-__device__ __forceinline__ void enumerate_then_process(Smem& sm, int n_items, uint2* list, int list_cap, Enum enumerate,
-                                                       Proc process)
+__device__ __forceinline__ void enumerate_then_process(Smem& sm, int n_items, uint2* list, int list_cap, uint2* ovf,
+                                                       int ovf_cap, Enum enumerate, Proc process)
 {
+    // pairs beyond the shared-memory list go to an overflow list in the slab (never processed inside the
+    // enumeration loop: that would drag the heavy code and its registers into the innermost loop)
     for (int base = 0; base < n_items; base += kBlock) {
         if (threadIdx.x == 0) sm.ctx.nsel2 = 0;
         __syncthreads();
@@ -146,11 +148,15 @@ __device__ __forceinline__ void enumerate_then_process(Smem& sm, int n_items, ui
             enumerate(i, [&](int a, int b) {
                 const int idx = atomicAdd(&sm.ctx.nsel2, 1);
                 if (idx < list_cap) list[idx] = make_uint2((unsigned)a, (unsigned)b);
-                else process(a, b);
+                else if (idx - list_cap < ovf_cap) ovf[idx - list_cap] = make_uint2((unsigned)a, (unsigned)b);
+                else sm.ctx.status |= ST_OVER_PAIRS;
             });
         __syncthreads();
-        const int cnt = min(sm.ctx.nsel2, list_cap);
+        const int tot = sm.ctx.nsel2;
+        const int cnt = min(tot, list_cap);
         for (int e = threadIdx.x; e < cnt; e += kBlock) process((int)list[e].x, (int)list[e].y);
+        const int nov = min(max(tot - list_cap, 0), ovf_cap);
+        for (int e = threadIdx.x; e < nov; e += kBlock) process((int)ovf[e].x, (int)ovf[e].y);
         __syncthreads();
     }
 }
@@ -279,6 +285,18 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         s.ppd[i] = pdi;
         s.pwmd[i] = (1 - pdi) * w;
         if (do_correct) gate_append(p, sm, s, i, m, local);
+        if (do_births) {
+            // upper bound of ln(w N(x; m, P)) at distance d: ln(w mult) - d^2 / (2 trace P)  (lambda_max <= trace)
+            double P[9];
+#pragma unroll
+            for (int a = 0; a < 9; a++) P[a] = mfield(in, p.cap, 4 + a)[i];
+            const double det = P[0] * (P[4] * P[8] - P[5] * P[7]) - P[1] * (P[3] * P[8] - P[5] * P[6]) +
+                               P[2] * (P[3] * P[7] - P[4] * P[6]);
+            const double tr = P[0] + P[4] + P[8];
+            const bool spd = (det > 0) && (tr > 0) && (w >= 0);
+            s.cnorm[i] = spd ? log(w * gauss_mult(det)) : INFINITY;
+            s.crad[i] = spd ? 1.0 / (2.0 * tr) : 0.0;
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -321,18 +339,24 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
                 s.vsum[u] = 0.0;
             }
             __syncthreads();
+            PHASE_MARK(sm, 27);
             grid_build(sm.sh, sm.ctx.grid, sm.gstart, uitems, ux, uy, uz, nU, c.explore_r, c.explore_r, c.explore_r, 512);
+            PHASE_MARK(sm, 28);
             const CellGrid& g = sm.ctx.grid;
+            const double logskip = log(c.explore_thr) - 32.3;   // ln(1e-14)
             // the point arrays live in the first 28 * nU bytes of the sort buffer; the pair list behind them
             const int list_off = (28 * nU + 15) / 16 * 2;   // in uint2 units, rounded to 16 bytes
             uint2* hits = reinterpret_cast<uint2*>(sm.skey) + list_off;
             const int hits_cap = (int)p.smem_sort_cap - list_off;
             enumerate_then_process(
-                sm, N, hits, hits_cap,
+                sm, N, hits, hits_cap, reinterpret_cast<uint2*>(s.edst), p.lay.cap_edges / 2,
                 [&](int i, auto emit) {
                     const double m[3] = {s.pm[i], s.pm[capp + i], s.pm[2 * capp + i]};
                     int lo[3], hi[3];
                     if (!grid_range(g, m[0], m[1], m[2], c.explore_r + 1e-9, lo, hi)) return;
+                    // terms whose upper bound is below 1e-14 of the threshold cannot move the sum out of the
+                    // +-1e-9 band that triggers the exact replay (at most max_components of them are skipped)
+                    const double lognorm = s.cnorm[i], itr = s.crad[i];
                     for (int cz = lo[2]; cz <= hi[2]; cz++)
                         for (int cy = lo[1]; cy <= hi[1]; cy++) {
                             const int rowc = (cz * g.dim[1] + cy) * g.dim[0];
@@ -340,7 +364,8 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
                             for (int q = qb; q < qe; q++) {
                                 const int u = uitems[q];
                                 const double dx = m[0] - ux[u], dy = m[1] - uy[u], dz = m[2] - uz[u];
-                                if (dx * dx + dy * dy + dz * dz <= c.explore_r2) emit(i, u);
+                                const double d2 = dx * dx + dy * dy + dz * dz;
+                                if (d2 <= c.explore_r2 && lognorm - d2 * itr >= logskip) emit(i, u);
                             }
                         }
                 },

@@ -10,7 +10,7 @@ namespace rbphd {
 // Terms of Map.Evaluate with Mahalanobis distance^2 above this are < 2e-22 of the component's peak and
 // are skipped (the reference sums them; the parity bar for weights is 1e-9 relative).
 constexpr double kEvalD2 = 100.0;
-constexpr double kQueryCell = 0.5;   // cell edge of the grid over the map-estimate points
+constexpr double kQueryCell = 0.7;   // cell edge of the grid over the map-estimate points
 
 struct CompSrc {
     const double* w;
@@ -65,7 +65,8 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
         atomicAdd(&vs[t], c.w[i] * (mult * exp(-0.5 * quadform3(Pinv, d))));
     };
     enumerate_then_process(
-        sm, c.n, reinterpret_cast<uint2*>(sm.skey), (int)p.smem_sort_cap,
+        sm, c.n, reinterpret_cast<uint2*>(sm.skey), (int)p.smem_sort_cap, reinterpret_cast<uint2*>(s.edst),
+        p.lay.cap_edges / 2,
         [&](int i, auto emit) {
             const double x = c.mx[i], y = c.my[i], z = c.mz[i];
             // trace of the covariance without loading the off-diagonal terms
