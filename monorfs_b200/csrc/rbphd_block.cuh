@@ -131,10 +131,17 @@ __device__ inline int block_select_smallest(const unsigned long long* key, const
         const int shift = 56 - 8 * pass;
         for (int b = threadIdx.x; b < 256; b += kBlock) hist[b] = 0;
         __syncthreads();
-        for (int e = threadIdx.x; e < n; e += kBlock) {
-            const unsigned long long kk = key[e];
-            if (pass == 0 || (kk >> (shift + 8)) == (prefix >> (shift + 8)))
-                atomicAdd(&hist[(int)((kk >> shift) & 255)], 1);
+        for (int base = 0; base < n; base += kBlock) {
+            const int e = base + threadIdx.x;
+            unsigned digit = 0xffffffffu;   // inactive lanes share one pseudo digit
+            if (e < n) {
+                const unsigned long long kk = key[e];
+                if (pass == 0 || (kk >> (shift + 8)) == (prefix >> (shift + 8))) digit = (unsigned)((kk >> shift) & 255);
+            }
+            // keys share their leading bytes (weights span a few binades): aggregate equal digits per warp
+            const unsigned peers = __match_any_sync(0xffffffffu, digit);
+            if (digit != 0xffffffffu && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1))
+                atomicAdd(&hist[(int)digit], __popc(peers));
         }
         __syncthreads();
         if (threadIdx.x == 0) {

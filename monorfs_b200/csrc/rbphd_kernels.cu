@@ -502,18 +502,25 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         }
         __syncthreads();
     }
-    for (int k = tid; k < M; k += kBlock) {
-        const int b = segstart[k], e = segstart[k + 1];
-        if (in_smem) {
-            for (int a = b + 1; a < e; a++) {
-                const unsigned vc = scomp[a], vs = sslot[a];
-                int q = a - 1;
-                while (q >= b && scomp[q] > vc) { scomp[q + 1] = scomp[q]; sslot[q + 1] = sslot[q]; q--; }
-                scomp[q + 1] = vc; sslot[q + 1] = vs;
-            }
-            for (int t = b; t < e; t++) s.bidx[t] = (int)sslot[t];
+    if (in_smem) {
+        // rank sort inside each segment, one thread per PAIR (balanced even when a few measurements gate
+        // dozens of components): rank = number of pairs of the same measurement with a smaller component
+        unsigned int* sorted = reinterpret_cast<unsigned int*>(sm.skey) + p.smem_sort_cap;   // upper half of the key buffer
+        for (int t = tid; t < np; t += kBlock) {
+            const unsigned myc = scomp[t];
+            const int k = (int)(s.pkey[sslot[t]] >> 32);
+            const int b = segstart[k], e = segstart[k + 1];
+            int rank = 0;
+            for (int q = b; q < e; q++) rank += (scomp[q] < myc) ? 1 : 0;
+            sorted[b + rank] = sslot[t];
         }
-        else {
+        __syncthreads();
+        for (int t = tid; t < np; t += kBlock) sslot[t] = sorted[t];
+        __syncthreads();
+    }
+    else {
+        for (int k = tid; k < M; k += kBlock) {
+            const int b = segstart[k], e = segstart[k + 1];
             for (int a = b + 1; a < e; a++) {
                 const int v = s.bidx[a];
                 const unsigned vi = (unsigned)(s.pkey[v] & 0xffffffffu);
@@ -522,12 +529,34 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
                 s.bidx[q + 1] = v;
             }
         }
+        __syncthreads();
+    }
+    // weight terms gathered once, in sorted order, into shared memory (the component keys are dead now)
+    double* spt = reinterpret_cast<double*>(sm.skey);
+    if (in_smem) {
+        for (int t = tid; t < np; t += kBlock) { const int j = (int)sslot[t]; s.bidx[t] = j; }
+        __syncthreads();
+        for (int t = tid; t < np; t += kBlock) spt[t] = s.pt[sslot[t]];
+        __syncthreads();
+    }
+    for (int k = tid; k < M; k += kBlock) {
+        const int b = segstart[k], e = segstart[k + 1];
         double ws = 0;
-        for (int t = b; t < e; t++) ws += s.pt[s.bidx[t]];
-        for (int t = b; t < e; t++) {
-            double wv = s.pt[s.bidx[t]] / (c.clutter + ws);
-            if (wv != wv) wv = 0;   // GAUSS:154
-            s.pwgt[t] = wv;
+        if (in_smem) {
+            for (int t = b; t < e; t++) ws += spt[t];
+            for (int t = b; t < e; t++) {
+                double wv = spt[t] / (c.clutter + ws);
+                if (wv != wv) wv = 0;   // GAUSS:154
+                s.pwgt[t] = wv;
+            }
+        }
+        else {
+            for (int t = b; t < e; t++) ws += s.pt[s.bidx[t]];
+            for (int t = b; t < e; t++) {
+                double wv = s.pt[s.bidx[t]] / (c.clutter + ws);
+                if (wv != wv) wv = 0;   // GAUSS:154
+                s.pwgt[t] = wv;
+            }
         }
     }
     __syncthreads();
@@ -664,65 +693,109 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
     __syncthreads();
 
     PHASE_MARK(sm, 7);
-    // B3: cell grid over the W0 means; out-edges r -> r' (r' > r, close w.r.t. candidate r's covariance)
+    // B3: cell grid over the W0 means; edges r -> r' (r' > r, close w.r.t. candidate r's covariance).
+    // The neighbour walk prefilters on a cell-ordered single-precision copy of the means in shared memory
+    // (conservative margin) and touches the FP64 data only for the few survivors; edges are rare (a few
+    // per hundred components), so they are appended to one list and sorted by (r, r') afterwards.
     const double* tx = s.tm; const double* ty = s.tm + capw; const double* tz = s.tm + 2 * capw;
     double mincell = 2.0 * rmean;
     grid_build(sm.sh, sm.ctx.grid, sm.gstart, s.gitems, tx, ty, tz, W0, mincell, mincell, mincell);
     const double t2 = c.merge_t * c.merge_t;
     PHASE_MARK(sm, 19);
-    for (int pass = 0; pass < 2; pass++) {
-        for (int r = tid; r < W0; r += kBlock) {
-            double P[9], Pinv[9];
-#pragma unroll
-            for (int a = 0; a < 9; a++) P[a] = s.tP[(size_t)a * capw + r];
-            mat3_inv(P, Pinv);
-            const double x = tx[r], y = ty[r], z = tz[r];
-            int cnt = 0;
-            const int off = (pass == 1) ? s.ecnt[r] : 0;
-            const int cape = p.lay.cap_edges;
-            for_neighbours(sm, s, W0, tx, ty, tz, x, y, z, s.rho[r], [&](int r2) {
-                if (r2 <= r) return;
-                double d[3] = {x - tx[r2], y - ty[r2], z - tz[r2]};   // a.Mean - b.Mean (GAUSS:367)
-                if (quadform3(Pinv, d) < t2) {
-                    if (pass == 1 && off + cnt < cape) s.edst[off + cnt] = r2;
-                    cnt++;
-                }
-            });
-            if (pass == 0) s.ecnt[r] = cnt;
-            else {
-                int e = min(off + cnt, cape);
-                for (int a = off + 1; a < e; a++) {   // ascending r' (= list order of the reference's inner loop)
-                    int v = s.edst[a], b = a - 1;
-                    while (b >= off && s.edst[b] > v) { s.edst[b + 1] = s.edst[b]; b--; }
-                    s.edst[b + 1] = v;
-                }
-            }
-        }
-        __syncthreads();
-        if (pass == 0) {
-            if (tid == 0) s.ecnt[W0] = 0;
-            __syncthreads();
-            int ne = block_scan_array(sm.sh, s.ecnt, W0 + 1);
-            if (tid == 0) { sm.ctx.nedges = ne; sm.ctx.dbg[3] += ne; sm.ctx.dbg[4] += W0; sm.ctx.dbg[5] += sm.ctx.ncand; if (ne > p.lay.cap_edges) sm.ctx.status |= ST_OVER_EDGES; }
-            __syncthreads();
+    float* fx = reinterpret_cast<float*>(sm.skey);        // cell-ordered copies (sort buffer is idle here)
+    float* fy = fx + W0;
+    float* fz = fy + W0;
+    int* frank = reinterpret_cast<int*>(sm.sval);
+    const bool fsm = (3 * (size_t)W0 * sizeof(float) <= sizeof(unsigned long long) * p.smem_sort_cap) &&
+                     ((size_t)W0 <= p.smem_sort_cap);
+    if (fsm) {
+        for (int t = tid; t < W0; t += kBlock) {
+            const int r = s.gitems[t];
+            frank[t] = r;
+            fx[t] = (float)tx[r]; fy[t] = (float)ty[r]; fz[t] = (float)tz[r];
         }
     }
+    if (tid == 0) sm.ctx.nedges = 0;
+    __syncthreads();
+    unsigned long long* elist = s.llkey;   // (r << 32 | r') edge keys; capacity cap_ll
+    const int cape = p.lay.cap_ll;
+    {
+        const CellGrid& g = sm.ctx.grid;
+        for (int r = tid; r < W0; r += kBlock) {
+            const double rho = s.rho[r];
+            const double x = tx[r], y = ty[r], z = tz[r];
+            bool have = false;
+            double Pinv[9];
+            auto test = [&](int r2) {
+                if (r2 <= r) return;
+                if (!have) {
+                    double P[9];
+#pragma unroll
+                    for (int a = 0; a < 9; a++) P[a] = s.tP[(size_t)a * capw + r];
+                    mat3_inv(P, Pinv);
+                    have = true;
+                }
+                double d[3] = {x - tx[r2], y - ty[r2], z - tz[r2]};   // a.Mean - b.Mean (GAUSS:367)
+                if (quadform3(Pinv, d) < t2) {
+                    int idx = atomicAdd(&sm.ctx.nedges, 1);
+                    if (idx < cape) elist[idx] = ((unsigned long long)r << 32) | (unsigned)r2;
+                }
+            };
+            int lo[3], hi[3];
+            bool brute = !(rho == rho) || isinf(rho) || !fsm;
+            if (!brute) {
+                if (!grid_range(g, x, y, z, rho, lo, hi)) continue;
+                long cells = (long)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
+                if (cells > 128) brute = true;
+            }
+            if (brute) {
+                for (int r2 = r + 1; r2 < W0; r2++) {
+                    if (rho == rho && !isinf(rho) &&
+                        (fabs(tx[r2] - x) > rho || fabs(ty[r2] - y) > rho || fabs(tz[r2] - z) > rho)) continue;
+                    test(r2);
+                }
+                continue;
+            }
+            const float xf = (float)x, yf = (float)y, zf = (float)z;
+            const float rf = (float)rho * 1.0001f + 1e-6f + 1e-6f * (fabsf(xf) + fabsf(yf) + fabsf(zf));
+            for (int cz = lo[2]; cz <= hi[2]; cz++)
+                for (int cy = lo[1]; cy <= hi[1]; cy++) {
+                    const int rowc = (cz * g.dim[1] + cy) * g.dim[0];
+                    const int qb = sm.gstart[rowc + lo[0]], qe = sm.gstart[rowc + hi[0] + 1];
+                    for (int q = qb; q < qe; q++)
+                        if (fabsf(fx[q] - xf) <= rf && fabsf(fy[q] - yf) <= rf && fabsf(fz[q] - zf) <= rf) {
+                            const int r2 = frank[q];
+                            if (r2 > r && fabs(tx[r2] - x) <= rho && fabs(ty[r2] - y) <= rho && fabs(tz[r2] - z) <= rho)
+                                test(r2);
+                        }
+                }
+        }
+    }
+    __syncthreads();
+    int ne = sm.ctx.nedges;
+    if (tid == 0) { sm.ctx.dbg[3] += ne; sm.ctx.dbg[4] += W0; sm.ctx.dbg[5] += sm.ctx.ncand; if (ne > cape) sm.ctx.status |= ST_OVER_EDGES; }
+    ne = min(ne, cape);
+    // edges ordered by (r, r'): r' ascending = list order of the reference's inner loop (PHD:936-942)
+    const int ne2 = next_pow2(ne > 1 ? ne : 1);
+    unsigned long long* ekey = (ne2 <= (int)p.smem_sort_cap) ? sm.skey : s.skey;
+    unsigned int* eval_ = (ne2 <= (int)p.smem_sort_cap) ? sm.sval : s.sval;
+    __syncthreads();
+    if (ne2 <= p.lay.cap_sort) {
+        for (int e = tid; e < ne2; e += kBlock) { ekey[e] = (e < ne) ? elist[e] : ~0ull; eval_[e] = 0u; }
+        block_bitonic_sort(ekey, eval_, ne2);
+    }
+    else if (tid == 0) sm.ctx.status |= ST_OVER_EDGES;
 
     PHASE_MARK(sm, 8);
     // B4: which candidates survive.  A component is absorbed iff some surviving earlier candidate is
     // close to it; resolve in rounds (the lowest undecided rank is always decidable).
     for (int r = tid; r < W0; r += kBlock) { s.nstate[r] = 0; s.nflag[r] = 0; s.nowner[r] = 0x7fffffff; }
     __syncthreads();
-    const int cape = p.lay.cap_edges;
     for (int round = 0; round <= W0; round++) {
-        for (int r = tid; r < W0; r += kBlock) {
-            int st = s.nstate[r];
-            if (st == 2) continue;
-            int b = min(s.ecnt[r], cape), e = min(s.ecnt[r + 1], cape);
-            for (int a = b; a < e; a++) {
-                int d = s.edst[a];
-                if (s.nstate[d] == 0) atomicOr(&s.nflag[d], (st == 1) ? 2 : 1);
-            }
+        for (int e = tid; e < ne; e += kBlock) {
+            const int src = (int)(ekey[e] >> 32), dst = (int)(ekey[e] & 0xffffffffu);
+            const int st = s.nstate[src];
+            if (st != 2 && s.nstate[dst] == 0) atomicOr(&s.nflag[dst], (st == 1) ? 2 : 1);
         }
         __syncthreads();
         int und = 0;
@@ -740,10 +813,9 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
         if (tot == 0) break;
     }
     // B5: owner of each absorbed component = the first surviving candidate that is close to it
-    for (int r = tid; r < W0; r += kBlock) {
-        if (s.nstate[r] != 1) continue;
-        int b = min(s.ecnt[r], cape), e = min(s.ecnt[r + 1], cape);
-        for (int a = b; a < e; a++) atomicMin(&s.nowner[s.edst[a]], r);
+    for (int e = tid; e < ne; e += kBlock) {
+        const int src = (int)(ekey[e] >> 32), dst = (int)(ekey[e] & 0xffffffffu);
+        if (s.nstate[src] == 1) atomicMin(&s.nowner[dst], src);
     }
     __syncthreads();
     PHASE_MARK(sm, 9);
@@ -757,7 +829,9 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
         int o = s.nflag[r];
         if (o >= nout) continue;
         double weight = 0.0, mean[3] = {0, 0, 0}, cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        int b = min(s.ecnt[r], cape), e = min(s.ecnt[r + 1], cape);
+        int b = lower_bound_u64(ekey, ne, (unsigned long long)r << 32);
+        int e = b;
+        while (e < ne && (int)(ekey[e] >> 32) == r) e++;
         int a = b - 1;
         int member = r;
         while (true) {
@@ -773,9 +847,9 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
                     cov[i * 3 + k] = cov[i * 3 + k] + w * (s.tP[(size_t)(i * 3 + k) * capw + member] + m[i] * m[k]);
             // next member owned by r
             a++;
-            while (a < e && s.nowner[s.edst[a]] != r) a++;
+            while (a < e && s.nowner[(int)(ekey[a] & 0xffffffffu)] != r) a++;
             if (a >= e) break;
-            member = s.edst[a];
+            member = (int)(ekey[a] & 0xffffffffu);
         }
         double ow, om[3], oP[9];
         if (weight < 1e-15) {

@@ -64,6 +64,9 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
         const double d[3] = {jx[t] - c.mx[i], jy[t] - c.my[i], jz[t] - c.mz[i]};   // x - Mean (GAUSS:201)
         atomicAdd(&vs[t], c.w[i] * (mult * exp(-0.5 * quadform3(Pinv, d))));
     };
+    const int fatcap = p.M;
+    if (tid == 0) sm.ctx.nU = 0;
+    __syncthreads();
     enumerate_then_process(
         sm, c.n, reinterpret_cast<uint2*>(sm.skey), (int)p.smem_sort_cap, reinterpret_cast<uint2*>(s.edst),
         p.lay.cap_edges / 2,
@@ -80,6 +83,10 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
                 if (!grid_range(g, x, y, z, sqrt(r2), lo, hi)) return;
                 long cells = (long)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
                 if (cells > 2048) brute = true;
+                else if (cells > 27) {   // wide component: a whole warp walks its cells later (balance)
+                    const int f = atomicAdd(&sm.ctx.nU, 1);
+                    if (f < fatcap) { sm.kidx[f] = i; return; }
+                }
             }
             if (brute) {
                 for (int t = 0; t < J; t++) {
@@ -100,6 +107,52 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
                 }
         },
         term_into);
+    {
+        const int nfat = min(sm.ctx.nU, fatcap);
+        const int lane = tid & 31, warp = tid >> 5;
+        uint2* list = reinterpret_cast<uint2*>(sm.skey);
+        uint2* ovf = reinterpret_cast<uint2*>(s.edst);
+        const int list_cap = (int)p.smem_sort_cap, ovf_cap = p.lay.cap_edges / 2;
+        for (int fbase = 0; fbase < nfat; fbase += kWarps) {
+            if (tid == 0) sm.ctx.nsel2 = 0;
+            __syncthreads();
+            const int f = fbase + warp;
+            if (f < nfat) {
+                const int i = sm.kidx[f];
+                const double x = c.mx[i], y = c.my[i], z = c.mz[i];
+                const double tr = ((i < c.ncov) ? c.cov[i] : c.defcov[0]) +
+                                  ((i < c.ncov) ? c.cov[(size_t)4 * c.covstride + i] : c.defcov[4]) +
+                                  ((i < c.ncov) ? c.cov[(size_t)8 * c.covstride + i] : c.defcov[8]);
+                const double r2 = kEvalD2 * tr * (1.0 + 1e-9);
+                int lo[3], hi[3];
+                if (grid_range(g, x, y, z, sqrt(r2), lo, hi)) {
+                    const int ny = hi[1] - lo[1] + 1, rows = ny * (hi[2] - lo[2] + 1);
+                    for (int rw = lane; rw < rows; rw += 32) {
+                        const int cz = lo[2] + rw / ny, cy = lo[1] + rw % ny;
+                        const int rowc = (cz * g.dim[1] + cy) * g.dim[0];
+                        const int b = sm.gstart[rowc + lo[0]], e = sm.gstart[rowc + hi[0] + 1];
+                        for (int q = b; q < e; q++) {
+                            const int t = s.gitems[q];
+                            const double dx = jx[t] - x, dy = jy[t] - y, dz = jz[t] - z;
+                            if (dx * dx + dy * dy + dz * dz <= r2) {
+                                const int idx = atomicAdd(&sm.ctx.nsel2, 1);
+                                if (idx < list_cap) list[idx] = make_uint2((unsigned)i, (unsigned)t);
+                                else if (idx - list_cap < ovf_cap) ovf[idx - list_cap] = make_uint2((unsigned)i, (unsigned)t);
+                                else sm.ctx.status |= ST_OVER_PAIRS;
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            const int tot = sm.ctx.nsel2;
+            const int cnt = min(tot, list_cap);
+            for (int e = tid; e < cnt; e += kBlock) term_into((int)list[e].x, (int)list[e].y);
+            const int nov = min(max(tot - list_cap, 0), ovf_cap);
+            for (int e = tid; e < nov; e += kBlock) term_into((int)ovf[e].x, (int)ovf[e].y);
+            __syncthreads();
+        }
+    }
     __syncthreads();
     PHASE_MARK(sm, 21);
     // nothing nearby at all: the reference's full sum decides between a denormal and log(0) = -inf
