@@ -373,6 +373,7 @@ int ensure_stage(rbphd_navigator* nav)
     if (nav->stage) return RBPHD_OK;
     rbphd_limits lim = nav->lim;
     lim.max_particles = 1;
+    lim.max_components = nav->cap + nav->Mcap;   // a predicted map holds the prior components plus the births
     nav->stage = rbphd_new(&nav->cfg, &lim);
     if (!nav->stage) return fail(nav, RBPHD_ERR_CUDA, "stage navigator: " + g_last_error);
     return RBPHD_OK;

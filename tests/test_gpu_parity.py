@@ -448,3 +448,49 @@ def test_c2_shape_sampled_parity(capi, orc, synth):
     if res:
         assert np.allclose(w, 1.0 / P)
     h.close()
+
+
+def test_c4_shape_sampled_parity(capi, orc, synth):
+    """BASELINE config 4's per-particle shape (2000 components x 500 measurements, MaxQuantity 4000): a few
+    particles against the oracle over consecutive SLAM frames.  Exercises the large-size lanes of the
+    kernel (radix-select before the candidate sort, counting sort of > 4096 pairs, overflow lists,
+    thousands of map-estimate points) that the small tests never reach."""
+    P, N, M = 4, 2000, 500
+    sc = synth.make_scene(P, N, M, seed=33)
+    h = capi.Handle(sc.params, max_particles=P, max_components=2 * N, max_measurements=M, max_pairs=16 * M)
+    nav = orc.Navigator(orc.make_config(sc.params), P, sc.poses[0])
+    h.reset(P, sc.poses[0], sc.map_w, sc.map_m, sc.map_P)
+    h.set_poses(sc.poses)
+    for i in range(P):
+        nav.set_pose(i, sc.poses[i])
+        nav.set_map(i, sc.map_w, sc.map_m, sc.map_P)
+    for f in range(3):
+        fr = sc.next_frame()
+        h.update(fr.reading, synth.DT, fr.gauss)
+        nav.update(fr.reading, synth.DT, fr.gauss)
+        # the Parallel.For body alone (maps + alphas); with 500 measurements exp() of the log-likelihood
+        # underflows to 0 in FP64 on both sides, so compare the parts of WeightAlpha through the stage API too
+        h.upload_frame_inputs(None, fr.z)
+        gbest, gres = h.slam_update(fr.z, fr.u)
+        obest, ores, oanc = nav.slam_update(fr.z, fr.u)
+        assert (gbest, gres) == (obest, ores), f"frame {f}"
+        assert h.get_ancestors().tolist() == oanc.tolist()
+        assert h.get_alphas().tolist() == nav.get_alphas().tolist() or close_rel(h.get_alphas(), nav.get_alphas())
+        counts = h.get_map_counts()
+        for i in range(P):
+            om = nav.get_map(i)
+            assert counts[i] == len(om[0]), f"frame {f} particle {i}: {counts[i]} vs {len(om[0])}"
+            assert_maps_equal(h.get_map(i), om, f"frame {f} particle {i}")
+    # WeightAlpha parts at this size (J ~ 1600 points, thousands of components)
+    pose = nav.get_poses()[0]
+    prior = nav.get_map(0)
+    fr = sc.next_frame()
+    ocfg = orc.make_config(sc.params)
+    pred = orc.predict(ocfg, pose, *prior, fr.z)[:3]
+    corr = orc.prune(ocfg, *orc.correct(ocfg, pose, *pred, fr.z))
+    exp = orc.weight_alpha(ocfg, pose, fr.z, pred, corr)
+    got = h.stage_weight_alpha(pose, fr.z, pred, corr)
+    assert got["J"] == exp["J"] and exp["J"] > 1000
+    for k in ("pcount", "ccount", "ploglik", "cloglik", "setloglik"):
+        assert close_rel(got[k], exp[k]), (k, got[k], exp[k])
+    h.close()
