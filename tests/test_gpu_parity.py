@@ -494,3 +494,28 @@ def test_c4_shape_sampled_parity(capi, orc, synth):
     for k in ("pcount", "ccount", "ploglik", "cloglik", "setloglik"):
         assert close_rel(got[k], exp[k]), (k, got[k], exp[k])
     h.close()
+
+
+def test_big_particle_fallback_lanes(capi, orc, synth):
+    """One particle with a map far beyond the shared-memory capacities of the fused kernel (more than 8192
+    gated pairs, tens of thousands of pre-prune candidates, thousands of map-estimate points): the
+    slab-resident (global memory) lanes must give the same answer.  Shape is towards BASELINE config 3."""
+    P, N, M = 2, 9000, 1000
+    sc = synth.make_scene(P, N, M, seed=35)
+    h = capi.Handle(sc.params, max_particles=P, max_components=2 * N, max_measurements=M, max_pairs=24 * M)
+    nav = orc.Navigator(orc.make_config(sc.params), P, sc.poses[0], only_mapping=True)
+    h.reset(P, sc.poses[0], sc.map_w, sc.map_m, sc.map_P)
+    h.set_poses(sc.poses)
+    for i in range(P):
+        nav.set_pose(i, sc.poses[i])
+        nav.set_map(i, sc.map_w, sc.map_m, sc.map_P)
+    for f in range(4):
+        fr = sc.next_frame()
+        h.counters(reset=True)
+        h.slam_update(fr.z, fr.u, only_mapping=True)
+        nav.slam_update(fr.z, fr.u)
+        for i in range(P):
+            assert_maps_equal(h.get_map(i), nav.get_map(i), f"frame {f} particle {i}")
+    ctr = h.counters()
+    assert ctr["pairs"] / ctr["particle_frames"] > 8192, ctr   # last frame: beyond the shared-memory pair lists
+    h.close()
