@@ -25,6 +25,7 @@ struct Ctx {
     unsigned long long selkey;
     double pose[7];
     CellGrid grid;
+    CellGrid vg;       // copy of the frame's camera-frame measurement grid header
     long long tlast;
     unsigned long long tphase[32];
     unsigned int dbg[16];
@@ -165,7 +166,7 @@ __device__ __forceinline__ void enumerate_then_process(Smem& sm, int n_items, ui
 // gate lookup: append every (k, i) with |m_i - c_k|^2 within the correct gate (PHD:882, MAP:170-184)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void gate_append(const KParams& p, Smem& sm, const Slab& s, int i, const double* m,
-                                            const Quat& local)
+                                            const Quat& local, bool grid_in_smem)
 {
     const DevCfg& c = p.cfg;
     const int M = p.M;
@@ -176,15 +177,18 @@ __device__ __forceinline__ void gate_append(const KParams& p, Smem& sm, const Sl
         }
         return;
     }
-    const CellGrid& g = p.vgrid->g;
+    // grid_in_smem: the cell offsets / items of the camera-frame grid were copied to sm.gstart / sm.kidx
+    const CellGrid& g = sm.ctx.vg;
     int lo[3], hi[3];
     if (!grid_range(g, local.x, local.y, local.z, c.gate_r + 1e-9, lo, hi)) return;
     for (int cz = lo[2]; cz <= hi[2]; cz++)
         for (int cy = lo[1]; cy <= hi[1]; cy++) {
             int rowc = (cz * g.dim[1] + cy) * g.dim[0];
-            int b = __ldg(&p.vgrid->start[rowc + lo[0]]), e = __ldg(&p.vgrid->start[rowc + hi[0] + 1]);
+            int b, e;
+            if (grid_in_smem) { b = sm.gstart[rowc + lo[0]]; e = sm.gstart[rowc + hi[0] + 1]; }
+            else { b = __ldg(&p.vgrid->start[rowc + lo[0]]); e = __ldg(&p.vgrid->start[rowc + hi[0] + 1]); }
             for (int t = b; t < e; t++) {
-                int k = __ldg(&p.vitems[t]);
+                int k = grid_in_smem ? sm.kidx[t] : __ldg(&p.vitems[t]);
                 double dx = m[0] - sm.cs[3 * k], dy = m[1] - sm.cs[3 * k + 1], dz = m[2] - sm.cs[3 * k + 2];
                 double d2 = dx * dx + dy * dy + dz * dz;
                 if (d2 <= c.gate_r2) {
@@ -261,6 +265,14 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
     const bool do_births = (p.mode == MODE_FRAME || p.mode == MODE_STAGE_PREDICT);
     const bool do_correct = (p.mode == MODE_FRAME || p.mode == MODE_STAGE_CORRECT);
 
+    // the frame's camera-frame measurement grid: offsets and items into shared memory for the A2 walk
+    // (sm.gstart / sm.kidx are reused by the per-particle grids later in the frame)
+    const bool vgrid_smem = do_correct && !c.ungated && M > 0;
+    if (vgrid_smem) {
+        const int ncell = sm.ctx.vg.ncell;
+        for (int a = tid; a <= ncell; a += kBlock) sm.gstart[a] = __ldg(&p.vgrid->start[a]);
+        for (int a = tid; a < M; a += kBlock) sm.kidx[a] = __ldg(&p.vitems[a]);
+    }
     // A1: measurements in map space (PRM:299-312)
     for (int k = tid; k < M; k += kBlock) {
         double ck[3];
@@ -284,7 +296,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         double pdi = detection_probability(c, mp);
         s.ppd[i] = pdi;
         s.pwmd[i] = (1 - pdi) * w;
-        if (do_correct) gate_append(p, sm, s, i, m, local);
+        if (do_correct) gate_append(p, sm, s, i, m, local, vgrid_smem);
         if (do_births) {
             // upper bound of ln(w N(x; m, P)) at distance d: ln(w mult) - d^2 / (2 trace P)  (lambda_max <= trace)
             double P[9];
@@ -352,11 +364,18 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
                 sm, N, hits, hits_cap, reinterpret_cast<uint2*>(s.edst), p.lay.cap_edges / 2,
                 [&](int i, auto emit) {
                     const double m[3] = {s.pm[i], s.pm[capp + i], s.pm[2 * capp + i]};
-                    int lo[3], hi[3];
-                    if (!grid_range(g, m[0], m[1], m[2], c.explore_r + 1e-9, lo, hi)) return;
                     // terms whose upper bound is below 1e-14 of the threshold cannot move the sum out of the
-                    // +-1e-9 band that triggers the exact replay (at most max_components of them are skipped)
+                    // +-1e-9 band that triggers the exact replay (at most max_components of them are skipped);
+                    // that bound also gives each component its own search radius inside the 1.5 m gate
                     const double lognorm = s.cnorm[i], itr = s.crad[i];
+                    double reach = c.explore_r + 1e-9;
+                    if (itr > 0) {
+                        const double r2max = (lognorm - logskip) / itr;
+                        if (!(r2max > 0)) return;
+                        reach = fmin(reach, sqrt(r2max) * (1.0 + 1e-9) + 1e-12);
+                    }
+                    int lo[3], hi[3];
+                    if (!grid_range(g, m[0], m[1], m[2], reach, lo, hi)) return;
                     for (int cz = lo[2]; cz <= hi[2]; cz++)
                         for (int cy = lo[1]; cy <= hi[1]; cy++) {
                             const int rowc = (cz * g.dim[1] + cy) * g.dim[0];
@@ -463,7 +482,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         double pdi = detection_probability(c, mp);
         s.ppd[i] = pdi;
         s.pwmd[i] = (1 - pdi) * c.birth_w;
-        if (do_correct) gate_append(p, sm, s, i, m, local);
+        if (do_correct) gate_append(p, sm, s, i, m, local, false);
     }
     __syncthreads();
     if (tid == 0 && sm.ctx.npairs > p.lay.cap_pairs) { sm.ctx.npairs = p.lay.cap_pairs; sm.ctx.status |= ST_OVER_PAIRS; }
@@ -984,6 +1003,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_particle_update(const __grid_cons
         __syncthreads();
     }
 
+    if (tid == 0) sm.ctx.vg = p.vgrid->g;
     unsigned long long acc_in = 0, acc_out = 0, acc_pairs = 0, acc_pf = 0;   // thread 0 only
     if (tid == 0) { for (int a = 0; a < 32; a++) sm.ctx.tphase[a] = 0; for (int a = 0; a < 16; a++) sm.ctx.dbg[a] = 0; sm.ctx.tlast = clock64(); }
     for (int particle = p.first + blockIdx.x; particle < p.first + p.P; particle += gridDim.x) {
