@@ -153,12 +153,14 @@ __device__ __forceinline__ void enumerate_then_process(Smem& sm, int n_items, ui
                 else sm.ctx.status |= ST_OVER_PAIRS;
             });
         __syncthreads();
+        PHASE_MARK(sm, 29);
         const int tot = sm.ctx.nsel2;
         const int cnt = min(tot, list_cap);
         for (int e = threadIdx.x; e < cnt; e += kBlock) process((int)list[e].x, (int)list[e].y);
         const int nov = min(max(tot - list_cap, 0), ovf_cap);
         for (int e = threadIdx.x; e < nov; e += kBlock) process((int)ovf[e].x, (int)ovf[e].y);
         __syncthreads();
+        PHASE_MARK(sm, 30);
     }
 }
 

@@ -54,6 +54,9 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
     const int tid = threadIdx.x, capj = p.lay.cap_j;
     const double* jx = s.jm; const double* jy = s.jm + capj; const double* jz = s.jm + 2 * capj;
     const CellGrid& g = sm.ctx.grid;
+    // cell-ordered single-precision copy of the points (x, y, z, index) in shared memory, made by the caller
+    const bool qsm = (J * 2 <= kVsCap);
+    const float4* qf = reinterpret_cast<const float4*>(sm.vs);
     for (int t = tid; t < J; t += kBlock) vs[t] = 0.0;
     __syncthreads();
     PHASE_MARK(sm, 20);
@@ -95,14 +98,25 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
                 }
                 return;
             }
+            const float xf = (float)x, yf = (float)y, zf = (float)z;
+            const float r2f = (float)r2 * 1.001f + 1e-4f;   // generous: an extra far term is harmless
             for (int cz = lo[2]; cz <= hi[2]; cz++)
                 for (int cy = lo[1]; cy <= hi[1]; cy++) {
                     const int rowc = (cz * g.dim[1] + cy) * g.dim[0];
                     const int b = sm.gstart[rowc + lo[0]], e = sm.gstart[rowc + hi[0] + 1];
-                    for (int q = b; q < e; q++) {
-                        const int t = s.gitems[q];
-                        const double dx = jx[t] - x, dy = jy[t] - y, dz = jz[t] - z;
-                        if (dx * dx + dy * dy + dz * dz <= r2) emit(i, t);
+                    if (qsm) {
+                        for (int q = b; q < e; q++) {
+                            const float4 v = qf[q];
+                            const float dx = v.x - xf, dy = v.y - yf, dz = v.z - zf;
+                            if (dx * dx + dy * dy + dz * dz <= r2f) emit(i, __float_as_int(v.w));
+                        }
+                    }
+                    else {
+                        for (int q = b; q < e; q++) {
+                            const int t = s.gitems[q];
+                            const double dx = jx[t] - x, dy = jy[t] - y, dz = jz[t] - z;
+                            if (dx * dx + dy * dy + dz * dz <= r2) emit(i, t);
+                        }
                     }
                 }
         },
@@ -132,9 +146,20 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
                         const int rowc = (cz * g.dim[1] + cy) * g.dim[0];
                         const int b = sm.gstart[rowc + lo[0]], e = sm.gstart[rowc + hi[0] + 1];
                         for (int q = b; q < e; q++) {
-                            const int t = s.gitems[q];
-                            const double dx = jx[t] - x, dy = jy[t] - y, dz = jz[t] - z;
-                            if (dx * dx + dy * dy + dz * dz <= r2) {
+                            int t;
+                            bool in;
+                            if (qsm) {
+                                const float4 v = qf[q];
+                                const float dx = v.x - (float)x, dy = v.y - (float)y, dz = v.z - (float)z;
+                                in = dx * dx + dy * dy + dz * dz <= (float)r2 * 1.001f + 1e-4f;
+                                t = __float_as_int(v.w);
+                            }
+                            else {
+                                t = s.gitems[q];
+                                const double dx = jx[t] - x, dy = jy[t] - y, dz = jz[t] - z;
+                                in = dx * dx + dy * dy + dz * dz <= r2;
+                            }
+                            if (in) {
                                 const int idx = atomicAdd(&sm.ctx.nsel2, 1);
                                 if (idx < list_cap) list[idx] = make_uint2((unsigned)i, (unsigned)t);
                                 else if (idx - list_cap < ovf_cap) ovf[idx - list_cap] = make_uint2((unsigned)i, (unsigned)t);
@@ -548,6 +573,14 @@ __device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const 
     PHASE_MARK(sm, 11);
     grid_build(sm.sh, sm.ctx.grid, sm.gstart, s.gitems, s.jm, s.jm + capj, s.jm + 2 * capj, J, kQueryCell, kQueryCell,
                kQueryCell);
+    if (J * 2 <= kVsCap) {
+        float4* qf = reinterpret_cast<float4*>(sm.vs);
+        for (int q = tid; q < J; q += kBlock) {
+            const int t = s.gitems[q];
+            qf[q] = make_float4((float)s.jm[t], (float)s.jm[capj + t], (float)s.jm[2 * capj + t], __int_as_float(t));
+        }
+        __syncthreads();
+    }
     PHASE_MARK(sm, 23);
     const double plog = eval_map_at_points(p, sm, s, pred, J, vs);
     PHASE_MARK(sm, 12);
