@@ -279,34 +279,54 @@ __device__ inline void grid_build(BlockShared& sh, CellGrid& g, int* start, int*
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += kBlock) atomicAdd(&start[grid_cell(g, px[i], py[i], pz[i])], 1);
     __syncthreads();
-    block_scan_array(sh, start, ncell + 1);   // start[c] = first slot of cell c, start[ncell] = n
-    // scatter with a per-cell cursor kept in items' tail?  Use a second pass with atomics on a copy:
-    // cursor = start (consumed), then restore by shifting.
+    // exclusive scan of the ncell + 1 counts: every thread owns a run of consecutive cells, so one
+    // block-wide scan of the run totals suffices
+    const int per = (ncell + 1 + kBlock - 1) / kBlock;
+    const int c0 = threadIdx.x * per;
+    {
+        int run = 0;
+        for (int a = 0; a < per; a++) { const int cc = c0 + a; if (cc <= ncell) run += start[cc]; }
+        int tot;
+        int prefix = block_excl_scan(sh, run, &tot);
+        for (int a = 0; a < per; a++) {
+            const int cc = c0 + a;
+            if (cc <= ncell) { const int v = start[cc]; start[cc] = prefix; prefix += v; }
+        }
+    }
+    __syncthreads();
+    // scatter with the offsets as cursors (start[c] ends up as the END of cell c) ...
     for (int i = threadIdx.x; i < n; i += kBlock) {
         int c = grid_cell(g, px[i], py[i], pz[i]);
         int slot = atomicAdd(&start[c], 1);
         items[slot] = i;
     }
     __syncthreads();
-    // start[c] now = end of cell c = original start[c+1]; shift right by one to restore
-    // (chunks from the top down, so a chunk never reads a slot a previous chunk already rewrote)
-    for (int base = (ncell / kBlock) * kBlock; base >= 0; base -= kBlock) {
-        int c = base + threadIdx.x;
-        int v = (c <= ncell && c > 0) ? start[c - 1] : 0;
+    // ... then shift right by one to restore the begin offsets (read the whole run first, then write)
+    {
+        int prev = (c0 > 0 && c0 - 1 <= ncell) ? start[c0 - 1] : 0;
+        int vals[16];
+        for (int a = 0; a < per && a < 16; a++) { const int cc = c0 + a; vals[a] = (cc <= ncell) ? start[cc] : 0; }
         __syncthreads();
-        if (c <= ncell) start[c] = v;
+        if (per <= 16) {
+            for (int a = 0; a < per; a++) {
+                const int cc = c0 + a;
+                if (cc <= ncell) start[cc] = (a == 0) ? prev : vals[a - 1];
+            }
+        }
         __syncthreads();
-    }
-    // ascending order inside each cell (deterministic enumeration)
-    for (int c = threadIdx.x; c < ncell; c += kBlock) {
-        int b = start[c], e = start[c + 1];
-        for (int i = b + 1; i < e; i++) {
-            int v = items[i], j = i - 1;
-            while (j >= b && items[j] > v) { items[j + 1] = items[j]; j--; }
-            items[j + 1] = v;
+        if (per > 16) {   // (not reached with kGridMaxCells <= 16 * kBlock; kept for safety)
+            for (int base = (ncell / kBlock) * kBlock; base >= 0; base -= kBlock) {
+                int c = base + threadIdx.x;
+                int v = (c <= ncell && c > 0) ? start[c - 1] : 0;
+                __syncthreads();
+                if (c <= ncell) start[c] = v;
+                __syncthreads();
+            }
         }
     }
-    __syncthreads();
+    // (The order of the indices inside a cell is whatever the atomics produced.  Every consumer either
+    // sorts what it derives from the walk -- gated pairs, merge edges, likelihood edges -- or only
+    // accumulates, so no per-cell sort is needed.)
 }
 
 // cell range covered by the ball (x,y,z; r); returns false if it misses the bounding box
