@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- RB-PHD SLAM per-frame update throughput on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|tiny] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c3|tiny] [--impl reference]
 
 One "step" = one frame = PHDNavigator.Update + SlamUpdate (PHD:295,323) over all particles of the
 workload, including weight normalisation / ESS test / resampling when it triggers.
@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "particle_frames_per_sec"
 UNIT = "particle-frames/s"
+MAPPING_ONLY = {"c3"}
 RECORD_BYTES = 80          # algorithmic FP64 record: weight + mean[3] + symmetric cov[6]
 PER_PARTICLE_BYTES = 128   # pose read+written (112) + weight read+written (16)
 
@@ -118,7 +119,8 @@ def cpu_baseline(workload, sample_particles, frames, seed):
     sc = synth.make_workload(workload, seed=seed, P=S)
     sc.params["nthreads"] = cores
     cfg = orc.make_config(sc.params)
-    nav = orc.Navigator(cfg, S, sc.poses[0])
+    mapping = workload in MAPPING_ONLY
+    nav = orc.Navigator(cfg, S, sc.poses[0], only_mapping=mapping)
     for i in range(S):
         nav.set_pose(i, sc.poses[i])
         nav.set_map(i, sc.map_w, sc.map_m, sc.map_P)
@@ -126,7 +128,8 @@ def cpu_baseline(workload, sample_particles, frames, seed):
     for _ in range(frames):
         fr = sc.next_frame()
         t0 = time.perf_counter()
-        nav.update(fr.reading, synth.DT, fr.gauss)
+        if not mapping:
+            nav.update(fr.reading, synth.DT, fr.gauss)
         nav.slam_update(fr.z, fr.u)
         times.append(time.perf_counter() - t0)
     nav.close()
@@ -146,14 +149,15 @@ def run_reference(args, rank, world):
     wl = synth.WORKLOADS[wl_name]
     cores = os.cpu_count() or 1
     # one step = one frame over a bounded particle sample sized for ~1-3 s per step
-    per_pf = {"c4": 0.6, "c4s": 0.6, "c2": 0.05, "c3": 8.0, "tiny": 0.001}.get(wl_name, 0.1)
+    per_pf = {"c4": 0.6, "c4s": 0.6, "c2": 0.05, "c3": 25.0, "tiny": 0.001}.get(wl_name, 0.1)
     S = int(max(cores, min(wl["P"], round(2.0 * cores / per_pf))))
     S = max(cores, (S // cores) * cores)
     from oracle import orc
     sc = synth.make_workload(wl_name, seed=synth.SEED, P=S)
     sc.params["nthreads"] = cores
     cfg = orc.make_config(sc.params)
-    nav = orc.Navigator(cfg, S, sc.poses[0])
+    mapping = wl_name in MAPPING_ONLY
+    nav = orc.Navigator(cfg, S, sc.poses[0], only_mapping=mapping)
     for i in range(S):
         nav.set_pose(i, sc.poses[i])
         nav.set_map(i, sc.map_w, sc.map_m, sc.map_P)
@@ -161,7 +165,8 @@ def run_reference(args, rank, world):
     for f in range(args.warmup + args.steps):
         fr = sc.next_frame()
         t0 = time.perf_counter()
-        nav.update(fr.reading, synth.DT, fr.gauss)
+        if not mapping:
+            nav.update(fr.reading, synth.DT, fr.gauss)
         nav.slam_update(fr.z, fr.u)
         dt = time.perf_counter() - t0
         if f >= args.warmup:
@@ -189,7 +194,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "tiny", "c4s"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "tiny", "c4s"])
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="frames of the host-buffer pass (default min(steps, 10))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -235,6 +240,7 @@ def main():
     def run_workload(name, steps, warmup, e2e_steps, do_profile):
         wl = synth.WORKLOADS[name]
         P, N, M = wl["P"], wl["N"], wl["M"]
+        mapping = name in MAPPING_ONLY   # config 3: independent mapping-only filters (PHD:297-300, 334)
         lo, hi = sharded.block_range(rank, world, P)
         Pl = hi - lo
         sc = synth.make_workload(name, seed=synth.SEED)
@@ -255,7 +261,7 @@ def main():
         h.synchronize()
         stream = torch.cuda.ExternalStream(h.stream, device=local_rank)
         for f in range(warmup):
-            nav.frame(frames[f].reading, synth.DT, M, frames[f].u, slot=f)
+            nav.frame(frames[f].reading, synth.DT, M, frames[f].u, slot=f, only_mapping=mapping)
         h.synchronize()
         h.counters(reset=True)
         launches0 = h.kernel_launches
@@ -269,7 +275,7 @@ def main():
         torch.cuda.synchronize()
         e0.record(stream)
         for f in range(warmup, nframes):
-            nav.frame(frames[f].reading, synth.DT, M, frames[f].u, slot=f)
+            nav.frame(frames[f].reading, synth.DT, M, frames[f].u, slot=f, only_mapping=mapping)
         e1.record(stream)
         h.synchronize()
         torch.cuda.synchronize()
@@ -280,7 +286,7 @@ def main():
         ctr = h.counters()
         phases = h.phase_cycles()
         dbgc = h.debug_counters()
-        prof = h.profile_read(steps) if (do_profile and world == 1) else None
+        prof = h.profile_read(steps) if do_profile else None
         resampled_frames = None
         res = dict(P=P, N=N, M=M, phases=phases, dbg=dbgc, ms_total=ms, steps=steps, launches=launches, counters=ctr, prof=prof, clocks=clocks,
                    mean_components=ctr["comps_out"] / max(1, ctr["particle_frames"]),
@@ -296,12 +302,13 @@ def main():
             def host_frame(fr):
                 nonlocal h2d, d2h, nres
                 if world == 1:
-                    h.update(fr.reading, synth.DT, fr.gauss[lo:hi])
-                    best, r = h.slam_update(fr.z, fr.u)
+                    if not mapping:
+                        h.update(fr.reading, synth.DT, fr.gauss[lo:hi])
+                    best, r = h.slam_update(fr.z, fr.u, only_mapping=mapping)
                     bl = best
                 else:
                     h.upload_frame_inputs(fr.gauss[lo:hi], fr.z, slot=0)
-                    best, r = nav.frame(fr.reading, synth.DT, M, fr.u, slot=0)
+                    best, r = nav.frame(fr.reading, synth.DT, M, fr.u, slot=0, only_mapping=mapping)
                     bl = best - lo if lo <= best < hi else -1
                 h2d += 8 * (6 * Pl + 3 * M + 6)
                 d2h += 64
@@ -389,8 +396,8 @@ def main():
                        "steps": main_res["e2e_steps"], "resampling_frames": main_res["e2e_resamples"]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = {"c4": 16, "c4s": 16, "c2": 160, "tiny": 64}.get(args.workload, 16)
-        nfr = {"c4": 3, "c4s": 3, "c2": 4, "tiny": 4}.get(args.workload, 2)
+        sample = {"c4": 16, "c4s": 16, "c2": 160, "c3": os.cpu_count() or 1, "tiny": 64}.get(args.workload, 16)
+        nfr = {"c4": 3, "c4s": 3, "c2": 4, "c3": 1, "tiny": 4}.get(args.workload, 2)
         line["cpu_baseline"] = cpu_baseline(args.workload, sample, nfr, synth.SEED)
 
     if not args.no_secondary and args.workload == "c4" and world == 1:

@@ -974,8 +974,12 @@ int rbphd_slam_update_local(rbphd_navigator* nav, int slot, int m, int only_mapp
     if (m < 0 || m > nav->Mcap) return fail(nav, RBPHD_ERR_ARGUMENT, "m > max_measurements");
     if (slot < 0 || slot >= nav->slots) return fail(nav, RBPHD_ERR_ARGUMENT, "input slot out of range");
     if (int r = set_device(nav)) return r;
-    if (int r = enqueue_map_update(nav, m, only_mapping, MODE_FRAME, slot)) return r;
+    cudaEvent_t* ev = nullptr;   // stage timing: the pose and the global tail are separate calls on this path
+    if (nav->prof_frames < nav->prof_max) ev = &nav->pev[6 * (size_t)nav->prof_frames++];
+    if (ev) { cudaEventRecord(ev[0], nav->stream); cudaEventRecord(ev[1], nav->stream); }
+    if (int r = enqueue_map_update(nav, m, only_mapping, MODE_FRAME, slot, ev ? ev + 2 : nullptr)) return r;
     if (only_mapping) { launch_flip(nav->stream, nav->st); nav->launches += 1; }
+    if (ev) { cudaEventRecord(ev[4], nav->stream); cudaEventRecord(ev[5], nav->stream); }
     return check_async(nav, "local slam update");
 }
 

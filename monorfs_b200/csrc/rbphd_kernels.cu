@@ -763,7 +763,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
                 }
             };
             int lo[3], hi[3];
-            bool brute = !(rho == rho) || isinf(rho) || !fsm;
+            bool brute = !(rho == rho) || isinf(rho);
             if (!brute) {
                 if (!grid_range(g, x, y, z, rho, lo, hi)) continue;
                 long cells = (long)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
@@ -783,12 +783,21 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
                 for (int cy = lo[1]; cy <= hi[1]; cy++) {
                     const int rowc = (cz * g.dim[1] + cy) * g.dim[0];
                     const int qb = sm.gstart[rowc + lo[0]], qe = sm.gstart[rowc + hi[0] + 1];
-                    for (int q = qb; q < qe; q++)
-                        if (fabsf(fx[q] - xf) <= rf && fabsf(fy[q] - yf) <= rf && fabsf(fz[q] - zf) <= rf) {
-                            const int r2 = frank[q];
+                    if (fsm) {
+                        for (int q = qb; q < qe; q++)
+                            if (fabsf(fx[q] - xf) <= rf && fabsf(fy[q] - yf) <= rf && fabsf(fz[q] - zf) <= rf) {
+                                const int r2 = frank[q];
+                                if (r2 > r && fabs(tx[r2] - x) <= rho && fabs(ty[r2] - y) <= rho && fabs(tz[r2] - z) <= rho)
+                                    test(r2);
+                            }
+                    }
+                    else {   // more candidates than the shared-memory copy holds: walk the cell lists in the slab
+                        for (int q = qb; q < qe; q++) {
+                            const int r2 = s.gitems[q];
                             if (r2 > r && fabs(tx[r2] - x) <= rho && fabs(ty[r2] - y) <= rho && fabs(tz[r2] - z) <= rho)
                                 test(r2);
                         }
+                    }
                 }
         }
     }

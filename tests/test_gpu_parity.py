@@ -519,3 +519,30 @@ def test_big_particle_fallback_lanes(capi, orc, synth):
     ctr = h.counters()
     assert ctr["pairs"] / ctr["particle_frames"] > 8192, ctr   # last frame: beyond the shared-memory pair lists
     h.close()
+
+
+def test_c3_shape_sampled_parity(capi, orc, synth):
+    """BASELINE config 3's per-particle shape (mapping-only, 50 000 components x 1000 measurements per frame,
+    box scaled x25): two filters on the GPU, one of them against the oracle over two frames (the oracle needs
+    ~25 s per particle-frame at this size), the other checked through size-independent properties."""
+    P, N, M = 2, 50000, 1000
+    sc = synth.make_workload("c3", P=P, N=N, M=M, seed=35)
+    h = capi.Handle(sc.params, max_particles=P, max_components=2 * N, max_measurements=M, max_pairs=16 * M)
+    h.reset(P, sc.poses[0], sc.map_w, sc.map_m, sc.map_P)
+    h.set_poses(sc.poses)
+    nav = orc.Navigator(orc.make_config(sc.params), 1, sc.poses[0], only_mapping=True)
+    nav.set_pose(0, sc.poses[0])
+    nav.set_map(0, sc.map_w, sc.map_m, sc.map_P)
+    for f in range(2):
+        fr = sc.next_frame()
+        h.slam_update(fr.z, fr.u, only_mapping=True)
+        nav.slam_update(fr.z, fr.u)
+        counts = h.get_map_counts()
+        om = nav.get_map(0)
+        assert counts[0] == len(om[0]) and counts[0] > N
+        assert_maps_equal(h.get_map(0), om, f"c3 frame {f}")
+        w1, m1, P1 = h.get_map(1)
+        assert np.all(np.isfinite(w1)) and np.all(np.isfinite(m1)) and np.all(np.isfinite(P1))
+        assert abs(len(w1) - counts[0]) < 0.01 * N
+    assert np.array_equal(h.get_weights(), np.full(P, 1.0 / P))   # OnlyMapping leaves the weights alone (PHD:334)
+    h.close()
