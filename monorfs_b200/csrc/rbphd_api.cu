@@ -198,11 +198,13 @@ void make_layout(ScratchLayout& l, int cap, int Mcap, int cap_pairs, int maxq)
     auto take = [&](size_t& field, size_t bytes) { field = off; off = align_up(off + bytes, 16); };
     const size_t D = sizeof(double), I = sizeof(int), U = sizeof(unsigned long long);
     take(l.pm, 3 * D * l.cap_pred);  take(l.pwt, D * l.cap_pred);  take(l.pwmd, D * l.cap_pred);
-    take(l.ppd, D * l.cap_pred);     take(l.flagf, I * (l.cap_pred + 2));  take(l.fidx, I * (l.cap_pred + 2));
+    take(l.ppd, D * l.cap_pred);     take(l.cact, I * (l.cap_pred + 2));
     take(l.bidx, I * (cap_pairs + 2));
     take(l.pkey, U * cap_pairs);     take(l.pt, D * cap_pairs);    take(l.pmean, 3 * D * cap_pairs);
-    take(l.pcov, 9 * D * cap_pairs); take(l.pwgt, D * cap_pairs);
+    take(l.pwgt, D * cap_pairs);
+    take(l.crec, 37 * D * l.cap_pred); take(l.cpn, 9 * D * l.cap_pred);
     take(l.skey, U * l.cap_sort);    take(l.sval, sizeof(unsigned) * l.cap_sort);
+    take(l.skey2, U * l.cap_sort);   take(l.sval2, sizeof(unsigned) * l.cap_sort);
     take(l.tw, D * l.cap_top);       take(l.tm, 3 * D * l.cap_top); take(l.tP, 9 * D * l.cap_top);
     take(l.rho, D * l.cap_top);
     take(l.ecnt, I * (l.cap_top + 2)); take(l.edst, I * l.cap_edges);

@@ -66,6 +66,47 @@ __device__ inline int block_scan_array(BlockShared& sh, int* a, int n)
     return carry;
 }
 
+// in-place exclusive scans of two int arrays of length n at once (one pass, the two sums packed into
+// the halves of a 64-bit add; each total must stay below 2^31); totals in *tot_a / *tot_b
+__device__ inline void block_scan_array2(BlockShared& sh, int* a, int* b, int n, int* tot_a, int* tot_b)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long carry = 0;
+    unsigned long long* wsum = reinterpret_cast<unsigned long long*>(sh.warp_d);   // kWarps + 1 entries
+    for (int base = 0; base < n; base += kBlock) {
+        const int i = base + threadIdx.x;
+        unsigned long long v = 0;
+        if (i < n) v = (unsigned long long)(unsigned)a[i] | ((unsigned long long)(unsigned)b[i] << 32);
+        unsigned long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        __syncthreads();
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned long long w = (lane < kWarps) ? wsum[lane] : 0ull;
+            unsigned long long wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            if (lane < kWarps) wsum[lane] = wi - w;
+            if (lane == kWarps - 1) wsum[kWarps] = wi;
+        }
+        __syncthreads();
+        const unsigned long long ex = carry + wsum[warp] + incl - v;
+        if (i < n) { a[i] = (int)(unsigned)(ex & 0xffffffffull); b[i] = (int)(unsigned)(ex >> 32); }
+        carry += wsum[kWarps];
+    }
+    __syncthreads();
+    *tot_a = (int)(unsigned)(carry & 0xffffffffull);
+    *tot_b = (int)(unsigned)(carry >> 32);
+}
+
 __device__ __forceinline__ double block_sum(BlockShared& sh, double v)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -115,6 +156,119 @@ __device__ inline void block_bitonic_sort(unsigned long long* key, unsigned int*
             __syncthreads();
         }
     }
+}
+
+// lanes of the warp whose 8-bit digit equals this lane's (invalid lanes match nobody): eight ballots, which
+// issue at full rate, instead of MATCH.ANY
+__device__ __forceinline__ unsigned warp_match_digit(unsigned d, bool valid)
+{
+    unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned bal = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return valid ? peers : 0u;
+}
+
+// Stable LSD radix sort (8-bit digits) of n (key,val) pairs, ascending by key; equal keys keep their input
+// order.  (k0,v0) holds the input, (k1,v1) is scratch of the same length (any memory space); the return value
+// says which of the two holds the result.  Every warp owns a contiguous chunk of the input, counts its digits
+// into its own 256-bin histogram (whist: kWarps*256 ints of shared memory; dbase: 256 ints) and ranks equal
+// digits inside a 32-element row with match_any, so no atomics are needed and the order is deterministic.
+// Digits on which all keys agree are skipped (weights span a few binades: the leading byte usually does).
+__device__ inline int block_radix_sort(BlockShared& sh, unsigned long long* k0, unsigned int* v0,
+                                       unsigned long long* k1, unsigned int* v1, int n, int* whist, int* dbase, unsigned int* tdbg = nullptr)
+{
+    long long t0 = clock64();
+#define RS_MARK(i) do { if (tdbg && threadIdx.x == 0) { long long t1 = clock64(); tdbg[i] += (unsigned int)((t1 - t0) >> 4); t0 = t1; } } while (0)
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long o = 0, a = ~0ull;
+    for (int e = threadIdx.x; e < n; e += kBlock) { const unsigned long long k = k0[e]; o |= k; a &= k; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { o |= __shfl_xor_sync(0xffffffffu, o, d); a &= __shfl_xor_sync(0xffffffffu, a, d); }
+    __syncthreads();
+    if (lane == 0) { sh.warp_d[warp] = __longlong_as_double((long long)o); sh.warp_d[kWarps + warp] = __longlong_as_double((long long)a); }
+    __syncthreads();
+    o = 0; a = ~0ull;
+    for (int w = 0; w < kWarps; w++) {
+        o |= (unsigned long long)__double_as_longlong(sh.warp_d[w]);
+        a &= (unsigned long long)__double_as_longlong(sh.warp_d[kWarps + w]);
+    }
+    const unsigned long long diff = (n > 1) ? (o ^ a) : 0ull;
+    RS_MARK(12);
+    const int C = (((n + kWarps - 1) / kWarps) + 31) & ~31;
+    const int beg = min(n, warp * C), end = min(n, beg + C);
+    int* wh = whist + warp * 256;
+    const unsigned lt = (1u << lane) - 1u;
+    int cur = 0;
+    for (int shift = 0; shift < 64; shift += 8) {
+        if (((diff >> shift) & 255ull) == 0) continue;
+        const unsigned long long* ks = cur ? k1 : k0;
+        const unsigned int* vs = cur ? v1 : v0;
+        unsigned long long* kd = cur ? k0 : k1;
+        unsigned int* vd = cur ? v0 : v1;
+        __syncthreads();
+        for (int b = threadIdx.x; b < kWarps * 256; b += kBlock) whist[b] = 0;
+        __syncthreads();
+        // rows of 32 keys, kRows rows loaded ahead of their use (the source may be global memory)
+        constexpr int kRows = 8;
+        for (int base = beg; base < end; base += 32 * kRows) {
+            unsigned long long kk[kRows];
+#pragma unroll
+            for (int r = 0; r < kRows; r++) { const int e = base + 32 * r + lane; kk[r] = (e < end) ? ks[e] : 0ull; }
+#pragma unroll
+            for (int r = 0; r < kRows; r++) {
+                const int e = base + 32 * r + lane;
+                const bool valid = e < end;
+                const unsigned d = (unsigned)((kk[r] >> shift) & 255ull);
+                const unsigned peers = warp_match_digit(d, valid);
+                if (valid && lane == __ffs(peers) - 1) wh[d] += __popc(peers);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        RS_MARK(13);
+        int tot = 0;   // digit-major offsets: all warps' counts of digit t, in warp order
+        if (threadIdx.x < 256)
+#pragma unroll
+            for (int w = 0; w < kWarps; w++) { const int c = whist[w * 256 + threadIdx.x]; whist[w * 256 + threadIdx.x] = tot; tot += c; }
+        int total;
+        const int basep = block_excl_scan(sh, tot, &total);
+        if (threadIdx.x < 256) dbase[threadIdx.x] = basep;
+        __syncthreads();
+        RS_MARK(14);
+        constexpr int kRowsS = 4;
+        for (int base = beg; base < end; base += 32 * kRowsS) {
+            unsigned long long kk[kRowsS];
+            unsigned int vv[kRowsS];
+#pragma unroll
+            for (int r = 0; r < kRowsS; r++) {
+                const int e = base + 32 * r + lane;
+                kk[r] = 0; vv[r] = 0;
+                if (e < end) { kk[r] = ks[e]; vv[r] = vs[e]; }
+            }
+#pragma unroll
+            for (int r = 0; r < kRowsS; r++) {
+                const int e = base + 32 * r + lane;
+                const bool valid = e < end;
+                const unsigned d = (unsigned)((kk[r] >> shift) & 255ull);
+                const unsigned peers = warp_match_digit(d, valid);
+                const int off = valid ? wh[d] : 0;
+                __syncwarp();
+                if (valid && lane == __ffs(peers) - 1) wh[d] = off + __popc(peers);
+                __syncwarp();
+                if (valid) { const int pos = dbase[d] + off + __popc(peers & lt); kd[pos] = kk[r]; vd[pos] = vv[r]; }
+            }
+        }
+        cur ^= 1;
+        __syncthreads();
+        RS_MARK(15);
+    }
+    __syncthreads();
+    return cur;
 }
 
 // Keep the `want` smallest (key, then val) of n candidates when n exceeds what a later sort can hold:

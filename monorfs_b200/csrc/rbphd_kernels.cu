@@ -20,7 +20,7 @@ namespace rbphd {
 // shared-memory context of one CTA of k_particle_update
 // ------------------------------------------------------------------------------------------------
 struct Ctx {
-    int N, B, Npred, npairs, npairs_prior, L, ncand, W0, nedges, nout, nF, nU, nsel, nsel2;
+    int N, B, Npred, npairs, npairs_prior, L, ncand, W0, nedges, nout, nF, nU, nsel, nsel2, nact;
     int status;
     unsigned long long selkey;
     double pose[7];
@@ -60,15 +60,17 @@ struct Smem {
 
 constexpr int kSortCap = 8192;   // (key,val) pairs the shared-memory sort buffer holds
 constexpr int kVsCap = 4096;
+static_assert(sizeof(double) * kVsCap >= sizeof(int) * kWarps * 256, "the radix-sort histograms alias the vs buffer");
 
 struct Slab {
     // predicted map = prior components followed by births
     double *pm, *pwt, *pwmd, *ppd;
-    int *flagf, *fidx, *bidx;
+    int *cact, *bidx;      // predicted components with at least one gated pair; pair slots in output order
     unsigned long long* pkey;
-    double *pt, *pmean, *pcov, *pwgt;
-    unsigned long long* skey;
-    unsigned int* sval;
+    double *pt, *pmean, *pwgt;
+    double *crec, *cpn;    // per gated component: measurement-space record (kRec doubles) and updated covariance (9)
+    unsigned long long *skey, *skey2;
+    unsigned int *sval, *sval2;
     double *tw, *tm, *tP, *rho;
     int *ecnt, *edst, *nstate, *nowner, *nflag, *gitems;
     int *jidx;
@@ -87,11 +89,13 @@ __device__ __forceinline__ Slab make_slab(unsigned char* base, const ScratchLayo
 {
     Slab s;
     s.pm = (double*)(base + l.pm); s.pwt = (double*)(base + l.pwt); s.pwmd = (double*)(base + l.pwmd);
-    s.ppd = (double*)(base + l.ppd); s.flagf = (int*)(base + l.flagf); s.fidx = (int*)(base + l.fidx);
+    s.ppd = (double*)(base + l.ppd); s.cact = (int*)(base + l.cact);
     s.bidx = (int*)(base + l.bidx);
     s.pkey = (unsigned long long*)(base + l.pkey); s.pt = (double*)(base + l.pt);
-    s.pmean = (double*)(base + l.pmean); s.pcov = (double*)(base + l.pcov); s.pwgt = (double*)(base + l.pwgt);
+    s.pmean = (double*)(base + l.pmean); s.pwgt = (double*)(base + l.pwgt);
+    s.crec = (double*)(base + l.crec); s.cpn = (double*)(base + l.cpn);
     s.skey = (unsigned long long*)(base + l.skey); s.sval = (unsigned int*)(base + l.sval);
+    s.skey2 = (unsigned long long*)(base + l.skey2); s.sval2 = (unsigned int*)(base + l.sval2);
     s.tw = (double*)(base + l.tw); s.tm = (double*)(base + l.tm); s.tP = (double*)(base + l.tP);
     s.rho = (double*)(base + l.rho);
     s.ecnt = (int*)(base + l.ecnt); s.edst = (int*)(base + l.edst); s.nstate = (int*)(base + l.nstate);
@@ -165,18 +169,16 @@ __device__ __forceinline__ void enumerate_then_process(Smem& sm, int n_items, ui
 }
 
 // ------------------------------------------------------------------------------------------------
-// gate lookup: append every (k, i) with |m_i - c_k|^2 within the correct gate (PHD:882, MAP:170-184)
+// gate lookup: f(k) for every measurement k with |m_i - c_k|^2 within the correct gate (PHD:882, MAP:170-184)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gate_append(const KParams& p, Smem& sm, const Slab& s, int i, const double* m,
-                                            const Quat& local, bool grid_in_smem)
+template <class F>
+__device__ __forceinline__ void gate_walk(const KParams& p, const Smem& sm, const double* m, const Quat& local,
+                                          bool grid_in_smem, F f)
 {
     const DevCfg& c = p.cfg;
     const int M = p.M;
     if (c.ungated) {
-        for (int k = 0; k < M; k++) {
-            int j = atomicAdd(&sm.ctx.npairs, 1);
-            if (j < p.lay.cap_pairs) s.pkey[j] = ((unsigned long long)k << 32) | (unsigned)i;
-        }
+        for (int k = 0; k < M; k++) f(k);
         return;
     }
     // grid_in_smem: the cell offsets / items of the camera-frame grid were copied to sm.gstart / sm.kidx
@@ -193,64 +195,125 @@ __device__ __forceinline__ void gate_append(const KParams& p, Smem& sm, const Sl
                 int k = grid_in_smem ? sm.kidx[t] : __ldg(&p.vitems[t]);
                 double dx = m[0] - sm.cs[3 * k], dy = m[1] - sm.cs[3 * k + 1], dz = m[2] - sm.cs[3 * k + 2];
                 double d2 = dx * dx + dy * dy + dz * dz;
-                if (d2 <= c.gate_r2) {
-                    int j = atomicAdd(&sm.ctx.npairs, 1);
-                    if (j < p.lay.cap_pairs) s.pkey[j] = ((unsigned long long)k << 32) | (unsigned)i;
-                }
+                if (d2 <= c.gate_r2) f(k);
             }
         }
 }
 
 // ------------------------------------------------------------------------------------------------
-// one gated pair: measurement-space Gaussian of the component, Kalman gain, updated mean and
-// covariance, un-normalised weight term (PHD:858-870, 886-902) and, for prior components, the
-// exploration density term w_i N(c_k; m_i, P_i) (PHD:956-959, MAP:210-220)
+// CorrectConditional, the part that depends on the component only (PHD:858-866, 895-897): expected
+// measurement, S^-1 and the Gaussian multiplier, Kalman gain K, updated covariance (I - K H) P.  The
+// reference recomputes these for every (measurement, component) pair; they are the same numbers each
+// time, so they are computed once per gated component and kept in a record the pairs read.
+// record (kRec fields, struct of arrays over the gated components in index order): 0-2 h(m)  3 mult  4-12 S^-1  13-21 K  22 pd*w  23-25 m  26 w  27 mult_P  28-36 P^-1
 // ------------------------------------------------------------------------------------------------
-__device__ inline void eval_pair(const KParams& p, Smem& sm, const Slab& s, const double* in, int j)
+constexpr int kRec = 37;
+// field f of slot a of a struct-of-arrays record block (consecutive slots are consecutive in memory, so the
+// dense per-slot passes read and write it coalesced)
+template <class T>
+struct RecRef {
+    T* base;
+    size_t stride;
+    __device__ __forceinline__ T& operator[](int f) const { return base[(size_t)f * stride]; }
+};
+
+__device__ __noinline__ void comp_update(const KParams& p, Smem& sm, const Slab& s, const double* in, int a,
+                                         bool want_explore, int pair_offset, bool grid_in_smem)
 {
     const DevCfg& c = p.cfg;
-    const int N = sm.ctx.N, capq = p.lay.cap_pairs;
-    const unsigned long long key = s.pkey[j];
-    const int i = (int)(key & 0xffffffffu), k = (int)(key >> 32);
+    const int N = sm.ctx.N;
+    const int i = s.cact[a];
+    const int pair_base = pair_offset + s.nflag[i];
+    const RecRef<double> rec{s.crec + a, (size_t)p.lay.cap_pred};
     double w, m[3], P[9];
     load_pred(p, s, in, N, i, w, m, P);
-    Pose pose = pose_load(sm.ctx.pose);
-    double diff[3], mp[3], H[9], PH[9], S[9], Sinv[9];
-    Quat local;
-    to_local(pose, m, diff, local);
-    measure_from_local(c, diff, local, mp);
-    jacobian_l(c, pose, local, H);
-    mat3_mul_bt(P, H, PH);          // PH = P H^T
-    mat3_mul(H, PH, S);             // S = H P H^T + R
+    const Pose pose = pose_load(sm.ctx.pose);
+    double H[9], PH[9], Sinv[9];
+    {
+        double diff[3], mp[3];
+        Quat local;
+        to_local(pose, m, diff, local);
+        // the component's pairs, in one contiguous block of the pair list (slots counted by the A2 walk)
+        int slot = pair_base;
+        gate_walk(p, sm, m, local, grid_in_smem, [&](int k) {
+            if (slot < p.lay.cap_pairs) s.pkey[slot] = ((unsigned long long)k << 32) | (unsigned)a;
+            slot++;
+        });
+        measure_from_local(c, diff, local, mp);
+        jacobian_l(c, pose, local, H);
+        rec[0] = mp[0]; rec[1] = mp[1]; rec[2] = mp[2];
+        rec[22] = s.ppd[i] * w;
+        rec[23] = m[0]; rec[24] = m[1]; rec[25] = m[2];
+        rec[26] = w;
+    }
+    if (want_explore && i < N) {   // exploration term of a prior component (PHD:956-959): P^-1 and its multiplier
+        double Pinv[9];
+        const double detp = mat3_inv(P, Pinv);
+        rec[27] = gauss_mult(detp);
 #pragma unroll
-    for (int a = 0; a < 9; a++) S[a] = S[a] + c.R[a];
-    double det = mat3_inv(S, Sinv);
-    double mult = gauss_mult(det);
-    const double* zk = &sm.zs[3 * k];
-    double innov[3] = {zk[0] - mp[0], zk[1] - mp[1], zk[2] - mp[2]};
-    double q = mult * exp(-0.5 * quadform3(Sinv, innov));
-    double pdi = s.ppd[i];
-    s.pt[j] = pdi * w * q;
-
-    double K[9], kd[3], KH[9], IKH[9], Pn[9];
+        for (int f = 0; f < 9; f++) rec[28 + f] = Pinv[f];
+    }
+    mat3_mul_bt(P, H, PH);          // PH = P H^T
+    {
+        double S[9];
+        mat3_mul(H, PH, S);         // S = H P H^T + R
+#pragma unroll
+        for (int f = 0; f < 9; f++) S[f] = S[f] + c.R[f];
+        const double det = mat3_inv(S, Sinv);
+        rec[3] = gauss_mult(det);
+#pragma unroll
+        for (int f = 0; f < 9; f++) rec[4 + f] = Sinv[f];
+    }
+    double K[9];
     mat3_mul(PH, Sinv, K);
-    mat3_vec(K, innov, kd);
-    s.pmean[j] = m[0] + kd[0]; s.pmean[capq + j] = m[1] + kd[1]; s.pmean[2 * capq + j] = m[2] + kd[2];
+#pragma unroll
+    for (int f = 0; f < 9; f++) rec[13 + f] = K[f];
+    double KH[9], IKH[9], Pn[9];
     mat3_mul(K, H, KH);
 #pragma unroll
-    for (int a = 0; a < 3; a++)
+    for (int r = 0; r < 3; r++)
 #pragma unroll
-        for (int b = 0; b < 3; b++) IKH[a * 3 + b] = ((a == b) ? 1.0 : 0.0) - KH[a * 3 + b];
+        for (int b = 0; b < 3; b++) IKH[r * 3 + b] = ((r == b) ? 1.0 : 0.0) - KH[r * 3 + b];
     mat3_mul(IKH, P, Pn);
 #pragma unroll
-    for (int a = 0; a < 9; a++) s.pcov[(size_t)a * capq + j] = Pn[a];
+    for (int f = 0; f < 9; f++) s.cpn[(size_t)f * p.lay.cap_pred + a] = Pn[f];
+}
 
-    if (i < N && !sm.kflag[k]) {   // exploration term of a prior component (one term >= threshold decides)
+// ------------------------------------------------------------------------------------------------
+// one gated pair: un-normalised weight term and updated mean (PHD:886-902) from the component's record;
+// for prior components the exploration density term w_i N(c_k; m_i, P_i) (PHD:956-959, MAP:210-220)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void eval_pair(const KParams& p, Smem& sm, const Slab& s, int j, int nact_prior)
+{
+    const DevCfg& c = p.cfg;
+    const int capq = p.lay.cap_pairs;
+    const unsigned long long key = s.pkey[j];
+    const int a = (int)(key & 0xffffffffu), k = (int)(key >> 32);
+    const RecRef<const double> rec{s.crec + a, (size_t)p.lay.cap_pred};
+    const double* zk = &sm.zs[3 * k];
+    const double innov[3] = {zk[0] - rec[0], zk[1] - rec[1], zk[2] - rec[2]};
+    {
+        double Sinv[9];
+#pragma unroll
+        for (int f = 0; f < 9; f++) Sinv[f] = rec[4 + f];
+        const double q = rec[3] * exp(-0.5 * quadform3(Sinv, innov));
+        s.pt[j] = rec[22] * q;
+    }
+    const double m[3] = {rec[23], rec[24], rec[25]};
+    {
+        double K[9], kd[3];
+#pragma unroll
+        for (int f = 0; f < 9; f++) K[f] = rec[13 + f];
+        mat3_vec(K, innov, kd);
+        s.pmean[j] = m[0] + kd[0]; s.pmean[capq + j] = m[1] + kd[1]; s.pmean[2 * capq + j] = m[2] + kd[2];
+    }
+    if (a < nact_prior && !sm.kflag[k]) {   // exploration term of a prior component (one term >= threshold decides)
         double Pinv[9];
-        double detp = mat3_inv(P, Pinv);
+#pragma unroll
+        for (int f = 0; f < 9; f++) Pinv[f] = rec[28 + f];
         const double* ck = &sm.cs[3 * k];
-        double dc[3] = {ck[0] - m[0], ck[1] - m[1], ck[2] - m[2]};
-        double e = w * (gauss_mult(detp) * exp(-0.5 * quadform3(Pinv, dc)));
+        const double dc[3] = {ck[0] - m[0], ck[1] - m[1], ck[2] - m[2]};
+        const double e = rec[26] * (rec[27] * exp(-0.5 * quadform3(Pinv, dc)));
         if (e >= c.explore_thr) sm.kflag[k] = 1;
     }
 }
@@ -298,7 +361,12 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         double pdi = detection_probability(c, mp);
         s.ppd[i] = pdi;
         s.pwmd[i] = (1 - pdi) * w;
-        if (do_correct) gate_append(p, sm, s, i, m, local, vgrid_smem);
+        if (do_correct) {
+            int cnt = 0;
+            gate_walk(p, sm, m, local, vgrid_smem, [&](int) { cnt++; });
+            s.nflag[i] = cnt;
+            s.nstate[i] = (cnt > 0) ? 1 : 0;
+        }
         if (do_births) {
             // upper bound of ln(w N(x; m, P)) at distance d: ln(w mult) - d^2 / (2 trace P)  (lambda_max <= trace)
             double P[9];
@@ -313,15 +381,31 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        if (sm.ctx.npairs > p.lay.cap_pairs) { sm.ctx.npairs = p.lay.cap_pairs; sm.ctx.status |= ST_OVER_PAIRS; }
-        sm.ctx.npairs_prior = sm.ctx.npairs;
+    // pair slots: every component's pairs take one contiguous block, blocks in component order, so that the
+    // threads of a warp in the per-pair pass read the records of a handful of components (broadcast loads)
+    // (and the gated components one slot each, in index order, for their records)
+    int npairs_prior = 0, nact_prior = 0;
+    if (do_correct) {
+        block_scan_array2(sm.sh, s.nflag, s.nstate, N, &npairs_prior, &nact_prior);
+        for (int i = tid; i < N; i += kBlock) {
+            const int a = s.nstate[i];
+            if (((i + 1 < N) ? s.nstate[i + 1] : nact_prior) != a) s.cact[a] = i;
+        }
     }
+    if (tid == 0) {
+        if (npairs_prior > p.lay.cap_pairs) { sm.ctx.status |= ST_OVER_PAIRS; }
+        sm.ctx.npairs_prior = sm.ctx.npairs = min(npairs_prior, p.lay.cap_pairs);
+        sm.ctx.nact = nact_prior;
+    }
+    npairs_prior = min(npairs_prior, p.lay.cap_pairs);
     __syncthreads();
 
     PHASE_MARK(sm, 1);
-    // A3: gated pairs of prior components
-    for (int j = tid; j < sm.ctx.npairs_prior; j += kBlock) eval_pair(p, sm, s, in, j);
+    // A3: gated prior components (dense: one thread per component that has a pair), then their pairs
+    for (int a = tid; a < nact_prior; a += kBlock) comp_update(p, sm, s, in, a, do_births, 0, vgrid_smem);
+    __syncthreads();
+    PHASE_MARK(sm, 31);
+    for (int j = tid; j < npairs_prior; j += kBlock) eval_pair(p, sm, s, j, nact_prior);
     __syncthreads();
     PHASE_MARK(sm, 2);
 
@@ -484,12 +568,34 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         double pdi = detection_probability(c, mp);
         s.ppd[i] = pdi;
         s.pwmd[i] = (1 - pdi) * c.birth_w;
-        if (do_correct) gate_append(p, sm, s, i, m, local, false);
+        if (do_correct) {
+            int cnt = 0;
+            gate_walk(p, sm, m, local, false, [&](int) { cnt++; });
+            s.nflag[i] = cnt;
+            s.nstate[i] = (cnt > 0) ? 1 : 0;
+        }
     }
     __syncthreads();
-    if (tid == 0 && sm.ctx.npairs > p.lay.cap_pairs) { sm.ctx.npairs = p.lay.cap_pairs; sm.ctx.status |= ST_OVER_PAIRS; }
+    int nact = nact_prior;
+    if (do_correct) {
+        int nb = 0, na = 0;
+        block_scan_array2(sm.sh, s.nflag + N, s.nstate + N, Npred - N, &nb, &na);
+        for (int i = N + tid; i < Npred; i += kBlock) {
+            const int a = s.nstate[i];
+            if (((i + 1 < Npred) ? s.nstate[i + 1] : na) != a) s.cact[nact_prior + a] = i;
+        }
+        nact = nact_prior + na;
+        const int np_all = npairs_prior + nb;
+        if (tid == 0) {
+            if (np_all > p.lay.cap_pairs) sm.ctx.status |= ST_OVER_PAIRS;
+            sm.ctx.npairs = min(np_all, p.lay.cap_pairs);
+            sm.ctx.nact = nact;
+        }
+        __syncthreads();
+    }
+    for (int a = nact_prior + tid; a < nact; a += kBlock) comp_update(p, sm, s, in, a, false, npairs_prior, false);
     __syncthreads();
-    for (int j = sm.ctx.npairs_prior + tid; j < sm.ctx.npairs; j += kBlock) eval_pair(p, sm, s, in, j);
+    for (int j = npairs_prior + tid; j < sm.ctx.npairs; j += kBlock) eval_pair(p, sm, s, j, nact_prior);
     __syncthreads();
 
     PHASE_MARK(sm, 4);
@@ -602,7 +708,9 @@ __device__ __forceinline__ void load_corrected(const KParams& p, const Smem& sm,
         w = s.pwgt[t];
         m[0] = s.pmean[j]; m[1] = s.pmean[capq + j]; m[2] = s.pmean[2 * capq + j];
 #pragma unroll
-        for (int a = 0; a < 9; a++) P[a] = s.pcov[(size_t)a * capq + j];
+        const size_t ca = (size_t)(s.pkey[j] & 0xffffffffu);   // the updated covariance belongs to the component
+#pragma unroll
+        for (int f = 0; f < 9; f++) P[f] = s.cpn[(size_t)f * p.lay.cap_pred + ca];
     }
 }
 
@@ -647,49 +755,58 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
     const int L = sm.ctx.L, Npred = sm.ctx.Npred;
     const int capw = p.lay.cap_top;
 
-    // B1: entries that survive the MinWeight test, sorted by (weight desc, list position asc)
-    if (tid == 0) sm.ctx.ncand = 0;
-    __syncthreads();
-    for (int e = tid; e < L; e += kBlock) {
-        double w = (e < Npred) ? s.pwmd[e] : s.pwgt[e - Npred];
-        if (!(w < c.min_w)) {
-            int idx = atomicAdd(&sm.ctx.ncand, 1);
-            s.skey[idx] = weight_desc_key(w);
-            s.sval[idx] = (unsigned)e;
+    // B1: entries that survive the MinWeight test, sorted by (weight desc, list position asc): an ordered
+    // compaction (each warp owns a contiguous chunk of the list) followed by a stable radix sort on the weight
+    auto entry_weight = [&](int e) { return (e < Npred) ? s.pwmd[e] : s.pwgt[e - Npred]; };
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        const int C = (((L + kWarps - 1) / kWarps) + 31) & ~31;
+        const int beg = min(L, warp * C), end = min(L, beg + C);
+        constexpr int kRows = 4;   // rows of 32 entries loaded ahead of their use
+        int cnt = 0;
+        for (int base = beg; base < end; base += 32 * kRows) {
+            double w[kRows];
+#pragma unroll
+            for (int r = 0; r < kRows; r++) { const int e = base + 32 * r + lane; w[r] = (e < end) ? entry_weight(e) : 0.0; }
+#pragma unroll
+            for (int r = 0; r < kRows; r++) {
+                const bool keep = (base + 32 * r + lane < end) && !(w[r] < c.min_w);
+                cnt += __popc(__ballot_sync(0xffffffffu, keep));
+            }
         }
-    }
-    __syncthreads();
-    int nc = sm.ctx.ncand;
-    const int want = min(c.maxq, nc);
-    if (nc > (int)p.smem_sort_cap && want < nc) {
-        // more candidates than the shared-memory sort holds and only the `want` heaviest are needed
-        int cnt = block_select_smallest(s.skey, s.sval, nc, want, sm.skey, sm.sval, (int)p.smem_sort_cap, sm.hist,
-                                        &sm.ctx.nsel, &sm.ctx.selkey);
-        if (cnt >= 0) {
-            nc = cnt;
-            const int n2 = next_pow2(nc > 1 ? nc : 1);
-            for (int j = nc + tid; j < n2; j += kBlock) { sm.skey[j] = ~0ull; sm.sval[j] = ~0u; }
-            block_bitonic_sort(sm.skey, sm.sval, n2);
+        int total;
+        int wbase = block_excl_scan(sm.sh, (lane == 0) ? cnt : 0, &total);
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        for (int base = beg; base < end; base += 32 * kRows) {
+            double w[kRows];
+#pragma unroll
+            for (int r = 0; r < kRows; r++) { const int e = base + 32 * r + lane; w[r] = (e < end) ? entry_weight(e) : 0.0; }
+#pragma unroll
+            for (int r = 0; r < kRows; r++) {
+                const int e = base + 32 * r + lane;
+                const bool keep = (e < end) && !(w[r] < c.min_w);
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    const int idx = wbase + __popc(m & ((1u << lane) - 1u));
+                    s.skey[idx] = weight_desc_key(w[r]);
+                    s.sval[idx] = (unsigned)e;
+                }
+                wbase += __popc(m);
+            }
         }
+        if (tid == 0) sm.ctx.ncand = total;
+        __syncthreads();
     }
-    const bool selected = (nc != sm.ctx.ncand);
-    const int nc2 = next_pow2(nc > 1 ? nc : 1);
+    const int nc = sm.ctx.ncand;
     unsigned long long* skey = s.skey;
     unsigned int* sval = s.sval;
-    if (selected) { skey = sm.skey; sval = sm.sval; }
-    else if (nc2 <= (int)p.smem_sort_cap) {
-        for (int j = tid; j < nc2; j += kBlock) {
-            sm.skey[j] = (j < nc) ? s.skey[j] : ~0ull;
-            sm.sval[j] = (j < nc) ? s.sval[j] : ~0u;
-        }
-        skey = sm.skey; sval = sm.sval;
+    {
+        const bool in_smem = nc <= (int)p.smem_sort_cap;
+        unsigned long long* k1 = in_smem ? sm.skey : s.skey2;
+        unsigned int* v1 = in_smem ? sm.sval : s.sval2;
+        if (block_radix_sort(sm.sh, s.skey, s.sval, k1, v1, nc, reinterpret_cast<int*>(sm.vs), sm.hist, sm.ctx.dbg)) { skey = k1; sval = v1; }
     }
-    else {
-        for (int j = nc + tid; j < nc2; j += kBlock) { s.skey[j] = ~0ull; s.sval[j] = ~0u; }
-    }
-    if (!selected) block_bitonic_sort(skey, sval, nc2);
     PHASE_MARK(sm, 6);
-    nc = min(nc, sm.ctx.ncand);
 
     const int W0 = min(min(c.maxq, nc), capw);
     if (tid == 0) { sm.ctx.W0 = W0; if (min(c.maxq, nc) > capw) sm.ctx.status |= ST_OVER_COMPONENTS; }
@@ -803,7 +920,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
     }
     __syncthreads();
     int ne = sm.ctx.nedges;
-    if (tid == 0) { sm.ctx.dbg[3] += ne; sm.ctx.dbg[4] += W0; sm.ctx.dbg[5] += sm.ctx.ncand; if (ne > cape) sm.ctx.status |= ST_OVER_EDGES; }
+    if (tid == 0) { sm.ctx.dbg[2] += sm.ctx.nact; sm.ctx.dbg[3] += ne; sm.ctx.dbg[4] += W0; sm.ctx.dbg[5] += sm.ctx.ncand; if (ne > cape) sm.ctx.status |= ST_OVER_EDGES; }
     ne = min(ne, cape);
     // edges ordered by (r, r'): r' ascending = list order of the reference's inner loop (PHD:936-942)
     const int ne2 = next_pow2(ne > 1 ? ne : 1);
@@ -1024,7 +1141,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_particle_update(const __grid_cons
             Ctx& c = sm.ctx;
             c.N = min(p.counts[cur][particle], p.cap);
             c.B = 0; c.Npred = c.N; c.npairs = 0; c.npairs_prior = 0; c.L = c.N; c.ncand = 0; c.W0 = 0;
-            c.nedges = 0; c.nout = 0; c.nF = 0; c.status = 0;
+            c.nedges = 0; c.nout = 0; c.nF = 0; c.status = 0; c.nact = 0;
             for (int a = 0; a < 7; a++) c.pose[a] = p.poses[(size_t)particle * 7 + a];
         }
         __syncthreads();

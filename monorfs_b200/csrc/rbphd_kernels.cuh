@@ -44,9 +44,9 @@ struct FrameGrid {
 // byte offsets inside one CTA's scratch slab
 struct ScratchLayout {
     int cap_pred, cap_pairs, cap_list, cap_sort, cap_top, cap_edges, cap_j, cap_ll, cap_nodes;
-    size_t pm, pwt, pwmd, ppd, flagf, fidx, bidx;
-    size_t pkey, pt, pmean, pcov, pwgt;
-    size_t skey, sval;
+    size_t pm, pwt, pwmd, ppd, cact, bidx;
+    size_t pkey, pt, pmean, pwgt, crec, cpn;
+    size_t skey, sval, skey2, sval2;
     size_t tw, tm, tP, rho;
     size_t ecnt, edst, nstate, nowner, nflag, gitems;
     // weight stage
