@@ -141,30 +141,38 @@ __device__ __forceinline__ void load_pred(const KParams& p, const Slab& s, const
 // ------------------------------------------------------------------------------------------------
 template <class Enum, class Proc>
 __device__ __forceinline__ void enumerate_then_process(Smem& sm, int n_items, uint2* list, int list_cap, uint2* ovf,
-                                                       int ovf_cap, Enum enumerate, Proc process)
+                                                       int ovf_cap, Enum enumerate, Proc process,
+                                                       int mark_enum = 29, int mark_proc = 30, int batch = kBlock)
 {
     // pairs beyond the shared-memory list go to an overflow list in the slab (never processed inside the
-    // enumeration loop: that would drag the heavy code and its registers into the innermost loop)
-    for (int base = 0; base < n_items; base += kBlock) {
+    // enumeration loop: that would drag the heavy code and its registers into the innermost loop).
+    // `batch` items are enumerated between two barriers; callers that expect few pairs pass all their items.
+    for (int base = 0; base < n_items; base += batch) {
         if (threadIdx.x == 0) sm.ctx.nsel2 = 0;
         __syncthreads();
-        const int i = base + threadIdx.x;
-        if (i < n_items)
+        const int stop = min(n_items, base + batch);
+        for (int i = base + threadIdx.x; i < stop; i += kBlock)
             enumerate(i, [&](int a, int b) {
-                const int idx = atomicAdd(&sm.ctx.nsel2, 1);
+                // one atomic per group of lanes that emit together
+                const unsigned act = __activemask();
+                const int lane = threadIdx.x & 31, leader = __ffs(act) - 1;
+                int idx = 0;
+                if (lane == leader) idx = atomicAdd(&sm.ctx.nsel2, __popc(act));
+                idx = __shfl_sync(act, idx, leader) + __popc(act & ((1u << lane) - 1u));
                 if (idx < list_cap) list[idx] = make_uint2((unsigned)a, (unsigned)b);
                 else if (idx - list_cap < ovf_cap) ovf[idx - list_cap] = make_uint2((unsigned)a, (unsigned)b);
                 else sm.ctx.status |= ST_OVER_PAIRS;
             });
         __syncthreads();
-        PHASE_MARK(sm, 29);
+        PHASE_MARK(sm, mark_enum);
         const int tot = sm.ctx.nsel2;
+        if (threadIdx.x == 0 && mark_enum == 29) sm.ctx.dbg[6] += tot;
         const int cnt = min(tot, list_cap);
         for (int e = threadIdx.x; e < cnt; e += kBlock) process((int)list[e].x, (int)list[e].y);
         const int nov = min(max(tot - list_cap, 0), ovf_cap);
         for (int e = threadIdx.x; e < nov; e += kBlock) process((int)ovf[e].x, (int)ovf[e].y);
         __syncthreads();
-        PHASE_MARK(sm, 30);
+        PHASE_MARK(sm, mark_proc);
     }
 }
 
@@ -483,7 +491,8 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
                     const double dc[3] = {ux[u] - m[0], uy[u] - m[1], uz[u] - m[2]};
                     atomicAdd(&s.vsum[u], s.pwt[ci] * (wm * exp(-0.5 * quadform3(Pinv, dc))));
                     DBG_ADD(sm, 1, 1);
-                });
+                },
+                17, 17, (N + kBlock - 1) / kBlock * kBlock);
             __syncthreads();
             for (int u = tid; u < nU; u += kBlock) sm.dens[u] = s.vsum[u];
             __syncthreads();
@@ -804,7 +813,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
         const bool in_smem = nc <= (int)p.smem_sort_cap;
         unsigned long long* k1 = in_smem ? sm.skey : s.skey2;
         unsigned int* v1 = in_smem ? sm.sval : s.sval2;
-        if (block_radix_sort(sm.sh, s.skey, s.sval, k1, v1, nc, reinterpret_cast<int*>(sm.vs), sm.hist, sm.ctx.dbg)) { skey = k1; sval = v1; }
+        if (block_radix_sort(sm.sh, s.skey, s.sval, k1, v1, nc, reinterpret_cast<int*>(sm.vs), sm.hist)) { skey = k1; sval = v1; }
     }
     PHASE_MARK(sm, 6);
 
@@ -859,64 +868,69 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
     const int cape = p.lay.cap_ll;
     {
         const CellGrid& g = sm.ctx.grid;
-        for (int r = tid; r < W0; r += kBlock) {
+        // exact test of one candidate pair (r, r2 > r): box, then Mahalanobis distance under r's covariance
+        auto test = [&](int r, int r2) {
             const double rho = s.rho[r];
             const double x = tx[r], y = ty[r], z = tz[r];
-            bool have = false;
-            double Pinv[9];
-            auto test = [&](int r2) {
-                if (r2 <= r) return;
-                if (!have) {
-                    double P[9];
+            const double d[3] = {x - tx[r2], y - ty[r2], z - tz[r2]};   // a.Mean - b.Mean (GAUSS:367)
+            if (rho == rho && !isinf(rho) && (fabs(d[0]) > rho || fabs(d[1]) > rho || fabs(d[2]) > rho)) return;
+            double P[9], Pinv[9];
 #pragma unroll
-                    for (int a = 0; a < 9; a++) P[a] = s.tP[(size_t)a * capw + r];
-                    mat3_inv(P, Pinv);
-                    have = true;
-                }
-                double d[3] = {x - tx[r2], y - ty[r2], z - tz[r2]};   // a.Mean - b.Mean (GAUSS:367)
-                if (quadform3(Pinv, d) < t2) {
-                    int idx = atomicAdd(&sm.ctx.nedges, 1);
-                    if (idx < cape) elist[idx] = ((unsigned long long)r << 32) | (unsigned)r2;
-                }
-            };
-            int lo[3], hi[3];
-            bool brute = !(rho == rho) || isinf(rho);
-            if (!brute) {
-                if (!grid_range(g, x, y, z, rho, lo, hi)) continue;
-                long cells = (long)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
-                if (cells > 128) brute = true;
+            for (int a = 0; a < 9; a++) P[a] = s.tP[(size_t)a * capw + r];
+            mat3_inv(P, Pinv);
+            if (quadform3(Pinv, d) < t2) {
+                int idx = atomicAdd(&sm.ctx.nedges, 1);
+                if (idx < cape) elist[idx] = ((unsigned long long)r << 32) | (unsigned)r2;
             }
-            if (brute) {
-                for (int r2 = r + 1; r2 < W0; r2++) {
-                    if (rho == rho && !isinf(rho) &&
-                        (fabs(tx[r2] - x) > rho || fabs(ty[r2] - y) > rho || fabs(tz[r2] - z) > rho)) continue;
-                    test(r2);
+        };
+        // the walk only prefilters (single precision, shared memory) and lists the surviving pairs; the exact
+        // tests then run densely, one thread per pair (no global-memory latency inside the divergent walk)
+        const int list_off = fsm ? (3 * W0 * (int)sizeof(float) + 15) / 16 * 2 : 0;   // uint2 units behind fx/fy/fz
+        uint2* list = reinterpret_cast<uint2*>(sm.skey) + list_off;
+        const int list_cap = (int)p.smem_sort_cap - list_off;
+        enumerate_then_process(
+            sm, W0, list, list_cap, reinterpret_cast<uint2*>(s.edst), p.lay.cap_edges / 2,
+            [&](int r, auto emit) {
+                const double rho = s.rho[r];
+                const double x = tx[r], y = ty[r], z = tz[r];
+                int lo[3], hi[3];
+                bool brute = !(rho == rho) || isinf(rho);
+                if (!brute) {
+                    if (!grid_range(g, x, y, z, rho, lo, hi)) return;
+                    long cells = (long)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
+                    if (cells > 128) brute = true;
                 }
-                continue;
-            }
-            const float xf = (float)x, yf = (float)y, zf = (float)z;
-            const float rf = (float)rho * 1.0001f + 1e-6f + 1e-6f * (fabsf(xf) + fabsf(yf) + fabsf(zf));
-            for (int cz = lo[2]; cz <= hi[2]; cz++)
-                for (int cy = lo[1]; cy <= hi[1]; cy++) {
-                    const int rowc = (cz * g.dim[1] + cy) * g.dim[0];
-                    const int qb = sm.gstart[rowc + lo[0]], qe = sm.gstart[rowc + hi[0] + 1];
-                    if (fsm) {
-                        for (int q = qb; q < qe; q++)
-                            if (fabsf(fx[q] - xf) <= rf && fabsf(fy[q] - yf) <= rf && fabsf(fz[q] - zf) <= rf) {
-                                const int r2 = frank[q];
-                                if (r2 > r && fabs(tx[r2] - x) <= rho && fabs(ty[r2] - y) <= rho && fabs(tz[r2] - z) <= rho)
-                                    test(r2);
-                            }
+                if (brute) {
+                    for (int r2 = r + 1; r2 < W0; r2++) {
+                        if (rho == rho && !isinf(rho) &&
+                            (fabs(tx[r2] - x) > rho || fabs(ty[r2] - y) > rho || fabs(tz[r2] - z) > rho)) continue;
+                        emit(r, r2);
                     }
-                    else {   // more candidates than the shared-memory copy holds: walk the cell lists in the slab
-                        for (int q = qb; q < qe; q++) {
-                            const int r2 = s.gitems[q];
-                            if (r2 > r && fabs(tx[r2] - x) <= rho && fabs(ty[r2] - y) <= rho && fabs(tz[r2] - z) <= rho)
-                                test(r2);
+                    return;
+                }
+                const float xf = (float)x, yf = (float)y, zf = (float)z;
+                const float rf = (float)rho * 1.0001f + 1e-6f + 1e-6f * (fabsf(xf) + fabsf(yf) + fabsf(zf));
+                for (int cz = lo[2]; cz <= hi[2]; cz++)
+                    for (int cy = lo[1]; cy <= hi[1]; cy++) {
+                        const int rowc = (cz * g.dim[1] + cy) * g.dim[0];
+                        const int qb = sm.gstart[rowc + lo[0]], qe = sm.gstart[rowc + hi[0] + 1];
+                        if (fsm) {
+                            for (int q = qb; q < qe; q++)
+                                if (fabsf(fx[q] - xf) <= rf && fabsf(fy[q] - yf) <= rf && fabsf(fz[q] - zf) <= rf) {
+                                    const int r2 = frank[q];
+                                    if (r2 > r) emit(r, r2);
+                                }
+                        }
+                        else {   // more candidates than the shared-memory copy holds: walk the cell lists in the slab
+                            for (int q = qb; q < qe; q++) {
+                                const int r2 = s.gitems[q];
+                                if (r2 > r && fabs(tx[r2] - x) <= rho && fabs(ty[r2] - y) <= rho && fabs(tz[r2] - z) <= rho)
+                                    emit(r, r2);
+                            }
                         }
                     }
-                }
-        }
+            },
+            test, 8, 8, (W0 + kBlock - 1) / kBlock * kBlock);
     }
     __syncthreads();
     int ne = sm.ctx.nedges;

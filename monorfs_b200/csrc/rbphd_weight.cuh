@@ -10,7 +10,7 @@ namespace rbphd {
 // Terms of Map.Evaluate with Mahalanobis distance^2 above this are < 2e-22 of the component's peak and
 // are skipped (the reference sums them; the parity bar for weights is 1e-9 relative).
 constexpr double kEvalD2 = 100.0;
-constexpr double kQueryCell = 0.7;   // cell edge of the grid over the map-estimate points
+constexpr double kQueryCell = 0.4;   // cell edge of the grid over the map-estimate points
 
 struct CompSrc {
     const double* w;
@@ -60,10 +60,30 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
     for (int t = tid; t < J; t += kBlock) vs[t] = 0.0;
     __syncthreads();
     PHASE_MARK(sm, 20);
-    auto term_into = [&](int i, int t) {   // w_i N(jm_t; m_i, P_i) -> vs[t]
-        double P[9], Pinv[9];
+    // per-component records (struct of arrays in the slab, written coalesced by one dense pass): P^-1, the
+    // Gaussian multiplier and the squared cull radius kEvalD2 * bound, where bound >= lambda_max(P):
+    // ||P^2||_F^(1/2) = (sum lambda^4)^(1/4), within 32 % of lambda_max (the trace is up to 3x larger)
+    double* rec = s.cinv;
+    const size_t rs = (size_t)p.lay.cap_pred;
+    for (int i = tid; i < c.n; i += kBlock) {
+        double P[9], Pinv[9], P2[9];
         comp_cov(c, i, P);
         const double mult = gauss_mult(mat3_inv(P, Pinv));
+#pragma unroll
+        for (int a = 0; a < 9; a++) rec[(size_t)a * rs + i] = Pinv[a];
+        rec[9 * rs + i] = mult;
+        mat3_mul(P, P, P2);
+        double f = 0;
+#pragma unroll
+        for (int a = 0; a < 9; a++) f += P2[a] * P2[a];
+        rec[10 * rs + i] = kEvalD2 * sqrt(sqrt(f)) * (1.0 + 1e-6);
+    }
+    __syncthreads();
+    auto term_into = [&](int i, int t) {   // w_i N(jm_t; m_i, P_i) -> vs[t]
+        double Pinv[9];
+#pragma unroll
+        for (int a = 0; a < 9; a++) Pinv[a] = rec[(size_t)a * rs + i];
+        const double mult = rec[9 * rs + i];
         const double d[3] = {jx[t] - c.mx[i], jy[t] - c.my[i], jz[t] - c.mz[i]};   // x - Mean (GAUSS:201)
         atomicAdd(&vs[t], c.w[i] * (mult * exp(-0.5 * quadform3(Pinv, d))));
     };
@@ -75,12 +95,8 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
         p.lay.cap_edges / 2,
         [&](int i, auto emit) {
             const double x = c.mx[i], y = c.my[i], z = c.mz[i];
-            // trace of the covariance without loading the off-diagonal terms
-            const double tr = ((i < c.ncov) ? c.cov[i] : c.defcov[0]) +
-                              ((i < c.ncov) ? c.cov[(size_t)4 * c.covstride + i] : c.defcov[4]) +
-                              ((i < c.ncov) ? c.cov[(size_t)8 * c.covstride + i] : c.defcov[8]);
-            double r2 = kEvalD2 * tr * (1.0 + 1e-9);
-            bool brute = !(r2 >= 0) || isinf(r2);   // NaN / negative trace: never cull
+            const double r2 = rec[10 * rs + i];
+            bool brute = !(r2 >= 0) || isinf(r2);   // NaN covariance: never cull
             int lo[3], hi[3];
             if (!brute) {
                 if (!grid_range(g, x, y, z, sqrt(r2), lo, hi)) return;
@@ -134,10 +150,7 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
             if (f < nfat) {
                 const int i = sm.kidx[f];
                 const double x = c.mx[i], y = c.my[i], z = c.mz[i];
-                const double tr = ((i < c.ncov) ? c.cov[i] : c.defcov[0]) +
-                                  ((i < c.ncov) ? c.cov[(size_t)4 * c.covstride + i] : c.defcov[4]) +
-                                  ((i < c.ncov) ? c.cov[(size_t)8 * c.covstride + i] : c.defcov[8]);
-                const double r2 = kEvalD2 * tr * (1.0 + 1e-9);
+                const double r2 = rec[10 * rs + i];
                 int lo[3], hi[3];
                 if (grid_range(g, x, y, z, sqrt(r2), lo, hi)) {
                     const int ny = hi[1] - lo[1] + 1, rows = ny * (hi[2] - lo[2] + 1);
