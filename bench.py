@@ -396,7 +396,8 @@ def main():
                        "steps": main_res["e2e_steps"], "resampling_frames": main_res["e2e_resamples"]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = {"c4": 16, "c4s": 16, "c2": 160, "c3": os.cpu_count() or 1, "tiny": 64}.get(args.workload, 16)
+        ncpu = os.cpu_count() or 1
+        sample = {"c4": 24 * ncpu, "c4s": 24 * ncpu, "c2": 2000, "c3": ncpu, "tiny": 64}.get(args.workload, 16)
         nfr = {"c4": 3, "c4s": 3, "c2": 4, "c3": 1, "tiny": 4}.get(args.workload, 2)
         line["cpu_baseline"] = cpu_baseline(args.workload, sample, nfr, synth.SEED)
 

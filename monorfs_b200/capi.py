@@ -353,10 +353,10 @@ class Handle:
               "B6 merge+write", "C1-3 map estimate", "C4 eval predicted", "C4 eval corrected", "C5 set likelihood",
               "tail", "A4a undecided list", "A4b density accumulate", "A4c decide", "B3a merge grid build",
               "C4a zero", "C4b accumulate", "C4c log-sum", "C3b query grid build", "C5a gate edges", "C5b components",
-              "C5c edge sort", "A4b1 gather points", "A4b2 mini grid build", "enumerate (A4b+C4b thin)", "dense process (A4b+C4b thin)", "x31")
+              "C5c edge sort", "A4b1 gather points", "A4b2 mini grid build", "C4b enumerate", "C4b dense process", "A3a gated component update")
 
-    DEBUG_COUNTERS = ("undecided measurements", "explore hits", "explore active comps", "merge edges", "W0",
-                      "candidates", "eval candidates", "eval hits", "eval cell rows", "likelihood edges", "J",
+    DEBUG_COUNTERS = ("undecided measurements", "explore hits", "gated components", "merge edges", "W0",
+                      "candidates", "eval pairs", "eval hits", "eval cell rows", "likelihood edges", "J",
                       "murty blocks", "d12", "d13", "d14", "d15")
 
     def phase_cycles(self):

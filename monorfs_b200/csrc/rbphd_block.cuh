@@ -179,10 +179,8 @@ __device__ __forceinline__ unsigned warp_match_digit(unsigned d, bool valid)
 // digits inside a 32-element row with match_any, so no atomics are needed and the order is deterministic.
 // Digits on which all keys agree are skipped (weights span a few binades: the leading byte usually does).
 __device__ inline int block_radix_sort(BlockShared& sh, unsigned long long* k0, unsigned int* v0,
-                                       unsigned long long* k1, unsigned int* v1, int n, int* whist, int* dbase, unsigned int* tdbg = nullptr)
+                                       unsigned long long* k1, unsigned int* v1, int n, int* whist, int* dbase)
 {
-    long long t0 = clock64();
-#define RS_MARK(i) do { if (tdbg && threadIdx.x == 0) { long long t1 = clock64(); tdbg[i] += (unsigned int)((t1 - t0) >> 4); t0 = t1; } } while (0)
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long o = 0, a = ~0ull;
@@ -198,7 +196,6 @@ __device__ inline int block_radix_sort(BlockShared& sh, unsigned long long* k0, 
         a &= (unsigned long long)__double_as_longlong(sh.warp_d[kWarps + w]);
     }
     const unsigned long long diff = (n > 1) ? (o ^ a) : 0ull;
-    RS_MARK(12);
     const int C = (((n + kWarps - 1) / kWarps) + 31) & ~31;
     const int beg = min(n, warp * C), end = min(n, beg + C);
     int* wh = whist + warp * 256;
@@ -230,8 +227,7 @@ __device__ inline int block_radix_sort(BlockShared& sh, unsigned long long* k0, 
             }
         }
         __syncthreads();
-        RS_MARK(13);
-        int tot = 0;   // digit-major offsets: all warps' counts of digit t, in warp order
+            int tot = 0;   // digit-major offsets: all warps' counts of digit t, in warp order
         if (threadIdx.x < 256)
 #pragma unroll
             for (int w = 0; w < kWarps; w++) { const int c = whist[w * 256 + threadIdx.x]; whist[w * 256 + threadIdx.x] = tot; tot += c; }
@@ -239,8 +235,7 @@ __device__ inline int block_radix_sort(BlockShared& sh, unsigned long long* k0, 
         const int basep = block_excl_scan(sh, tot, &total);
         if (threadIdx.x < 256) dbase[threadIdx.x] = basep;
         __syncthreads();
-        RS_MARK(14);
-        constexpr int kRowsS = 4;
+            constexpr int kRowsS = 4;
         for (int base = beg; base < end; base += 32 * kRowsS) {
             unsigned long long kk[kRowsS];
             unsigned int vv[kRowsS];
@@ -265,8 +260,7 @@ __device__ inline int block_radix_sort(BlockShared& sh, unsigned long long* k0, 
         }
         cur ^= 1;
         __syncthreads();
-        RS_MARK(15);
-    }
+        }
     __syncthreads();
     return cur;
 }
@@ -350,9 +344,8 @@ struct CellGrid {
 
 __device__ __forceinline__ int grid_coord(const CellGrid& g, int a, double x)
 {
-    double f = floor((x - g.org[a]) * g.inv[a]);
-    int c = (f < 0) ? 0 : ((f >= (double)g.dim[a]) ? g.dim[a] - 1 : (int)f);
-    return c;
+    // round down and clamp in the integer domain (the conversion saturates; NaN gives 0)
+    return max(0, min(g.dim[a] - 1, __double2int_rd((x - g.org[a]) * g.inv[a])));
 }
 __device__ __forceinline__ int grid_cell(const CellGrid& g, double x, double y, double z)
 {
