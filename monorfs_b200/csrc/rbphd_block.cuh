@@ -265,6 +265,149 @@ __device__ inline int block_radix_sort(BlockShared& sh, unsigned long long* k0, 
     return cur;
 }
 
+// Bucket sort of n (key,val) pairs, ascending by (key, then val); vals must be distinct.  One pass spreads the
+// keys over kSortBuckets equal slices of [min key, max key] (histogram and cursors: shared-memory atomics),
+// then every bucket is finished on its own: up to kBucketThreadMax entries by one thread (insertion sort), up
+// to kBucketWarpMax by one warp (rank sort held in registers), longer ones (a group of equal weights, e.g. the
+// frame's births) by the whole CTA (rank sort through tmpk/tmpv).  Far cheaper than a full radix or bitonic
+// sort when the keys are spread out, which weights are.  Returns false -- leaving (kin,vin) untouched -- when
+// one bucket is so long that its O(len^2) rank sort would cost more than the radix sort the caller then uses.
+// (kout,vout): n entries, ideally shared memory; hist: kSortBuckets + 1 ints of shared memory;
+// biglist: kBigBuckets + 2 ints of shared memory (buckets longer than kBucketThreadMax); wscratch: when
+// (kout,vout) are in global memory, kWarps * 1.5 * kBucketWarpMax 64-bit words of shared memory.
+constexpr int kSortBuckets = 4096;
+constexpr int kBucketThreadMax = 6;
+constexpr int kBucketWarpMax = 128;
+constexpr int kBigBuckets = 4000;
+
+__device__ inline bool block_bucket_sort(BlockShared& sh, const unsigned long long* kin, const unsigned int* vin,
+                                         unsigned long long* kout, unsigned int* vout, int n, int* hist, int* biglist,
+                                         unsigned long long* tmpk, unsigned int* tmpv,
+                                         unsigned long long* wscratch = nullptr)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (int e = threadIdx.x; e < n; e += kBlock) { const unsigned long long k = kin[e]; lo = min(lo, k); hi = max(hi, k); }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+    __syncthreads();
+    if (lane == 0) { sh.warp_d[warp] = __longlong_as_double((long long)lo); sh.warp_d[kWarps + warp] = __longlong_as_double((long long)hi); }
+    for (int b = threadIdx.x; b <= kSortBuckets; b += kBlock) hist[b] = 0;
+    if (threadIdx.x == 0) { biglist[kBigBuckets] = 0; biglist[kBigBuckets + 1] = 0; }
+    __syncthreads();
+    for (int w = 0; w < kWarps; w++) {
+        lo = min(lo, (unsigned long long)__double_as_longlong(sh.warp_d[w]));
+        hi = max(hi, (unsigned long long)__double_as_longlong(sh.warp_d[kWarps + w]));
+    }
+    const unsigned long long range = hi - lo;
+    const int shift = max(0, (64 - __clzll((long long)range)) - 12);   // (key - lo) >> shift < 4096
+    for (int e = threadIdx.x; e < n; e += kBlock) atomicAdd(&hist[(int)((kin[e] - lo) >> shift)], 1);
+    __syncthreads();
+    int longest = 0;
+    for (int b = threadIdx.x; b < kSortBuckets; b += kBlock) longest = max(longest, hist[b]);
+    if (__syncthreads_or((long long)longest * longest > 600ll * n && longest > kBucketWarpMax)) return false;
+    block_scan_array(sh, hist, kSortBuckets + 1);   // hist[b] = start of bucket b; used as the scatter cursor
+    for (int e = threadIdx.x; e < n; e += kBlock) {
+        const unsigned long long k = kin[e];
+        const int pos = atomicAdd(&hist[(int)((k - lo) >> shift)], 1);
+        kout[pos] = k;
+        vout[pos] = vin[e];
+    }
+    __syncthreads();
+    // after the scatter hist[b] = end of bucket b = start of bucket b + 1
+    for (int b = threadIdx.x; b < kSortBuckets; b += kBlock) {
+        const int beg = (b == 0) ? 0 : hist[b - 1], end = hist[b];
+        const int len = end - beg;
+        if (len <= 1) continue;
+        if (len > kBucketThreadMax) {
+            // medium buckets are listed from the front, long ones from the back of the same list
+            if (len <= kBucketWarpMax) {
+                const int slot = atomicAdd(&biglist[kBigBuckets], 1);
+                if (slot + biglist[kBigBuckets + 1] < kBigBuckets) { biglist[slot] = b; continue; }
+            }
+            else {
+                const int slot = atomicAdd(&biglist[kBigBuckets + 1], 1);
+                if (slot + biglist[kBigBuckets] < kBigBuckets) { biglist[kBigBuckets - 1 - slot] = b; continue; }
+            }
+        }
+        for (int a = beg + 1; a < end; a++) {   // (also the overflow of the list: slow, still correct)
+            const unsigned long long k = kout[a];
+            const unsigned int v = vout[a];
+            int q = a - 1;
+            while (q >= beg && (kout[q] > k || (kout[q] == k && vout[q] > v))) { kout[q + 1] = kout[q]; vout[q + 1] = vout[q]; q--; }
+            kout[q + 1] = k;
+            vout[q + 1] = v;
+        }
+    }
+    __syncthreads();
+    const int nlong = min(biglist[kBigBuckets + 1], kBigBuckets);
+    const int nmed = min(biglist[kBigBuckets], kBigBuckets - nlong);
+    for (int t = warp; t < nmed; t += kWarps) {
+        const int b = biglist[t];
+        const int beg = (b == 0) ? 0 : hist[b - 1], end = hist[b];
+        constexpr int R = kBucketWarpMax / 32;
+        unsigned long long k[R];
+        unsigned int v[R];
+        int rank[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int a = beg + lane + 32 * r;
+            k[r] = ~0ull; v[r] = ~0u; rank[r] = 0;
+            if (a < end) { k[r] = kout[a]; v[r] = vout[a]; }
+        }
+        if (wscratch) {   // (kout,vout) live in global memory: rank against a shared-memory copy of the bucket
+            unsigned long long* wk = wscratch + (size_t)warp * (kBucketWarpMax + kBucketWarpMax / 2);
+            unsigned int* wv = reinterpret_cast<unsigned int*>(wk + kBucketWarpMax);
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if (beg + lane + 32 * r < end) { wk[lane + 32 * r] = k[r]; wv[lane + 32 * r] = v[r]; }
+            __syncwarp();
+            const int len = end - beg;
+            for (int q = 0; q < len; q++) {
+                const unsigned long long kq = wk[q];
+                const unsigned int vq = wv[q];
+#pragma unroll
+                for (int r = 0; r < R; r++) rank[r] += (kq < k[r] || (kq == k[r] && vq < v[r])) ? 1 : 0;
+            }
+        }
+        else {
+            for (int q = beg; q < end; q++) {
+                const unsigned long long kq = kout[q];
+                const unsigned int vq = vout[q];
+#pragma unroll
+                for (int r = 0; r < R; r++) rank[r] += (kq < k[r] || (kq == k[r] && vq < v[r])) ? 1 : 0;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            if (beg + lane + 32 * r < end) { kout[beg + rank[r]] = k[r]; vout[beg + rank[r]] = v[r]; }
+        __syncwarp();
+    }
+    for (int t = 0; t < nlong; t++) {   // the whole CTA on one long bucket
+        const int b = biglist[kBigBuckets - 1 - t];
+        const int beg = (b == 0) ? 0 : hist[b - 1], end = hist[b];
+        for (int a = beg + threadIdx.x; a < end; a += kBlock) {
+            const unsigned long long k = kout[a];
+            const unsigned int v = vout[a];
+            int rank = 0;
+            for (int q = beg; q < end; q++) {
+                const unsigned long long kq = kout[q];
+                rank += (kq < k || (kq == k && vout[q] < v)) ? 1 : 0;
+            }
+            tmpk[beg + rank] = k;
+            tmpv[beg + rank] = v;
+        }
+        __syncthreads();
+        for (int a = beg + threadIdx.x; a < end; a += kBlock) { kout[a] = tmpk[a]; vout[a] = tmpv[a]; }
+    }
+    __syncthreads();
+    return true;
+}
+
 // Keep the `want` smallest (key, then val) of n candidates when n exceeds what a later sort can hold:
 // radix-select the want-th key (8 bits per pass, histogram in shared memory) and copy every candidate
 // with key <= it to (okey, oval).  Returns the number copied (>= want; more only on ties), or -1 if it

@@ -20,7 +20,7 @@ namespace rbphd {
 // shared-memory context of one CTA of k_particle_update
 // ------------------------------------------------------------------------------------------------
 struct Ctx {
-    int N, B, Npred, npairs, npairs_prior, L, ncand, W0, nedges, nout, nF, nU, nsel, nsel2, nact;
+    int N, B, Npred, npairs, npairs_prior, L, ncand, W0, nedges, nout, nF, nU, nsel, nsel2, nact, work;
     int status;
     unsigned long long selkey;
     double pose[7];
@@ -61,6 +61,7 @@ struct Smem {
 constexpr int kSortCap = 8192;   // (key,val) pairs the shared-memory sort buffer holds
 constexpr int kVsCap = 4096;
 static_assert(sizeof(double) * kVsCap >= sizeof(int) * kWarps * 256, "the radix-sort histograms alias the vs buffer");
+static_assert(sizeof(double) * kVsCap >= sizeof(int) * (kSortBuckets + 1 + kBigBuckets + 2), "the bucket-sort histogram and long-bucket list alias the vs buffer");
 
 struct Slab {
     // predicted map = prior components followed by births
@@ -142,27 +143,41 @@ __device__ __forceinline__ void load_pred(const KParams& p, const Slab& s, const
 template <class Enum, class Proc>
 __device__ __forceinline__ void enumerate_then_process(Smem& sm, int n_items, uint2* list, int list_cap, uint2* ovf,
                                                        int ovf_cap, Enum enumerate, Proc process,
-                                                       int mark_enum = 29, int mark_proc = 30, int batch = kBlock)
+                                                       int mark_enum = 29, int mark_proc = 30)
 {
-    // pairs beyond the shared-memory list go to an overflow list in the slab (never processed inside the
-    // enumeration loop: that would drag the heavy code and its registers into the innermost loop).
-    // `batch` items are enumerated between two barriers; callers that expect few pairs pass all their items.
-    for (int base = 0; base < n_items; base += batch) {
+    // Items are handed out to the warps 32 at a time from a shared counter (walk lengths differ a lot between
+    // items; a static assignment leaves most warps waiting at the barrier for the unlucky one).  A round of
+    // enumeration ends when the items run out or the shared-memory list is full; the pairs the warps still
+    // in flight add beyond that go to an overflow list in the slab (never processed inside the enumeration
+    // loop: that would drag the heavy code and its registers into the innermost loop).
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) sm.ctx.work = 0;
+    for (;;) {
         if (threadIdx.x == 0) sm.ctx.nsel2 = 0;
         __syncthreads();
-        const int stop = min(n_items, base + batch);
-        for (int i = base + threadIdx.x; i < stop; i += kBlock)
-            enumerate(i, [&](int a, int b) {
-                // one atomic per group of lanes that emit together
-                const unsigned act = __activemask();
-                const int lane = threadIdx.x & 31, leader = __ffs(act) - 1;
-                int idx = 0;
-                if (lane == leader) idx = atomicAdd(&sm.ctx.nsel2, __popc(act));
-                idx = __shfl_sync(act, idx, leader) + __popc(act & ((1u << lane) - 1u));
-                if (idx < list_cap) list[idx] = make_uint2((unsigned)a, (unsigned)b);
-                else if (idx - list_cap < ovf_cap) ovf[idx - list_cap] = make_uint2((unsigned)a, (unsigned)b);
-                else sm.ctx.status |= ST_OVER_PAIRS;
-            });
+        const int done = sm.ctx.work;
+        __syncthreads();
+        if (done >= n_items) break;
+        for (;;) {
+            int base = n_items;
+            if (lane == 0 && *(volatile int*)&sm.ctx.nsel2 < list_cap) base = atomicAdd(&sm.ctx.work, 32);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n_items) break;
+            const int i = base + lane;
+            if (i < n_items)
+                enumerate(i, [&](int a, int b) {
+                    // one atomic per group of lanes that emit together
+                    const unsigned act = __activemask();
+                    const int leader = __ffs(act) - 1;
+                    int idx = 0;
+                    if (lane == leader) idx = atomicAdd(&sm.ctx.nsel2, __popc(act));
+                    idx = __shfl_sync(act, idx, leader) + __popc(act & ((1u << lane) - 1u));
+                    if (idx < list_cap) list[idx] = make_uint2((unsigned)a, (unsigned)b);
+                    else if (idx - list_cap < ovf_cap) ovf[idx - list_cap] = make_uint2((unsigned)a, (unsigned)b);
+                    else sm.ctx.status |= ST_OVER_PAIRS;
+                });
+            __syncwarp();
+        }
         __syncthreads();
         PHASE_MARK(sm, mark_enum);
         const int tot = sm.ctx.nsel2;
@@ -171,7 +186,6 @@ __device__ __forceinline__ void enumerate_then_process(Smem& sm, int n_items, ui
         for (int e = threadIdx.x; e < cnt; e += kBlock) process((int)list[e].x, (int)list[e].y);
         const int nov = min(max(tot - list_cap, 0), ovf_cap);
         for (int e = threadIdx.x; e < nov; e += kBlock) process((int)ovf[e].x, (int)ovf[e].y);
-        __syncthreads();
         PHASE_MARK(sm, mark_proc);
     }
 }
@@ -492,7 +506,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
                     atomicAdd(&s.vsum[u], s.pwt[ci] * (wm * exp(-0.5 * quadform3(Pinv, dc))));
                     DBG_ADD(sm, 1, 1);
                 },
-                17, 17, (N + kBlock - 1) / kBlock * kBlock);
+                17, 17);
             __syncthreads();
             for (int u = tid; u < nU; u += kBlock) sm.dens[u] = s.vsum[u];
             __syncthreads();
@@ -813,7 +827,15 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
         const bool in_smem = nc <= (int)p.smem_sort_cap;
         unsigned long long* k1 = in_smem ? sm.skey : s.skey2;
         unsigned int* v1 = in_smem ? sm.sval : s.sval2;
-        if (block_radix_sort(sm.sh, s.skey, s.sval, k1, v1, nc, reinterpret_cast<int*>(sm.vs), sm.hist)) { skey = k1; sval = v1; }
+        // weights are spread out: one bucket pass + tiny per-bucket sorts; the radix sort is the fallback for
+        // degenerate key sets (thousands of equal weights)
+        if (block_bucket_sort(sm.sh, s.skey, s.sval, k1, v1, nc, reinterpret_cast<int*>(sm.vs),
+                              reinterpret_cast<int*>(sm.vs) + kSortBuckets + 1, s.skey, s.sval, in_smem ? nullptr : sm.skey)) {
+            skey = k1; sval = v1;
+        }
+        else if (block_radix_sort(sm.sh, s.skey, s.sval, k1, v1, nc, reinterpret_cast<int*>(sm.vs), sm.hist)) {
+            skey = k1; sval = v1;
+        }
     }
     PHASE_MARK(sm, 6);
 
@@ -930,7 +952,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
                         }
                     }
             },
-            test, 8, 8, (W0 + kBlock - 1) / kBlock * kBlock);
+            test, 8, 8);
     }
     __syncthreads();
     int ne = sm.ctx.nedges;

@@ -553,19 +553,28 @@ __device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const 
     unsigned int* sval = s.sval;
     int nsort = tot;
     if (wantj > 0) {
-        int cnt = -1;
-        if (wantj < tot)
-            cnt = block_select_smallest(s.skey, s.sval, tot, wantj, sm.skey, sm.sval, (int)p.smem_sort_cap, sm.hist,
-                                        &sm.ctx.nsel, &sm.ctx.selkey);
-        else if (tot <= (int)p.smem_sort_cap) {
-            for (int j = tid; j < tot; j += kBlock) { sm.skey[j] = s.skey[j]; sm.sval[j] = s.sval[j]; }
-            cnt = tot;
+        // the whole multiset fits the shared-memory buffer: bucket sort (weights are spread out)
+        bool sorted = false;
+        if (tot <= (int)p.smem_sort_cap) {
+            sorted = block_bucket_sort(sm.sh, s.skey, s.sval, sm.skey, sm.sval, tot, reinterpret_cast<int*>(sm.vs),
+                                       reinterpret_cast<int*>(sm.vs) + kSortBuckets + 1, s.skey, s.sval);
+            if (sorted) { skey = sm.skey; sval = sm.sval; }
         }
-        if (cnt >= 0) { skey = sm.skey; sval = sm.sval; nsort = cnt; }
-        const int n2 = next_pow2(nsort > 1 ? nsort : 1);
-        if (skey == sm.skey || n2 <= gcap) {
-            for (int j = nsort + tid; j < n2; j += kBlock) { skey[j] = ~0ull; sval[j] = ~0u; }
-            block_bitonic_sort(skey, sval, n2);
+        if (!sorted) {   // too large, or degenerate keys: radix-select the part that is needed, bitonic sort
+            int cnt = -1;
+            if (wantj < tot)
+                cnt = block_select_smallest(s.skey, s.sval, tot, wantj, sm.skey, sm.sval, (int)p.smem_sort_cap, sm.hist,
+                                            &sm.ctx.nsel, &sm.ctx.selkey);
+            else if (tot <= (int)p.smem_sort_cap) {
+                for (int j = tid; j < tot; j += kBlock) { sm.skey[j] = s.skey[j]; sm.sval[j] = s.sval[j]; }
+                cnt = tot;
+            }
+            if (cnt >= 0) { skey = sm.skey; sval = sm.sval; nsort = cnt; }
+            const int n2 = next_pow2(nsort > 1 ? nsort : 1);
+            if (skey == sm.skey || n2 <= gcap) {
+                for (int j = nsort + tid; j < n2; j += kBlock) { skey[j] = ~0ull; sval[j] = ~0u; }
+                block_bitonic_sort(skey, sval, n2);
+            }
         }
     }
     __syncthreads();
