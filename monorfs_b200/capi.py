@@ -356,7 +356,7 @@ class Handle:
               "C5c edge sort", "A4b1 gather points", "A4b2 mini grid build", "C4b enumerate", "C4b dense process", "A3a gated component update")
 
     DEBUG_COUNTERS = ("undecided measurements", "explore hits", "gated components", "merge edges", "W0",
-                      "candidates", "eval pairs", "eval hits", "eval cell rows", "likelihood edges", "J",
+                      "candidates", "eval pairs", "wide components", "eval cell rows", "likelihood edges", "J",
                       "murty blocks", "d12", "d13", "d14", "d15")
 
     def phase_cycles(self):

@@ -537,7 +537,19 @@ __device__ inline void grid_build(BlockShared& sh, CellGrid& g, int* start, int*
             mc[a] = (mincell3[a] > 0 && mincell3[a] < INFINITY) ? mincell3[a] : ext[a] / 16.0;
             if (!(mc[a] > 0)) mc[a] = 1.0;
         }
+        // start from the closed-form factor (volume / maxcells, longest axis / kGridMaxDim); the loop only
+        // corrects for axes thinner than one cell (this section is serial: keep the divisions few)
         double f = 1.0;
+        {
+            double vol = 1.0;
+            for (int a = 0; a < 3; a++) {
+                const double da = ext[a] / mc[a];
+                f = fmax(f, da / (double)kGridMaxDim);
+                vol *= fmax(da, 1.0);
+            }
+            f = fmax(f, cbrt(vol / (double)maxcells));
+            if (!(f >= 1.0) || isinf(f)) f = 1.0;
+        }
         for (int it = 0; it < 200; it++) {
             long cells = 1;
             bool ok = true;

@@ -10,7 +10,7 @@ namespace rbphd {
 // Terms of Map.Evaluate with Mahalanobis distance^2 above this are < 2e-22 of the component's peak and
 // are skipped (the reference sums them; the parity bar for weights is 1e-9 relative).
 constexpr double kEvalD2 = 100.0;
-constexpr double kQueryCell = 0.4;   // cell edge of the grid over the map-estimate points
+constexpr double kQueryCell = 0.6;   // cell edge of the grid over the map-estimate points
 
 struct CompSrc {
     const double* w;
@@ -139,6 +139,7 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
         term_into);
     {
         const int nfat = min(sm.ctx.nU, fatcap);
+        if (tid == 0) sm.ctx.dbg[7] += sm.ctx.nU;
         const int lane = tid & 31, warp = tid >> 5;
         uint2* list = reinterpret_cast<uint2*>(sm.skey);
         uint2* ovf = reinterpret_cast<uint2*>(s.edst);
