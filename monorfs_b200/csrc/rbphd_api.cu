@@ -203,6 +203,7 @@ void make_layout(ScratchLayout& l, int cap, int Mcap, int cap_pairs, int maxq)
     take(l.pkey, U * cap_pairs);     take(l.pt, D * cap_pairs);    take(l.pmean, 3 * D * cap_pairs);
     take(l.pwgt, D * cap_pairs);
     take(l.crec, 37 * D * l.cap_pred); take(l.cpn, 9 * D * l.cap_pred);
+    take(l.hits4, U * l.cap_pred);
     take(l.skey, U * l.cap_sort);    take(l.sval, sizeof(unsigned) * l.cap_sort);
     take(l.skey2, U * l.cap_sort);   take(l.sval2, sizeof(unsigned) * l.cap_sort);
     take(l.tw, D * l.cap_top);       take(l.tm, 3 * D * l.cap_top); take(l.tP, 9 * D * l.cap_top);

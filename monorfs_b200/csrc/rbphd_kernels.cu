@@ -69,6 +69,7 @@ struct Slab {
     int *cact, *bidx;      // predicted components with at least one gated pair; pair slots in output order
     unsigned long long* pkey;
     double *pt, *pmean, *pwgt;
+    unsigned long long* hits4;   // per predicted component: up to four gated measurements packed by the counting walk
     double *crec, *cpn;    // per gated component: measurement-space record (kRec doubles) and updated covariance (9)
     unsigned long long *skey, *skey2;
     unsigned int *sval, *sval2;
@@ -95,6 +96,7 @@ __device__ __forceinline__ Slab make_slab(unsigned char* base, const ScratchLayo
     s.pkey = (unsigned long long*)(base + l.pkey); s.pt = (double*)(base + l.pt);
     s.pmean = (double*)(base + l.pmean); s.pwgt = (double*)(base + l.pwgt);
     s.crec = (double*)(base + l.crec); s.cpn = (double*)(base + l.cpn);
+    s.hits4 = (unsigned long long*)(base + l.hits4);
     s.skey = (unsigned long long*)(base + l.skey); s.sval = (unsigned int*)(base + l.sval);
     s.skey2 = (unsigned long long*)(base + l.skey2); s.sval2 = (unsigned int*)(base + l.sval2);
     s.tw = (double*)(base + l.tw); s.tm = (double*)(base + l.tm); s.tP = (double*)(base + l.tP);
@@ -222,6 +224,19 @@ __device__ __forceinline__ void gate_walk(const KParams& p, const Smem& sm, cons
         }
 }
 
+// The counting walk of a component also packs its first four gated measurements (15 bits each) and
+// min(count, 15) into one word, so that the pass that writes the pairs re-walks the grid only for the few
+// components with more than four pairs.
+__device__ __forceinline__ void hits_add(unsigned long long& packed, int& cnt, int k)
+{
+    if (cnt < 4) packed |= (unsigned long long)(unsigned)k << (15 * cnt);
+    cnt++;
+}
+__device__ __forceinline__ unsigned long long hits_close(unsigned long long packed, int cnt, int M)
+{
+    return packed | ((unsigned long long)((M <= 32767) ? min(cnt, 15) : 15) << 60);
+}
+
 // ------------------------------------------------------------------------------------------------
 // CorrectConditional, the part that depends on the component only (PHD:858-866, 895-897): expected
 // measurement, S^-1 and the Gaussian multiplier, Kalman gain K, updated covariance (I - K H) P.  The
@@ -257,10 +272,19 @@ __device__ __noinline__ void comp_update(const KParams& p, Smem& sm, const Slab&
         to_local(pose, m, diff, local);
         // the component's pairs, in one contiguous block of the pair list (slots counted by the A2 walk)
         int slot = pair_base;
-        gate_walk(p, sm, m, local, grid_in_smem, [&](int k) {
-            if (slot < p.lay.cap_pairs) s.pkey[slot] = ((unsigned long long)k << 32) | (unsigned)a;
-            slot++;
-        });
+        const unsigned long long packed = s.hits4[i];
+        const int npacked = (int)(packed >> 60);
+        if (npacked <= 4) {
+            for (int t = 0; t < npacked; t++, slot++)
+                if (slot < p.lay.cap_pairs)
+                    s.pkey[slot] = ((unsigned long long)((packed >> (15 * t)) & 0x7fffull) << 32) | (unsigned)a;
+        }
+        else {
+            gate_walk(p, sm, m, local, grid_in_smem, [&](int k) {
+                if (slot < p.lay.cap_pairs) s.pkey[slot] = ((unsigned long long)k << 32) | (unsigned)a;
+                slot++;
+            });
+        }
         measure_from_local(c, diff, local, mp);
         jacobian_l(c, pose, local, H);
         rec[0] = mp[0]; rec[1] = mp[1]; rec[2] = mp[2];
@@ -305,7 +329,8 @@ __device__ __noinline__ void comp_update(const KParams& p, Smem& sm, const Slab&
 // one gated pair: un-normalised weight term and updated mean (PHD:886-902) from the component's record;
 // for prior components the exploration density term w_i N(c_k; m_i, P_i) (PHD:956-959, MAP:210-220)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void eval_pair(const KParams& p, Smem& sm, const Slab& s, int j, int nact_prior)
+__device__ __forceinline__ void eval_pair(const KParams& p, Smem& sm, const Slab& s, int j, int nact_prior,
+                                          bool explore)
 {
     const DevCfg& c = p.cfg;
     const int capq = p.lay.cap_pairs;
@@ -329,7 +354,7 @@ __device__ __forceinline__ void eval_pair(const KParams& p, Smem& sm, const Slab
         mat3_vec(K, innov, kd);
         s.pmean[j] = m[0] + kd[0]; s.pmean[capq + j] = m[1] + kd[1]; s.pmean[2 * capq + j] = m[2] + kd[2];
     }
-    if (a < nact_prior && !sm.kflag[k]) {   // exploration term of a prior component (one term >= threshold decides)
+    if (explore && a < nact_prior && !sm.kflag[k]) {   // exploration term of a prior component (one term >= threshold decides)
         double Pinv[9];
 #pragma unroll
         for (int f = 0; f < 9; f++) Pinv[f] = rec[28 + f];
@@ -385,9 +410,11 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         s.pwmd[i] = (1 - pdi) * w;
         if (do_correct) {
             int cnt = 0;
-            gate_walk(p, sm, m, local, vgrid_smem, [&](int) { cnt++; });
+            unsigned long long packed = 0;
+            gate_walk(p, sm, m, local, vgrid_smem, [&](int k) { hits_add(packed, cnt, k); });
             s.nflag[i] = cnt;
             s.nstate[i] = (cnt > 0) ? 1 : 0;
+            s.hits4[i] = hits_close(packed, cnt, M);
         }
         if (do_births) {
             // upper bound of ln(w N(x; m, P)) at distance d: ln(w mult) - d^2 / (2 trace P)  (lambda_max <= trace)
@@ -423,11 +450,19 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
     __syncthreads();
 
     PHASE_MARK(sm, 1);
-    // A3: gated prior components (dense: one thread per component that has a pair), then their pairs
-    for (int a = tid; a < nact_prior; a += kBlock) comp_update(p, sm, s, in, a, do_births, 0, vgrid_smem);
+    // A3: gated prior components (dense: one thread per component that has a pair), then their pairs.
+    // A round of comp_update costs about the same whether 1024 or 100 threads take part (a long dependent
+    // FP64 chain), so a short last round is put off and shares the round of the births (A7).  Its pairs then
+    // miss the early exploration flags; those measurements are decided by the exact sum of A4 instead.
+    int a_split = nact_prior, j_split = npairs_prior;
+    if (do_births && nact_prior > kBlock && (nact_prior % kBlock) != 0 && (nact_prior % kBlock) <= kBlock / 2) {
+        a_split = (nact_prior / kBlock) * kBlock;
+        j_split = min(s.nflag[s.cact[a_split]], npairs_prior);
+    }
+    for (int a = tid; a < a_split; a += kBlock) comp_update(p, sm, s, in, a, do_births, 0, vgrid_smem);
     __syncthreads();
     PHASE_MARK(sm, 31);
-    for (int j = tid; j < npairs_prior; j += kBlock) eval_pair(p, sm, s, j, nact_prior);
+    for (int j = tid; j < j_split; j += kBlock) eval_pair(p, sm, s, j, nact_prior, true);
     __syncthreads();
     PHASE_MARK(sm, 2);
 
@@ -593,9 +628,11 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         s.pwmd[i] = (1 - pdi) * c.birth_w;
         if (do_correct) {
             int cnt = 0;
-            gate_walk(p, sm, m, local, false, [&](int) { cnt++; });
+            unsigned long long packed = 0;
+            gate_walk(p, sm, m, local, false, [&](int k) { hits_add(packed, cnt, k); });
             s.nflag[i] = cnt;
             s.nstate[i] = (cnt > 0) ? 1 : 0;
+            s.hits4[i] = hits_close(packed, cnt, M);
         }
     }
     __syncthreads();
@@ -616,9 +653,10 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         }
         __syncthreads();
     }
-    for (int a = nact_prior + tid; a < nact; a += kBlock) comp_update(p, sm, s, in, a, false, npairs_prior, false);
+    for (int a = a_split + tid; a < nact; a += kBlock)
+        comp_update(p, sm, s, in, a, false, (a < nact_prior) ? 0 : npairs_prior, false);
     __syncthreads();
-    for (int j = npairs_prior + tid; j < sm.ctx.npairs; j += kBlock) eval_pair(p, sm, s, j, nact_prior);
+    for (int j = j_split + tid; j < sm.ctx.npairs; j += kBlock) eval_pair(p, sm, s, j, nact_prior, false);
     __syncthreads();
 
     PHASE_MARK(sm, 4);

@@ -45,7 +45,7 @@ struct FrameGrid {
 struct ScratchLayout {
     int cap_pred, cap_pairs, cap_list, cap_sort, cap_top, cap_edges, cap_j, cap_ll, cap_nodes;
     size_t pm, pwt, pwmd, ppd, cact, bidx;
-    size_t pkey, pt, pmean, pwgt, crec, cpn;
+    size_t pkey, pt, pmean, pwgt, crec, cpn, hits4;
     size_t skey, sval, skey2, sval2;
     size_t tw, tm, tP, rho;
     size_t ecnt, edst, nstate, nowner, nflag, gitems;
