@@ -43,23 +43,44 @@ struct Ctx {
     } while (0)
 
 
+constexpr int kSortCap = 8192;   // (key,val) pairs the shared-memory sort buffer holds
+constexpr int kVsCap = 4096;
+
+// Dynamic shared memory of k_particle_update: this header, then the fixed-size buffers at compile-time
+// offsets, then the per-measurement arrays (sized by the frame's M).  The accessors go through the
+// `extern __shared__` symbol, so the compiler knows the address space and emits LDS/STS (pointers kept in a
+// struct in shared memory would turn every access into a generic load behind a pointer load).
+extern __shared__ __align__(16) unsigned char g_smem[];
+
 struct Smem {
     BlockShared sh;
     Ctx ctx;
-    double* zs;      // 3*M
-    double* cs;      // 3*M   measurement points in map space for the current particle
-    int* kflag;      // M     explored flag
-    int* kidx;       // M+1   birth index / generic per-measurement ints
-    int* gstart;     // kGridMaxCells+1
-    unsigned long long* skey;   // sort buffer (smem_sort_cap)
-    unsigned int* sval;
-    double* vs;      // kVsCap   per-query accumulators of Map.Evaluate
-    double* dens;    // M        exploration density accumulators
-    int* hist;       // 256      radix-select histogram
+    int Mc;          // measurements rounded up to even (set once per launch)
+
+    static __host__ __device__ constexpr size_t off_skey() { return (sizeof(Smem) + 15) & ~size_t(15); }
+    static __host__ __device__ constexpr size_t off_sval() { return off_skey() + sizeof(unsigned long long) * kSortCap; }
+    static __host__ __device__ constexpr size_t off_vs() { return off_sval() + sizeof(unsigned int) * kSortCap; }
+    static __host__ __device__ constexpr size_t off_hist() { return off_vs() + sizeof(double) * kVsCap; }
+    static __host__ __device__ constexpr size_t off_gstart() { return off_hist() + sizeof(int) * 256; }
+    static __host__ __device__ constexpr size_t off_var() { return (off_gstart() + sizeof(int) * (kGridMaxCells + 1) + 15) & ~size_t(15); }
+    static __host__ __device__ size_t bytes(int M)
+    {
+        const size_t Mc = (size_t)(((M + 1) & ~1) > 0 ? ((M + 1) & ~1) : 2);
+        return (off_var() + sizeof(double) * 7 * Mc + 2 * sizeof(int) * (Mc + 2) + 15) & ~size_t(15);
+    }
+
+    __device__ __forceinline__ unsigned long long* skey() const { return reinterpret_cast<unsigned long long*>(g_smem + off_skey()); }   // sort buffer (kSortCap)
+    __device__ __forceinline__ unsigned int* sval() const { return reinterpret_cast<unsigned int*>(g_smem + off_sval()); }
+    __device__ __forceinline__ double* vs() const { return reinterpret_cast<double*>(g_smem + off_vs()); }        // kVsCap: Map.Evaluate query copies / sort histograms
+    __device__ __forceinline__ int* hist() const { return reinterpret_cast<int*>(g_smem + off_hist()); }          // 256
+    __device__ __forceinline__ int* gstart() const { return reinterpret_cast<int*>(g_smem + off_gstart()); }      // kGridMaxCells + 1
+    __device__ __forceinline__ double* zs() const { return reinterpret_cast<double*>(g_smem + off_var()); }       // 3*M measurements
+    __device__ __forceinline__ double* cs() const { return zs() + 3 * Mc; }      // 3*M measurement points in map space for the current particle
+    __device__ __forceinline__ double* dens() const { return zs() + 6 * Mc; }    // M   exploration density accumulators
+    __device__ __forceinline__ int* kflag() const { return reinterpret_cast<int*>(zs() + 7 * Mc); }   // M   explored flag
+    __device__ __forceinline__ int* kidx() const { return kflag() + (Mc + 2); }  // M+1 birth index / generic per-measurement ints
 };
 
-constexpr int kSortCap = 8192;   // (key,val) pairs the shared-memory sort buffer holds
-constexpr int kVsCap = 4096;
 static_assert(sizeof(double) * kVsCap >= sizeof(int) * kWarps * 256, "the radix-sort histograms alias the vs buffer");
 static_assert(sizeof(double) * kVsCap >= sizeof(int) * (kSortBuckets + 1 + kBigBuckets + 2), "the bucket-sort histogram and long-bucket list alias the vs buffer");
 
@@ -205,7 +226,7 @@ __device__ __forceinline__ void gate_walk(const KParams& p, const Smem& sm, cons
         for (int k = 0; k < M; k++) f(k);
         return;
     }
-    // grid_in_smem: the cell offsets / items of the camera-frame grid were copied to sm.gstart / sm.kidx
+    // grid_in_smem: the cell offsets / items of the camera-frame grid were copied to sm.gstart() / sm.kidx()
     const CellGrid& g = sm.ctx.vg;
     int lo[3], hi[3];
     if (!grid_range(g, local.x, local.y, local.z, c.gate_r + 1e-9, lo, hi)) return;
@@ -213,11 +234,11 @@ __device__ __forceinline__ void gate_walk(const KParams& p, const Smem& sm, cons
         for (int cy = lo[1]; cy <= hi[1]; cy++) {
             int rowc = (cz * g.dim[1] + cy) * g.dim[0];
             int b, e;
-            if (grid_in_smem) { b = sm.gstart[rowc + lo[0]]; e = sm.gstart[rowc + hi[0] + 1]; }
+            if (grid_in_smem) { b = sm.gstart()[rowc + lo[0]]; e = sm.gstart()[rowc + hi[0] + 1]; }
             else { b = __ldg(&p.vgrid->start[rowc + lo[0]]); e = __ldg(&p.vgrid->start[rowc + hi[0] + 1]); }
             for (int t = b; t < e; t++) {
-                int k = grid_in_smem ? sm.kidx[t] : __ldg(&p.vitems[t]);
-                double dx = m[0] - sm.cs[3 * k], dy = m[1] - sm.cs[3 * k + 1], dz = m[2] - sm.cs[3 * k + 2];
+                int k = grid_in_smem ? sm.kidx()[t] : __ldg(&p.vitems[t]);
+                double dx = m[0] - sm.cs()[3 * k], dy = m[1] - sm.cs()[3 * k + 1], dz = m[2] - sm.cs()[3 * k + 2];
                 double d2 = dx * dx + dy * dy + dz * dz;
                 if (d2 <= c.gate_r2) f(k);
             }
@@ -337,7 +358,7 @@ __device__ __forceinline__ void eval_pair(const KParams& p, Smem& sm, const Slab
     const unsigned long long key = s.pkey[j];
     const int a = (int)(key & 0xffffffffu), k = (int)(key >> 32);
     const RecRef<const double> rec{s.crec + a, (size_t)p.lay.cap_pred};
-    const double* zk = &sm.zs[3 * k];
+    const double* zk = &sm.zs()[3 * k];
     const double innov[3] = {zk[0] - rec[0], zk[1] - rec[1], zk[2] - rec[2]};
     {
         double Sinv[9];
@@ -354,14 +375,14 @@ __device__ __forceinline__ void eval_pair(const KParams& p, Smem& sm, const Slab
         mat3_vec(K, innov, kd);
         s.pmean[j] = m[0] + kd[0]; s.pmean[capq + j] = m[1] + kd[1]; s.pmean[2 * capq + j] = m[2] + kd[2];
     }
-    if (explore && a < nact_prior && !sm.kflag[k]) {   // exploration term of a prior component (one term >= threshold decides)
+    if (explore && a < nact_prior && !sm.kflag()[k]) {   // exploration term of a prior component (one term >= threshold decides)
         double Pinv[9];
 #pragma unroll
         for (int f = 0; f < 9; f++) Pinv[f] = rec[28 + f];
-        const double* ck = &sm.cs[3 * k];
+        const double* ck = &sm.cs()[3 * k];
         const double dc[3] = {ck[0] - m[0], ck[1] - m[1], ck[2] - m[2]};
         const double e = rec[26] * (rec[27] * exp(-0.5 * quadform3(Pinv, dc)));
-        if (e >= c.explore_thr) sm.kflag[k] = 1;
+        if (e >= c.explore_thr) sm.kflag()[k] = 1;
     }
 }
 
@@ -378,19 +399,19 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
     const bool do_correct = (p.mode == MODE_FRAME || p.mode == MODE_STAGE_CORRECT);
 
     // the frame's camera-frame measurement grid: offsets and items into shared memory for the A2 walk
-    // (sm.gstart / sm.kidx are reused by the per-particle grids later in the frame)
+    // (sm.gstart() / sm.kidx() are reused by the per-particle grids later in the frame)
     const bool vgrid_smem = do_correct && !c.ungated && M > 0;
     if (vgrid_smem) {
         const int ncell = sm.ctx.vg.ncell;
-        for (int a = tid; a <= ncell; a += kBlock) sm.gstart[a] = __ldg(&p.vgrid->start[a]);
-        for (int a = tid; a < M; a += kBlock) sm.kidx[a] = __ldg(&p.vitems[a]);
+        for (int a = tid; a <= ncell; a += kBlock) sm.gstart()[a] = __ldg(&p.vgrid->start[a]);
+        for (int a = tid; a < M; a += kBlock) sm.kidx()[a] = __ldg(&p.vitems[a]);
     }
     // A1: measurements in map space (PRM:299-312)
     for (int k = tid; k < M; k += kBlock) {
         double ck[3];
-        measure_to_map(c, pose, &sm.zs[3 * k], ck);
-        sm.cs[3 * k] = ck[0]; sm.cs[3 * k + 1] = ck[1]; sm.cs[3 * k + 2] = ck[2];
-        sm.kflag[k] = do_births ? 0 : 1;
+        measure_to_map(c, pose, &sm.zs()[3 * k], ck);
+        sm.cs()[3 * k] = ck[0]; sm.cs()[3 * k + 1] = ck[1]; sm.cs()[3 * k + 2] = ck[2];
+        sm.kflag()[k] = do_births ? 0 : 1;
     }
     __syncthreads();
 
@@ -475,7 +496,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         if (tid == 0) sm.ctx.nU = 0;
         __syncthreads();
         for (int k = tid; k < M; k += kBlock)
-            if (!sm.kflag[k]) { int u = atomicAdd(&sm.ctx.nU, 1); sm.kidx[u] = k; }
+            if (!sm.kflag()[k]) { int u = atomicAdd(&sm.ctx.nU, 1); sm.kidx()[u] = k; }
         __syncthreads();
         const int nU = sm.ctx.nU;
         if (tid == 0) sm.ctx.dbg[0] += nU;
@@ -484,24 +505,24 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
             // small cell grid over the undecided measurement points (cell = explore radius); every prior
             // component then visits only the points in its 3x3x3 neighbourhood.  Partial sums go to the
             // slab with native FP64 global atomics (shared-memory FP64 atomics are CAS loops).
-            double* ux = reinterpret_cast<double*>(sm.skey);
+            double* ux = reinterpret_cast<double*>(sm.skey());
             double* uy = ux + nU;
             double* uz = uy + nU;
             int* uitems = reinterpret_cast<int*>(uz + nU);
             for (int u = tid; u < nU; u += kBlock) {
-                const int k = sm.kidx[u];
-                ux[u] = sm.cs[3 * k]; uy[u] = sm.cs[3 * k + 1]; uz[u] = sm.cs[3 * k + 2];
+                const int k = sm.kidx()[u];
+                ux[u] = sm.cs()[3 * k]; uy[u] = sm.cs()[3 * k + 1]; uz[u] = sm.cs()[3 * k + 2];
                 s.vsum[u] = 0.0;
             }
             __syncthreads();
             PHASE_MARK(sm, 27);
-            grid_build(sm.sh, sm.ctx.grid, sm.gstart, uitems, ux, uy, uz, nU, c.explore_r, c.explore_r, c.explore_r, 512);
+            grid_build(sm.sh, sm.ctx.grid, sm.gstart(), uitems, ux, uy, uz, nU, c.explore_r, c.explore_r, c.explore_r, 512);
             PHASE_MARK(sm, 28);
             const CellGrid& g = sm.ctx.grid;
             const double logskip = log(c.explore_thr) - 32.3;   // ln(1e-14)
             // the point arrays live in the first 28 * nU bytes of the sort buffer; the pair list behind them
             const int list_off = (28 * nU + 15) / 16 * 2;   // in uint2 units, rounded to 16 bytes
-            uint2* hits = reinterpret_cast<uint2*>(sm.skey) + list_off;
+            uint2* hits = reinterpret_cast<uint2*>(sm.skey()) + list_off;
             const int hits_cap = (int)p.smem_sort_cap - list_off;
             enumerate_then_process(
                 sm, N, hits, hits_cap, reinterpret_cast<uint2*>(s.edst), p.lay.cap_edges / 2,
@@ -522,7 +543,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
                     for (int cz = lo[2]; cz <= hi[2]; cz++)
                         for (int cy = lo[1]; cy <= hi[1]; cy++) {
                             const int rowc = (cz * g.dim[1] + cy) * g.dim[0];
-                            const int qb = sm.gstart[rowc + lo[0]], qe = sm.gstart[rowc + hi[0] + 1];
+                            const int qb = sm.gstart()[rowc + lo[0]], qe = sm.gstart()[rowc + hi[0] + 1];
                             for (int q = qb; q < qe; q++) {
                                 const int u = uitems[q];
                                 const double dx = m[0] - ux[u], dy = m[1] - uy[u], dz = m[2] - uz[u];
@@ -543,22 +564,22 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
                 },
                 17, 17);
             __syncthreads();
-            for (int u = tid; u < nU; u += kBlock) sm.dens[u] = s.vsum[u];
+            for (int u = tid; u < nU; u += kBlock) sm.dens()[u] = s.vsum[u];
             __syncthreads();
             PHASE_MARK(sm, 17);
             int ambiguous = 0;
             for (int u = tid; u < nU; u += kBlock) {
-                const double d = sm.dens[u];
-                const int k = sm.kidx[u];
-                if (d >= c.explore_thr * (1.0 + 1e-9)) sm.kflag[k] = 1;
-                else if (d >= c.explore_thr * (1.0 - 1e-9)) { sm.kflag[k] = 2; ambiguous = 1; }
+                const double d = sm.dens()[u];
+                const int k = sm.kidx()[u];
+                if (d >= c.explore_thr * (1.0 + 1e-9)) sm.kflag()[k] = 1;
+                else if (d >= c.explore_thr * (1.0 - 1e-9)) { sm.kflag()[k] = 2; ambiguous = 1; }
             }
             if (__syncthreads_or(ambiguous)) {
                 const int nF = N;
                 const int lane = tid & 31, warp = tid >> 5;
                 for (int k = warp; k < M; k += kWarps) {
-                    if (sm.kflag[k] != 2) continue;
-                    const double ck[3] = {sm.cs[3 * k], sm.cs[3 * k + 1], sm.cs[3 * k + 2]};
+                    if (sm.kflag()[k] != 2) continue;
+                    const double ck[3] = {sm.cs()[3 * k], sm.cs()[3 * k + 1], sm.cs()[3 * k + 2]};
                     double sum = 0;
                     for (int base = 0; base < nF; base += 32) {
                         int f = base + lane;
@@ -586,7 +607,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
                             mask &= mask - 1;
                         }
                     }
-                    if (lane == 0) sm.kflag[k] = (sum >= c.explore_thr) ? 1 : 0;
+                    if (lane == 0) sm.kflag()[k] = (sum >= c.explore_thr) ? 1 : 0;
                 }
                 __syncthreads();
             }
@@ -595,16 +616,16 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
 
         PHASE_MARK(sm, 18);
         // A5: births in measurement order (PHD:806-816)
-        for (int k = tid; k < M; k += kBlock) sm.kidx[k] = sm.kflag[k] ? 0 : 1;
+        for (int k = tid; k < M; k += kBlock) sm.kidx()[k] = sm.kflag()[k] ? 0 : 1;
         __syncthreads();
-        B = block_scan_array(sm.sh, sm.kidx, M);
+        B = block_scan_array(sm.sh, sm.kidx(), M);
         if (N + B > capp) { B = capp - N; if (tid == 0) sm.ctx.status |= ST_OVER_COMPONENTS; }
         for (int k = tid; k < M; k += kBlock) {
-            if (!sm.kflag[k]) {
-                int b = sm.kidx[k];
+            if (!sm.kflag()[k]) {
+                int b = sm.kidx()[k];
                 if (b < B) {
                     int i = N + b;
-                    s.pm[i] = sm.cs[3 * k]; s.pm[capp + i] = sm.cs[3 * k + 1]; s.pm[2 * capp + i] = sm.cs[3 * k + 2];
+                    s.pm[i] = sm.cs()[3 * k]; s.pm[capp + i] = sm.cs()[3 * k + 1]; s.pm[2 * capp + i] = sm.cs()[3 * k + 2];
                     s.pwt[i] = c.birth_w;
                 }
             }
@@ -663,8 +684,8 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
     // A8: order the pairs by (measurement, component) -- the reference's output order (PHD:881-903):
     // counting sort by measurement, then each measurement's short segment by component index
     const int np = sm.ctx.npairs;
-    int* segstart = sm.kidx;   // M + 1 (free after the births)
-    int* cursor = sm.kflag;    // M
+    int* segstart = sm.kidx();   // M + 1 (free after the births)
+    int* cursor = sm.kflag();    // M
     for (int k = tid; k <= M; k += kBlock) segstart[k] = 0;
     __syncthreads();
     for (int j = tid; j < np; j += kBlock) atomicAdd(&segstart[(int)(s.pkey[j] >> 32)], 1);
@@ -679,8 +700,8 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
     __syncthreads();
     // A9: per measurement: component order, weightsum, then the detection weights (PHD:886-902).
     // The segments are sorted on a shared-memory copy (component index, pair slot).
-    unsigned int* scomp = reinterpret_cast<unsigned int*>(sm.skey);   // np <= 2 * kSortCap entries
-    unsigned int* sslot = sm.sval;
+    unsigned int* scomp = reinterpret_cast<unsigned int*>(sm.skey());   // np <= 2 * kSortCap entries
+    unsigned int* sslot = sm.sval();
     const bool in_smem = np <= (int)p.smem_sort_cap;
     if (in_smem) {
         for (int t = tid; t < np; t += kBlock) {
@@ -693,7 +714,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
     if (in_smem) {
         // rank sort inside each segment, one thread per PAIR (balanced even when a few measurements gate
         // dozens of components): rank = number of pairs of the same measurement with a smaller component
-        unsigned int* sorted = reinterpret_cast<unsigned int*>(sm.skey) + p.smem_sort_cap;   // upper half of the key buffer
+        unsigned int* sorted = reinterpret_cast<unsigned int*>(sm.skey()) + p.smem_sort_cap;   // upper half of the key buffer
         for (int t = tid; t < np; t += kBlock) {
             const unsigned myc = scomp[t];
             const int k = (int)(s.pkey[sslot[t]] >> 32);
@@ -720,7 +741,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         __syncthreads();
     }
     // weight terms gathered once, in sorted order, into shared memory (the component keys are dead now)
-    double* spt = reinterpret_cast<double*>(sm.skey);
+    double* spt = reinterpret_cast<double*>(sm.skey());
     if (in_smem) {
         for (int t = tid; t < np; t += kBlock) { const int j = (int)sslot[t]; s.bidx[t] = j; }
         __syncthreads();
@@ -796,7 +817,7 @@ __device__ __forceinline__ void for_neighbours(const Smem& sm, const Slab& s, in
     for (int cz = lo[2]; cz <= hi[2]; cz++)
         for (int cy = lo[1]; cy <= hi[1]; cy++) {
             int rowc = (cz * g.dim[1] + cy) * g.dim[0];
-            int b = sm.gstart[rowc + lo[0]], e = sm.gstart[rowc + hi[0] + 1];
+            int b = sm.gstart()[rowc + lo[0]], e = sm.gstart()[rowc + hi[0] + 1];
             for (int t = b; t < e; t++) {
                 int r = s.gitems[t];
                 double dx = px[r] - x, dy = py[r] - y, dz = pz[r] - z;
@@ -863,15 +884,15 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
     unsigned int* sval = s.sval;
     {
         const bool in_smem = nc <= (int)p.smem_sort_cap;
-        unsigned long long* k1 = in_smem ? sm.skey : s.skey2;
-        unsigned int* v1 = in_smem ? sm.sval : s.sval2;
+        unsigned long long* k1 = in_smem ? sm.skey() : s.skey2;
+        unsigned int* v1 = in_smem ? sm.sval() : s.sval2;
         // weights are spread out: one bucket pass + tiny per-bucket sorts; the radix sort is the fallback for
         // degenerate key sets (thousands of equal weights)
-        if (block_bucket_sort(sm.sh, s.skey, s.sval, k1, v1, nc, reinterpret_cast<int*>(sm.vs),
-                              reinterpret_cast<int*>(sm.vs) + kSortBuckets + 1, s.skey, s.sval, in_smem ? nullptr : sm.skey)) {
+        if (block_bucket_sort(sm.sh, s.skey, s.sval, k1, v1, nc, reinterpret_cast<int*>(sm.vs()),
+                              reinterpret_cast<int*>(sm.vs()) + kSortBuckets + 1, s.skey, s.sval, in_smem ? nullptr : sm.skey())) {
             skey = k1; sval = v1;
         }
-        else if (block_radix_sort(sm.sh, s.skey, s.sval, k1, v1, nc, reinterpret_cast<int*>(sm.vs), sm.hist)) {
+        else if (block_radix_sort(sm.sh, s.skey, s.sval, k1, v1, nc, reinterpret_cast<int*>(sm.vs()), sm.hist())) {
             skey = k1; sval = v1;
         }
     }
@@ -906,13 +927,13 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
     // per hundred components), so they are appended to one list and sorted by (r, r') afterwards.
     const double* tx = s.tm; const double* ty = s.tm + capw; const double* tz = s.tm + 2 * capw;
     double mincell = 2.0 * rmean;
-    grid_build(sm.sh, sm.ctx.grid, sm.gstart, s.gitems, tx, ty, tz, W0, mincell, mincell, mincell);
+    grid_build(sm.sh, sm.ctx.grid, sm.gstart(), s.gitems, tx, ty, tz, W0, mincell, mincell, mincell);
     const double t2 = c.merge_t * c.merge_t;
     PHASE_MARK(sm, 19);
-    float* fx = reinterpret_cast<float*>(sm.skey);        // cell-ordered copies (sort buffer is idle here)
+    float* fx = reinterpret_cast<float*>(sm.skey());        // cell-ordered copies (sort buffer is idle here)
     float* fy = fx + W0;
     float* fz = fy + W0;
-    int* frank = reinterpret_cast<int*>(sm.sval);
+    int* frank = reinterpret_cast<int*>(sm.sval());
     const bool fsm = (3 * (size_t)W0 * sizeof(float) <= sizeof(unsigned long long) * p.smem_sort_cap) &&
                      ((size_t)W0 <= p.smem_sort_cap);
     if (fsm) {
@@ -946,7 +967,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
         // the walk only prefilters (single precision, shared memory) and lists the surviving pairs; the exact
         // tests then run densely, one thread per pair (no global-memory latency inside the divergent walk)
         const int list_off = fsm ? (3 * W0 * (int)sizeof(float) + 15) / 16 * 2 : 0;   // uint2 units behind fx/fy/fz
-        uint2* list = reinterpret_cast<uint2*>(sm.skey) + list_off;
+        uint2* list = reinterpret_cast<uint2*>(sm.skey()) + list_off;
         const int list_cap = (int)p.smem_sort_cap - list_off;
         enumerate_then_process(
             sm, W0, list, list_cap, reinterpret_cast<uint2*>(s.edst), p.lay.cap_edges / 2,
@@ -973,7 +994,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
                 for (int cz = lo[2]; cz <= hi[2]; cz++)
                     for (int cy = lo[1]; cy <= hi[1]; cy++) {
                         const int rowc = (cz * g.dim[1] + cy) * g.dim[0];
-                        const int qb = sm.gstart[rowc + lo[0]], qe = sm.gstart[rowc + hi[0] + 1];
+                        const int qb = sm.gstart()[rowc + lo[0]], qe = sm.gstart()[rowc + hi[0] + 1];
                         if (fsm) {
                             for (int q = qb; q < qe; q++)
                                 if (fabsf(fx[q] - xf) <= rf && fabsf(fy[q] - yf) <= rf && fabsf(fz[q] - zf) <= rf) {
@@ -998,8 +1019,8 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
     ne = min(ne, cape);
     // edges ordered by (r, r'): r' ascending = list order of the reference's inner loop (PHD:936-942)
     const int ne2 = next_pow2(ne > 1 ? ne : 1);
-    unsigned long long* ekey = (ne2 <= (int)p.smem_sort_cap) ? sm.skey : s.skey;
-    unsigned int* eval_ = (ne2 <= (int)p.smem_sort_cap) ? sm.sval : s.sval;
+    unsigned long long* ekey = (ne2 <= (int)p.smem_sort_cap) ? sm.skey() : s.skey;
+    unsigned int* eval_ = (ne2 <= (int)p.smem_sort_cap) ? sm.sval() : s.sval;
     __syncthreads();
     if (ne2 <= p.lay.cap_sort) {
         for (int e = tid; e < ne2; e += kBlock) { ekey[e] = (e < ne) ? elist[e] : ~0ull; eval_[e] = 0u; }
@@ -1123,49 +1144,13 @@ __device__ __forceinline__ void dump_comp(const KParams& p, int o, double w, con
     for (int a = 0; a < 9; a++) d[(size_t)(4 + a) * dc + o] = P[a];
 }
 
-__host__ __device__ inline size_t carve_offsets(int M, size_t sort_cap, size_t* off_out)
-{
-    // off_out: zs, cs, skey, sval, vs, dens, kflag, kidx, hist, gstart
-    size_t off = (sizeof(Smem) + 15) & ~size_t(15);
-    const int Mc = ((M + 1) & ~1) > 0 ? ((M + 1) & ~1) : 2;
-    off_out[0] = off; off += sizeof(double) * 3 * Mc;
-    off_out[1] = off; off += sizeof(double) * 3 * Mc;
-    off_out[2] = off; off += sizeof(unsigned long long) * sort_cap;
-    off_out[3] = off; off += sizeof(unsigned int) * sort_cap;
-    off_out[4] = off; off += sizeof(double) * kVsCap;
-    off_out[5] = off; off += sizeof(double) * Mc;
-    off_out[6] = off; off += sizeof(int) * (Mc + 2);
-    off_out[7] = off; off += sizeof(int) * (Mc + 2);
-    off_out[8] = off; off += sizeof(int) * 256;
-    off_out[9] = off; off += sizeof(int) * (kGridMaxCells + 1);
-    return (off + 15) & ~size_t(15);
-}
-
-__device__ __forceinline__ void carve_smem(unsigned char* raw, const KParams& p, Smem*& smp)
-{
-    smp = reinterpret_cast<Smem*>(raw);
-    size_t o[10];
-    carve_offsets(p.M, p.smem_sort_cap, o);
-    smp->zs = reinterpret_cast<double*>(raw + o[0]);
-    smp->cs = reinterpret_cast<double*>(raw + o[1]);
-    smp->skey = reinterpret_cast<unsigned long long*>(raw + o[2]);
-    smp->sval = reinterpret_cast<unsigned int*>(raw + o[3]);
-    smp->vs = reinterpret_cast<double*>(raw + o[4]);
-    smp->dens = reinterpret_cast<double*>(raw + o[5]);
-    smp->kflag = reinterpret_cast<int*>(raw + o[6]);
-    smp->kidx = reinterpret_cast<int*>(raw + o[7]);
-    smp->hist = reinterpret_cast<int*>(raw + o[8]);
-    smp->gstart = reinterpret_cast<int*>(raw + o[9]);
-}
-
 // ------------------------------------------------------------------------------------------------
 // the fused per-particle kernel (persistent: CTA b processes particles b, b+grid, ...)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock, 1) k_particle_update(const __grid_constant__ KParams p)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-    if (threadIdx.x == 0) { Smem* smp; carve_smem(smem_raw, p, smp); }
+    Smem& sm = *reinterpret_cast<Smem*>(g_smem);
+    if (threadIdx.x == 0) sm.Mc = ((p.M + 1) & ~1) > 0 ? ((p.M + 1) & ~1) : 2;
     __syncthreads();
     const int tid = threadIdx.x;
     const Slab s = make_slab(p.scratch + (size_t)blockIdx.x * p.lay.bytes, p.lay);
@@ -1179,7 +1164,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_particle_update(const __grid_cons
         if (bulk_ok) {
             if (tid == 0) {
                 unsigned bar_a = (unsigned)__cvta_generic_to_shared(&bar);
-                unsigned dst_a = (unsigned)__cvta_generic_to_shared(sm.zs);
+                unsigned dst_a = (unsigned)__cvta_generic_to_shared(sm.zs());
                 asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
@@ -1200,7 +1185,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_particle_update(const __grid_cons
             }
         }
         else {
-            for (int t = tid; t < 3 * p.M; t += kBlock) sm.zs[t] = p.z[t];
+            for (int t = tid; t < 3 * p.M; t += kBlock) sm.zs()[t] = p.z[t];
         }
         __syncthreads();
     }
@@ -1601,8 +1586,7 @@ size_t murty_workspace_bytes() { return sizeof(MurtyWork); }
 size_t particle_update_smem(int max_measurements, size_t* sort_cap)
 {
     if (sort_cap) *sort_cap = kSortCap;
-    size_t o[10];
-    return carve_offsets(max_measurements, kSortCap, o);
+    return Smem::bytes(max_measurements);
 }
 
 int particle_update_max_ctas_per_sm(size_t smem)

@@ -46,7 +46,7 @@ __device__ inline double eval_term_full(const CompSrc& c, int i, double x, doubl
 
 // v[t] = sum_i w_i N(jm_t; m_i, P_i) for the J points in s.jm (MAP:192-202), component-major: each thread
 // owns components, looks up the query points inside the component's influence radius in the cell grid
-// over the J points (sm.ctx.grid / sm.gstart / s.gitems, built by the caller) and accumulates into
+// over the J points (sm.ctx.grid / sm.gstart() / s.gitems, built by the caller) and accumulates into
 // vs[t] with double atomics.  Returns sum_t ln v[t].
 __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, const CompSrc& c, int J,
                                      double* vs)
@@ -56,7 +56,7 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
     const CellGrid& g = sm.ctx.grid;
     // cell-ordered single-precision copy of the points (x, y, z, index) in shared memory, made by the caller
     const bool qsm = (J * 2 <= kVsCap);
-    const float4* qf = reinterpret_cast<const float4*>(sm.vs);
+    const float4* qf = reinterpret_cast<const float4*>(sm.vs());
     for (int t = tid; t < J; t += kBlock) vs[t] = 0.0;
     __syncthreads();
     PHASE_MARK(sm, 20);
@@ -91,7 +91,7 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
     if (tid == 0) sm.ctx.nU = 0;
     __syncthreads();
     enumerate_then_process(
-        sm, c.n, reinterpret_cast<uint2*>(sm.skey), (int)p.smem_sort_cap, reinterpret_cast<uint2*>(s.edst),
+        sm, c.n, reinterpret_cast<uint2*>(sm.skey()), (int)p.smem_sort_cap, reinterpret_cast<uint2*>(s.edst),
         p.lay.cap_edges / 2,
         [&](int i, auto emit) {
             const double x = c.mx[i], y = c.my[i], z = c.mz[i];
@@ -104,7 +104,7 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
                 if (cells > 2048) brute = true;
                 else if (cells > 27) {   // wide component: a whole warp walks its cells later (balance)
                     const int f = atomicAdd(&sm.ctx.nU, 1);
-                    if (f < fatcap) { sm.kidx[f] = i; return; }
+                    if (f < fatcap) { sm.kidx()[f] = i; return; }
                 }
             }
             if (brute) {
@@ -119,7 +119,7 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
             for (int cz = lo[2]; cz <= hi[2]; cz++)
                 for (int cy = lo[1]; cy <= hi[1]; cy++) {
                     const int rowc = (cz * g.dim[1] + cy) * g.dim[0];
-                    const int b = sm.gstart[rowc + lo[0]], e = sm.gstart[rowc + hi[0] + 1];
+                    const int b = sm.gstart()[rowc + lo[0]], e = sm.gstart()[rowc + hi[0] + 1];
                     if (qsm) {
                         for (int q = b; q < e; q++) {
                             const float4 v = qf[q];
@@ -141,7 +141,7 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
         const int nfat = min(sm.ctx.nU, fatcap);
         if (tid == 0) sm.ctx.dbg[7] += sm.ctx.nU;
         const int lane = tid & 31, warp = tid >> 5;
-        uint2* list = reinterpret_cast<uint2*>(sm.skey);
+        uint2* list = reinterpret_cast<uint2*>(sm.skey());
         uint2* ovf = reinterpret_cast<uint2*>(s.edst);
         const int list_cap = (int)p.smem_sort_cap, ovf_cap = p.lay.cap_edges / 2;
         for (int fbase = 0; fbase < nfat; fbase += kWarps) {
@@ -149,7 +149,7 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
             __syncthreads();
             const int f = fbase + warp;
             if (f < nfat) {
-                const int i = sm.kidx[f];
+                const int i = sm.kidx()[f];
                 const double x = c.mx[i], y = c.my[i], z = c.mz[i];
                 const double r2 = rec[10 * rs + i];
                 int lo[3], hi[3];
@@ -158,7 +158,7 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
                     for (int rw = lane; rw < rows; rw += 32) {
                         const int cz = lo[2] + rw / ny, cy = lo[1] + rw % ny;
                         const int rowc = (cz * g.dim[1] + cy) * g.dim[0];
-                        const int b = sm.gstart[rowc + lo[0]], e = sm.gstart[rowc + hi[0] + 1];
+                        const int b = sm.gstart()[rowc + lo[0]], e = sm.gstart()[rowc + hi[0] + 1];
                         for (int q = b; q < e; q++) {
                             int t;
                             bool in;
@@ -422,7 +422,7 @@ __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab
                 int b = __ldg(&p.zgrid->start[rowc + lo[0]]), e = __ldg(&p.zgrid->start[rowc + hi[0] + 1]);
                 for (int q = b; q < e; q++) {
                     int k = __ldg(&p.zitems[q]);
-                    double d3[3] = {mp[0] - sm.zs[3 * k], mp[1] - sm.zs[3 * k + 1], mp[2] - sm.zs[3 * k + 2]};
+                    double d3[3] = {mp[0] - sm.zs()[3 * k], mp[1] - sm.zs()[3 * k + 1], mp[2] - sm.zs()[3 * k + 2]};
                     double d = sqrt(quadform3(c.Rinv, d3));
                     if (d < 5) {
                         int idx = atomicAdd(&s_nll, 1);
@@ -462,8 +462,8 @@ __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab
     PHASE_MARK(sm, 25);
     // edges ordered by (component label, landmark, measurement)
     const int n2 = next_pow2(nll > 1 ? nll : 1);
-    unsigned long long* skey = (n2 <= (int)p.smem_sort_cap) ? sm.skey : s.skey;
-    unsigned int* sval = (n2 <= (int)p.smem_sort_cap) ? sm.sval : s.sval;
+    unsigned long long* skey = (n2 <= (int)p.smem_sort_cap) ? sm.skey() : s.skey;
+    unsigned int* sval = (n2 <= (int)p.smem_sort_cap) ? sm.sval() : s.sval;
     for (int e = tid; e < n2; e += kBlock) {
         if (e < nll) {
             unsigned long long t = s.llkey[e] >> 32, k = s.llkey[e] & 0xffffffffu;
@@ -557,22 +557,22 @@ __device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const 
         // the whole multiset fits the shared-memory buffer: bucket sort (weights are spread out)
         bool sorted = false;
         if (tot <= (int)p.smem_sort_cap) {
-            sorted = block_bucket_sort(sm.sh, s.skey, s.sval, sm.skey, sm.sval, tot, reinterpret_cast<int*>(sm.vs),
-                                       reinterpret_cast<int*>(sm.vs) + kSortBuckets + 1, s.skey, s.sval);
-            if (sorted) { skey = sm.skey; sval = sm.sval; }
+            sorted = block_bucket_sort(sm.sh, s.skey, s.sval, sm.skey(), sm.sval(), tot, reinterpret_cast<int*>(sm.vs()),
+                                       reinterpret_cast<int*>(sm.vs()) + kSortBuckets + 1, s.skey, s.sval);
+            if (sorted) { skey = sm.skey(); sval = sm.sval(); }
         }
         if (!sorted) {   // too large, or degenerate keys: radix-select the part that is needed, bitonic sort
             int cnt = -1;
             if (wantj < tot)
-                cnt = block_select_smallest(s.skey, s.sval, tot, wantj, sm.skey, sm.sval, (int)p.smem_sort_cap, sm.hist,
+                cnt = block_select_smallest(s.skey, s.sval, tot, wantj, sm.skey(), sm.sval(), (int)p.smem_sort_cap, sm.hist(),
                                             &sm.ctx.nsel, &sm.ctx.selkey);
             else if (tot <= (int)p.smem_sort_cap) {
-                for (int j = tid; j < tot; j += kBlock) { sm.skey[j] = s.skey[j]; sm.sval[j] = s.sval[j]; }
+                for (int j = tid; j < tot; j += kBlock) { sm.skey()[j] = s.skey[j]; sm.sval()[j] = s.sval[j]; }
                 cnt = tot;
             }
-            if (cnt >= 0) { skey = sm.skey; sval = sm.sval; nsort = cnt; }
+            if (cnt >= 0) { skey = sm.skey(); sval = sm.sval(); nsort = cnt; }
             const int n2 = next_pow2(nsort > 1 ? nsort : 1);
-            if (skey == sm.skey || n2 <= gcap) {
+            if (skey == sm.skey() || n2 <= gcap) {
                 for (int j = nsort + tid; j < n2; j += kBlock) { skey[j] = ~0ull; sval[j] = ~0u; }
                 block_bitonic_sort(skey, sval, n2);
             }
@@ -594,10 +594,10 @@ __device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const 
                  p.cfg.birth_cov, Npred};
     double* vs = s.vsum;   // global: double atomics are native there (shared-memory ones are CAS loops)
     PHASE_MARK(sm, 11);
-    grid_build(sm.sh, sm.ctx.grid, sm.gstart, s.gitems, s.jm, s.jm + capj, s.jm + 2 * capj, J, kQueryCell, kQueryCell,
+    grid_build(sm.sh, sm.ctx.grid, sm.gstart(), s.gitems, s.jm, s.jm + capj, s.jm + 2 * capj, J, kQueryCell, kQueryCell,
                kQueryCell);
     if (J * 2 <= kVsCap) {
-        float4* qf = reinterpret_cast<float4*>(sm.vs);
+        float4* qf = reinterpret_cast<float4*>(sm.vs());
         for (int q = tid; q < J; q += kBlock) {
             const int t = s.gitems[q];
             qf[q] = make_float4((float)s.jm[t], (float)s.jm[capj + t], (float)s.jm[2 * capj + t], __int_as_float(t));
