@@ -213,7 +213,7 @@ void make_layout(ScratchLayout& l, int cap, int Mcap, int cap_pairs, int maxq)
     take(l.gitems, I * l.cap_nodes);
     take(l.jidx, I * l.cap_j);       take(l.jm, 3 * D * l.cap_j);  take(l.jmp, 3 * D * l.cap_j);
     take(l.jpd, D * l.cap_j);        take(l.vsum, D * l.cap_j);
-    take(l.cinv, 11 * D * l.cap_pred); take(l.cnorm, D * l.cap_pred); take(l.crad, D * l.cap_pred);   // exploration bound per component
+    take(l.cinv, 11 * D * l.cap_pred); take(l.cinv2, 11 * D * l.cap_pred); take(l.cnorm, D * l.cap_pred); take(l.crad, D * l.cap_pred);   // exploration bound per component
     take(l.fat, 16);  take(l.clist, 16); take(l.gx, 16);
     take(l.llkey, U * l.cap_ll);     take(l.llval, D * l.cap_ll);
     take(l.uf, I * (l.cap_j + Mcap + 2)); take(l.bcnt, I * (l.cap_j + Mcap + 2));

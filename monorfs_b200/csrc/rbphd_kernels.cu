@@ -97,7 +97,7 @@ struct Slab {
     double *tw, *tm, *tP, *rho;
     int *ecnt, *edst, *nstate, *nowner, *nflag, *gitems;
     int *jidx;
-    double *jm, *jmp, *jpd, *vsum, *cinv, *cnorm, *crad;
+    double *jm, *jmp, *jpd, *vsum, *cinv, *cinv2, *cnorm, *crad;
     int *fat, *clist;
     double* gx;
     unsigned long long* llkey;
@@ -126,6 +126,7 @@ __device__ __forceinline__ Slab make_slab(unsigned char* base, const ScratchLayo
     s.nowner = (int*)(base + l.nowner); s.nflag = (int*)(base + l.nflag); s.gitems = (int*)(base + l.gitems);
     s.jidx = (int*)(base + l.jidx); s.jm = (double*)(base + l.jm); s.jmp = (double*)(base + l.jmp);
     s.jpd = (double*)(base + l.jpd); s.vsum = (double*)(base + l.vsum); s.cinv = (double*)(base + l.cinv);
+    s.cinv2 = (double*)(base + l.cinv2);
     s.cnorm = (double*)(base + l.cnorm); s.crad = (double*)(base + l.crad); s.fat = (int*)(base + l.fat);
     s.clist = (int*)(base + l.clist); s.gx = (double*)(base + l.gx);
     s.llkey = (unsigned long long*)(base + l.llkey); s.llval = (double*)(base + l.llval);
@@ -386,6 +387,27 @@ __device__ __forceinline__ void eval_pair(const KParams& p, Smem& sm, const Slab
     }
 }
 
+// Evaluation record of one component (used by Map.Evaluate, MAP:192-202, and the exploration terms): P^-1, the
+// Gaussian multiplier, and the squared cull radius kEvalD2 * bound with bound >= lambda_max(P):
+// ||P^2||_F^(1/2) = (sum lambda^4)^(1/4), within 32 % of lambda_max (the trace is up to 3x larger).
+// Struct of arrays with stride rs; written where the covariance is in registers anyway (A2, A5, B6).
+constexpr double kEvalD2 = 100.0;   // terms of Map.Evaluate beyond this Mahalanobis distance^2 are < 2e-22 of the peak
+constexpr int kEvalRec = 11;
+__device__ __forceinline__ double eval_record(const double* P, double* rec, size_t rs, int i)
+{
+    double Pinv[9], P2[9];
+    const double det = mat3_inv(P, Pinv);
+#pragma unroll
+    for (int a = 0; a < 9; a++) rec[(size_t)a * rs + i] = Pinv[a];
+    rec[9 * rs + i] = gauss_mult(det);
+    mat3_mul(P, P, P2);
+    double f = 0;
+#pragma unroll
+    for (int a = 0; a < 9; a++) f += P2[a] * P2[a];
+    rec[10 * rs + i] = kEvalD2 * sqrt(sqrt(f)) * (1.0 + 1e-6);
+    return det;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Phase A: PredictConditional + CorrectConditional
 // ------------------------------------------------------------------------------------------------
@@ -397,6 +419,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
     const Pose pose = pose_load(sm.ctx.pose);
     const bool do_births = (p.mode == MODE_FRAME || p.mode == MODE_STAGE_PREDICT);
     const bool do_correct = (p.mode == MODE_FRAME || p.mode == MODE_STAGE_CORRECT);
+    const bool eval_recs = (p.mode == MODE_FRAME && !p.only_mapping);   // WeightAlpha follows: keep P^-1 records
 
     // the frame's camera-frame measurement grid: offsets and items into shared memory for the A2 walk
     // (sm.gstart() / sm.kidx() are reused by the per-particle grids later in the frame)
@@ -442,8 +465,10 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
             double P[9];
 #pragma unroll
             for (int a = 0; a < 9; a++) P[a] = mfield(in, p.cap, 4 + a)[i];
-            const double det = P[0] * (P[4] * P[8] - P[5] * P[7]) - P[1] * (P[3] * P[8] - P[5] * P[6]) +
-                               P[2] * (P[3] * P[7] - P[4] * P[6]);
+            // (frames that go on to WeightAlpha also need the component's evaluation record; same determinant)
+            const double det = eval_recs ? eval_record(P, s.cinv, (size_t)capp, i)
+                                         : P[0] * (P[4] * P[8] - P[5] * P[7]) - P[1] * (P[3] * P[8] - P[5] * P[6]) +
+                                               P[2] * (P[3] * P[7] - P[4] * P[6]);
             const double tr = P[0] + P[4] + P[8];
             const bool spd = (det > 0) && (tr > 0) && (w >= 0);
             s.cnorm[i] = spd ? log(w * gauss_mult(det)) : INFINITY;
@@ -627,6 +652,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
                     int i = N + b;
                     s.pm[i] = sm.cs()[3 * k]; s.pm[capp + i] = sm.cs()[3 * k + 1]; s.pm[2 * capp + i] = sm.cs()[3 * k + 2];
                     s.pwt[i] = c.birth_w;
+                    if (eval_recs) eval_record(c.birth_cov, s.cinv, (size_t)capp, i);
                 }
             }
         }
@@ -1115,6 +1141,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
         mfield(out, p.cap, 1)[o] = om[0]; mfield(out, p.cap, 2)[o] = om[1]; mfield(out, p.cap, 3)[o] = om[2];
 #pragma unroll
         for (int i = 0; i < 9; i++) mfield(out, p.cap, 4 + i)[o] = oP[i];
+        if (p.mode == MODE_FRAME && !p.only_mapping) eval_record(oP, s.cinv2, (size_t)p.lay.cap_pred, o);
     }
     if (tid == 0) sm.ctx.nout = nout;
     __syncthreads();
@@ -1123,7 +1150,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
 
 // implemented in rbphd_weight.cuh (included below): WeightAlpha (PHD:373-393)
 __device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const double* predcov, int npriorcov,
-                               const double* corr, int ncorr, double* parts);
+                               const double* corr, int ncorr, double* parts, bool recs_ready);
 __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab& s, int J);
 
 }  // namespace rbphd
@@ -1252,7 +1279,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_particle_update(const __grid_cons
             if (tid == 0) p.counts[1 - cur][particle] = sm.ctx.nout;
             if (p.mode == MODE_FRAME && !p.only_mapping) {
                 double parts[8];
-                double alpha = phase_weight(p, sm, s, in, sm.ctx.N, out, sm.ctx.nout, parts);
+                double alpha = phase_weight(p, sm, s, in, sm.ctx.N, out, sm.ctx.nout, parts, true);
                 if (tid == 0) {
                     p.alphas[particle] = alpha;
                     p.weights[particle] *= alpha;
@@ -1265,7 +1292,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_particle_update(const __grid_cons
             // buffer cur = predicted map, buffer 1-cur = corrected (pruned) map of the same particle slot
             double parts[8];
             int nc = min(p.counts[1 - cur][particle], p.cap);
-            double alpha = phase_weight(p, sm, s, in, sm.ctx.N, out, nc, parts);
+            double alpha = phase_weight(p, sm, s, in, sm.ctx.N, out, nc, parts, false);
             if (tid == 0) {
                 p.alphas[particle] = alpha;
                 if (p.alpha_parts)

@@ -50,7 +50,7 @@ struct ScratchLayout {
     size_t tw, tm, tP, rho;
     size_t ecnt, edst, nstate, nowner, nflag, gitems;
     // weight stage
-    size_t jidx, jm, jmp, jpd, vsum, cinv, cnorm, crad, fat, clist, gx, llkey, llval, uf, bsum, bcnt, bmin, mslots;
+    size_t jidx, jm, jmp, jpd, vsum, cinv, cinv2, cnorm, crad, fat, clist, gx, llkey, llval, uf, bsum, bcnt, bmin, mslots;
     size_t bytes;
 };
 

@@ -7,9 +7,8 @@
 
 namespace rbphd {
 
-// Terms of Map.Evaluate with Mahalanobis distance^2 above this are < 2e-22 of the component's peak and
+// Terms of Map.Evaluate with Mahalanobis distance^2 above kEvalD2 are < 2e-22 of the component's peak and
 // are skipped (the reference sums them; the parity bar for weights is 1e-9 relative).
-constexpr double kEvalD2 = 100.0;
 constexpr double kQueryCell = 0.6;   // cell edge of the grid over the map-estimate points
 
 struct CompSrc {
@@ -49,7 +48,7 @@ __device__ inline double eval_term_full(const CompSrc& c, int i, double x, doubl
 // over the J points (sm.ctx.grid / sm.gstart() / s.gitems, built by the caller) and accumulates into
 // vs[t] with double atomics.  Returns sum_t ln v[t].
 __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, const CompSrc& c, int J,
-                                     double* vs)
+                                     double* vs, double* rec, bool rec_ready)
 {
     const int tid = threadIdx.x, capj = p.lay.cap_j;
     const double* jx = s.jm; const double* jy = s.jm + capj; const double* jz = s.jm + 2 * capj;
@@ -60,23 +59,15 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
     for (int t = tid; t < J; t += kBlock) vs[t] = 0.0;
     __syncthreads();
     PHASE_MARK(sm, 20);
-    // per-component records (struct of arrays in the slab, written coalesced by one dense pass): P^-1, the
-    // Gaussian multiplier and the squared cull radius kEvalD2 * bound, where bound >= lambda_max(P):
-    // ||P^2||_F^(1/2) = (sum lambda^4)^(1/4), within 32 % of lambda_max (the trace is up to 3x larger)
-    double* rec = s.cinv;
+    // per-component evaluation records (eval_record): in a frame they were written where the covariances were
+    // in registers (A2 / A5 for the predicted map, B6 for the corrected one); the stage entry point makes them here
     const size_t rs = (size_t)p.lay.cap_pred;
-    for (int i = tid; i < c.n; i += kBlock) {
-        double P[9], Pinv[9], P2[9];
-        comp_cov(c, i, P);
-        const double mult = gauss_mult(mat3_inv(P, Pinv));
-#pragma unroll
-        for (int a = 0; a < 9; a++) rec[(size_t)a * rs + i] = Pinv[a];
-        rec[9 * rs + i] = mult;
-        mat3_mul(P, P, P2);
-        double f = 0;
-#pragma unroll
-        for (int a = 0; a < 9; a++) f += P2[a] * P2[a];
-        rec[10 * rs + i] = kEvalD2 * sqrt(sqrt(f)) * (1.0 + 1e-6);
+    if (!rec_ready) {
+        for (int i = tid; i < c.n; i += kBlock) {
+            double P[9];
+            comp_cov(c, i, P);
+            eval_record(P, rec, rs, i);
+        }
     }
     __syncthreads();
     auto term_into = [&](int i, int t) {   // w_i N(jm_t; m_i, P_i) -> vs[t]
@@ -510,7 +501,7 @@ __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab
 }
 
 __device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const double* predmap, int npriorcov,
-                               const double* corr, int ncorr, double* parts)
+                               const double* corr, int ncorr, double* parts, bool recs_ready)
 {
     const int tid = threadIdx.x, capp = p.lay.cap_pred, capj = p.lay.cap_j;
     const int Npred = sm.ctx.Npred;
@@ -605,11 +596,11 @@ __device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const 
         __syncthreads();
     }
     PHASE_MARK(sm, 23);
-    const double plog = eval_map_at_points(p, sm, s, pred, J, vs);
+    const double plog = eval_map_at_points(p, sm, s, pred, J, vs, s.cinv, recs_ready);
     PHASE_MARK(sm, 12);
     CompSrc cor{mfield(corr, p.cap, 0), mfield(corr, p.cap, 1), mfield(corr, p.cap, 2), mfield(corr, p.cap, 3),
                 mfield(corr, p.cap, 4), (size_t)p.cap, ncorr, p.cfg.birth_cov, ncorr};
-    const double clog = eval_map_at_points(p, sm, s, cor, J, vs);
+    const double clog = eval_map_at_points(p, sm, s, cor, J, vs, s.cinv2, recs_ready);
     PHASE_MARK(sm, 13);
 
     const double setll = phase_set_loglikelihood(p, sm, s, J);
