@@ -314,7 +314,9 @@ __device__ __noinline__ void comp_update(const KParams& p, Smem& sm, const Slab&
         rec[23] = m[0]; rec[24] = m[1]; rec[25] = m[2];
         rec[26] = w;
     }
-    if (want_explore && i < N) {   // exploration term of a prior component (PHD:956-959): P^-1 and its multiplier
+    // exploration term of a prior component (PHD:956-959): P^-1 and its multiplier.  In a full frame they are
+    // already in the evaluation record A2 wrote (eval_pair reads them there by component index)
+    if (want_explore && i < N && !(p.mode == MODE_FRAME && !p.only_mapping)) {
         double Pinv[9];
         const double detp = mat3_inv(P, Pinv);
         rec[27] = gauss_mult(detp);
@@ -377,12 +379,22 @@ __device__ __forceinline__ void eval_pair(const KParams& p, Smem& sm, const Slab
         s.pmean[j] = m[0] + kd[0]; s.pmean[capq + j] = m[1] + kd[1]; s.pmean[2 * capq + j] = m[2] + kd[2];
     }
     if (explore && a < nact_prior && !sm.kflag()[k]) {   // exploration term of a prior component (one term >= threshold decides)
-        double Pinv[9];
+        double Pinv[9], gm;
+        if (p.mode == MODE_FRAME && !p.only_mapping) {
+            const size_t rs = (size_t)p.lay.cap_pred;
+            const double* er = s.cinv + s.cact[a];
 #pragma unroll
-        for (int f = 0; f < 9; f++) Pinv[f] = rec[28 + f];
+            for (int f = 0; f < 9; f++) Pinv[f] = er[(size_t)f * rs];
+            gm = er[9 * rs];
+        }
+        else {
+#pragma unroll
+            for (int f = 0; f < 9; f++) Pinv[f] = rec[28 + f];
+            gm = rec[27];
+        }
         const double* ck = &sm.cs()[3 * k];
         const double dc[3] = {ck[0] - m[0], ck[1] - m[1], ck[2] - m[2]};
-        const double e = rec[26] * (rec[27] * exp(-0.5 * quadform3(Pinv, dc)));
+        const double e = rec[26] * (gm * exp(-0.5 * quadform3(Pinv, dc)));
         if (e >= c.explore_thr) sm.kflag()[k] = 1;
     }
 }
