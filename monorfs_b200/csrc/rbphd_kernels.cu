@@ -731,41 +731,59 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
     block_scan_array(sm.sh, segstart, M + 1);
     for (int k = tid; k < M; k += kBlock) cursor[k] = segstart[k];
     __syncthreads();
-    for (int j = tid; j < np; j += kBlock) {
-        int pos = atomicAdd(&cursor[(int)(s.pkey[j] >> 32)], 1);
-        s.bidx[pos] = j;
-    }
-    __syncthreads();
-    // A9: per measurement: component order, weightsum, then the detection weights (PHD:886-902).
-    // The segments are sorted on a shared-memory copy (component index, pair slot).
-    unsigned int* scomp = reinterpret_cast<unsigned int*>(sm.skey());   // np <= 2 * kSortCap entries
-    unsigned int* sslot = sm.sval();
-    const bool in_smem = np <= (int)p.smem_sort_cap;
+    // (measurement, slot) packed into 32 bits for the in-segment comparison
+    const bool in_smem = np <= (int)p.smem_sort_cap && M <= 32767 && p.lay.cap_pred <= (1 << 17);
     if (in_smem) {
-        for (int t = tid; t < np; t += kBlock) {
-            const int j = s.bidx[t];
-            scomp[t] = (unsigned)(s.pkey[j] & 0xffffffffu);
-            sslot[t] = (unsigned)j;
+        // everything stays in shared memory: packed (measurement, component slot), pair slot and weight term
+        // are scattered to the measurement's segment; A9 then ranks each pair inside its segment (one thread
+        // per PAIR: balanced even when a few measurements gate dozens of components), sums the segment in
+        // component order (weightsum, PHD:886-902) and writes detection weights and output order coalesced.
+        unsigned int* scomp = reinterpret_cast<unsigned int*>(sm.skey());
+        unsigned int* sorted = reinterpret_cast<unsigned int*>(sm.skey()) + p.smem_sort_cap;   // upper half of the key buffer
+        unsigned int* sslot = sm.sval();
+        double* sptmp = sm.vs();      // np doubles: runs on through the (idle) histogram and cell-offset buffers
+        static_assert(sizeof(double) * kVsCap + sizeof(int) * 256 + sizeof(int) * kGridMaxCells >= sizeof(double) * kSortCap,
+                      "weight terms of kSortCap pairs must fit vs + hist + gstart");
+        double* wsum = sm.dens();     // M
+        for (int j = tid; j < np; j += kBlock) {
+            const unsigned long long key = s.pkey[j];
+            const int k = (int)(key >> 32);
+            const int pos = atomicAdd(&cursor[k], 1);
+            scomp[pos] = ((unsigned)k << 17) | (unsigned)(key & 0x1ffffu);
+            sslot[pos] = (unsigned)j;
+            sptmp[pos] = s.pt[j];
         }
         __syncthreads();
-    }
-    if (in_smem) {
-        // rank sort inside each segment, one thread per PAIR (balanced even when a few measurements gate
-        // dozens of components): rank = number of pairs of the same measurement with a smaller component
-        unsigned int* sorted = reinterpret_cast<unsigned int*>(sm.skey()) + p.smem_sort_cap;   // upper half of the key buffer
         for (int t = tid; t < np; t += kBlock) {
             const unsigned myc = scomp[t];
-            const int k = (int)(s.pkey[sslot[t]] >> 32);
+            const int k = (int)(myc >> 17);
             const int b = segstart[k], e = segstart[k + 1];
             int rank = 0;
             for (int q = b; q < e; q++) rank += (scomp[q] < myc) ? 1 : 0;
-            sorted[b + rank] = sslot[t];
+            sorted[b + rank] = (unsigned)t;
         }
         __syncthreads();
-        for (int t = tid; t < np; t += kBlock) sslot[t] = sorted[t];
+        for (int k = tid; k < M; k += kBlock) {
+            const int b = segstart[k], e = segstart[k + 1];
+            double ws = 0;
+            for (int q = b; q < e; q++) ws += sptmp[sorted[q]];
+            wsum[k] = ws;
+        }
         __syncthreads();
+        for (int t = tid; t < np; t += kBlock) {
+            const unsigned src = sorted[t];
+            double wv = sptmp[src] / (c.clutter + wsum[scomp[src] >> 17]);
+            if (wv != wv) wv = 0;   // GAUSS:154
+            s.pwgt[t] = wv;
+            s.bidx[t] = (int)sslot[src];
+        }
     }
     else {
+        for (int j = tid; j < np; j += kBlock) {
+            int pos = atomicAdd(&cursor[(int)(s.pkey[j] >> 32)], 1);
+            s.bidx[pos] = j;
+        }
+        __syncthreads();
         for (int k = tid; k < M; k += kBlock) {
             const int b = segstart[k], e = segstart[k + 1];
             for (int a = b + 1; a < e; a++) {
@@ -775,29 +793,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
                 while (q >= b && (unsigned)(s.pkey[s.bidx[q]] & 0xffffffffu) > vi) { s.bidx[q + 1] = s.bidx[q]; q--; }
                 s.bidx[q + 1] = v;
             }
-        }
-        __syncthreads();
-    }
-    // weight terms gathered once, in sorted order, into shared memory (the component keys are dead now)
-    double* spt = reinterpret_cast<double*>(sm.skey());
-    if (in_smem) {
-        for (int t = tid; t < np; t += kBlock) { const int j = (int)sslot[t]; s.bidx[t] = j; }
-        __syncthreads();
-        for (int t = tid; t < np; t += kBlock) spt[t] = s.pt[sslot[t]];
-        __syncthreads();
-    }
-    for (int k = tid; k < M; k += kBlock) {
-        const int b = segstart[k], e = segstart[k + 1];
-        double ws = 0;
-        if (in_smem) {
-            for (int t = b; t < e; t++) ws += spt[t];
-            for (int t = b; t < e; t++) {
-                double wv = spt[t] / (c.clutter + ws);
-                if (wv != wv) wv = 0;   // GAUSS:154
-                s.pwgt[t] = wv;
-            }
-        }
-        else {
+            double ws = 0;
             for (int t = b; t < e; t++) ws += s.pt[s.bidx[t]];
             for (int t = b; t < e; t++) {
                 double wv = s.pt[s.bidx[t]] / (c.clutter + ws);
