@@ -277,14 +277,17 @@ __device__ inline int block_radix_sort(BlockShared& sh, unsigned long long* k0, 
 // (kout,vout) are in global memory, kWarps * 1.5 * kBucketWarpMax 64-bit words of shared memory.
 constexpr int kSortBuckets = 4096;
 constexpr int kBucketThreadMax = 6;
+constexpr int kBucketLocalMax = 24;   // thread-sorted through local memory when the output is in global memory
 constexpr int kBucketWarpMax = 128;
-constexpr int kBigBuckets = 4000;
+constexpr int kBigBuckets = kSortBuckets + 64;   // every bucket can be listed (medium ones in front, long ones at the back)
+constexpr int kLongBuckets = 64;    // share of the list kept for buckets longer than kBucketWarpMax
 
 __device__ inline bool block_bucket_sort(BlockShared& sh, const unsigned long long* kin, const unsigned int* vin,
                                          unsigned long long* kout, unsigned int* vout, int n, int* hist, int* biglist,
                                          unsigned long long* tmpk, unsigned int* tmpv,
                                          unsigned long long* wscratch = nullptr)
 {
+
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long lo = ~0ull, hi = 0ull;
     for (int e = threadIdx.x; e < n; e += kBlock) { const unsigned long long k = kin[e]; lo = min(lo, k); hi = max(hi, k); }
@@ -306,9 +309,15 @@ __device__ inline bool block_bucket_sort(BlockShared& sh, const unsigned long lo
     const int shift = max(0, (64 - __clzll((long long)range)) - 12);   // (key - lo) >> shift < 4096
     for (int e = threadIdx.x; e < n; e += kBlock) atomicAdd(&hist[(int)((kin[e] - lo) >> shift)], 1);
     __syncthreads();
-    int longest = 0;
-    for (int b = threadIdx.x; b < kSortBuckets; b += kBlock) longest = max(longest, hist[b]);
+    int longest = 0, nlong_mine = 0;
+    for (int b = threadIdx.x; b < kSortBuckets; b += kBlock) {
+        longest = max(longest, hist[b]);
+        nlong_mine += (hist[b] > kBucketWarpMax) ? 1 : 0;
+    }
     if (__syncthreads_or((long long)longest * longest > 600ll * n && longest > kBucketWarpMax)) return false;
+    if (__syncthreads_count(nlong_mine > 0) > kLongBuckets / 4) {   // (an upper bound is enough: <= 4 buckets per thread)
+        if (block_sum_int(sh, nlong_mine) > kLongBuckets) return false;
+    }
     block_scan_array(sh, hist, kSortBuckets + 1);   // hist[b] = start of bucket b; used as the scatter cursor
     for (int e = threadIdx.x; e < n; e += kBlock) {
         const unsigned long long k = kin[e];
@@ -322,15 +331,31 @@ __device__ inline bool block_bucket_sort(BlockShared& sh, const unsigned long lo
         const int beg = (b == 0) ? 0 : hist[b - 1], end = hist[b];
         const int len = end - beg;
         if (len <= 1) continue;
+        if (wscratch && len <= kBucketLocalMax) {
+            // (kout,vout) in global memory: one round trip to fetch the bucket, sort it in local memory, one to store
+            unsigned long long lk[kBucketLocalMax];
+            unsigned int lv[kBucketLocalMax];
+            for (int a = 0; a < len; a++) { lk[a] = kout[beg + a]; lv[a] = vout[beg + a]; }
+            for (int a = 1; a < len; a++) {
+                const unsigned long long k = lk[a];
+                const unsigned int v = lv[a];
+                int q = a - 1;
+                while (q >= 0 && (lk[q] > k || (lk[q] == k && lv[q] > v))) { lk[q + 1] = lk[q]; lv[q + 1] = lv[q]; q--; }
+                lk[q + 1] = k;
+                lv[q + 1] = v;
+            }
+            for (int a = 0; a < len; a++) { kout[beg + a] = lk[a]; vout[beg + a] = lv[a]; }
+            continue;
+        }
         if (len > kBucketThreadMax) {
-            // medium buckets are listed from the front, long ones from the back of the same list
+            // medium buckets are listed from the front, long ones from the back (fixed share) of the same list
             if (len <= kBucketWarpMax) {
                 const int slot = atomicAdd(&biglist[kBigBuckets], 1);
-                if (slot + biglist[kBigBuckets + 1] < kBigBuckets) { biglist[slot] = b; continue; }
+                if (slot < kBigBuckets - kLongBuckets) { biglist[slot] = b; continue; }
             }
             else {
                 const int slot = atomicAdd(&biglist[kBigBuckets + 1], 1);
-                if (slot + biglist[kBigBuckets] < kBigBuckets) { biglist[kBigBuckets - 1 - slot] = b; continue; }
+                if (slot < kLongBuckets) { biglist[kBigBuckets - 1 - slot] = b; continue; }
             }
         }
         for (int a = beg + 1; a < end; a++) {   // (also the overflow of the list: slow, still correct)
@@ -343,8 +368,8 @@ __device__ inline bool block_bucket_sort(BlockShared& sh, const unsigned long lo
         }
     }
     __syncthreads();
-    const int nlong = min(biglist[kBigBuckets + 1], kBigBuckets);
-    const int nmed = min(biglist[kBigBuckets], kBigBuckets - nlong);
+    const int nlong = min(biglist[kBigBuckets + 1], kLongBuckets);
+    const int nmed = min(biglist[kBigBuckets], kBigBuckets - kLongBuckets);
     for (int t = warp; t < nmed; t += kWarps) {
         const int b = biglist[t];
         const int beg = (b == 0) ? 0 : hist[b - 1], end = hist[b];
@@ -387,22 +412,37 @@ __device__ inline bool block_bucket_sort(BlockShared& sh, const unsigned long lo
             if (beg + lane + 32 * r < end) { kout[beg + rank[r]] = k[r]; vout[beg + rank[r]] = v[r]; }
         __syncwarp();
     }
+    if (nlong > 0) __syncthreads();   // the long-bucket staging reuses the warps' scratch
     for (int t = 0; t < nlong; t++) {   // the whole CTA on one long bucket
         const int b = biglist[kBigBuckets - 1 - t];
         const int beg = (b == 0) ? 0 : hist[b - 1], end = hist[b];
-        for (int a = beg + threadIdx.x; a < end; a += kBlock) {
-            const unsigned long long k = kout[a];
-            const unsigned int v = vout[a];
+        const int len = end - beg;
+        // rank against a shared-memory copy when (kout,vout) are in global memory (the scratch then spans the
+        // idle shared sort buffer: kWarps * 1.5 * kBucketWarpMax words >= 1.5 * len is checked)
+        const bool staged = wscratch && (size_t)len * 3 <= (size_t)kWarps * 3 * kBucketWarpMax;
+        const unsigned long long* rk = kout + beg;
+        const unsigned int* rv = vout + beg;
+        if (staged) {
+            unsigned long long* wk = wscratch;
+            unsigned int* wv = reinterpret_cast<unsigned int*>(wscratch + len);
+            for (int a = threadIdx.x; a < len; a += kBlock) { wk[a] = kout[beg + a]; wv[a] = vout[beg + a]; }
+            __syncthreads();
+            rk = wk; rv = wv;
+        }
+        for (int a = threadIdx.x; a < len; a += kBlock) {
+            const unsigned long long k = rk[a];
+            const unsigned int v = rv[a];
             int rank = 0;
-            for (int q = beg; q < end; q++) {
-                const unsigned long long kq = kout[q];
-                rank += (kq < k || (kq == k && vout[q] < v)) ? 1 : 0;
+            for (int q = 0; q < len; q++) {
+                const unsigned long long kq = rk[q];
+                rank += (kq < k || (kq == k && rv[q] < v)) ? 1 : 0;
             }
             tmpk[beg + rank] = k;
             tmpv[beg + rank] = v;
         }
         __syncthreads();
         for (int a = beg + threadIdx.x; a < end; a += kBlock) { kout[a] = tmpk[a]; vout[a] = tmpv[a]; }
+        __syncthreads();
     }
     __syncthreads();
     return true;

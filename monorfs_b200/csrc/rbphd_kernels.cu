@@ -82,7 +82,8 @@ struct Smem {
 };
 
 static_assert(sizeof(double) * kVsCap >= sizeof(int) * kWarps * 256, "the radix-sort histograms alias the vs buffer");
-static_assert(sizeof(double) * kVsCap >= sizeof(int) * (kSortBuckets + 1 + kBigBuckets + 2), "the bucket-sort histogram and long-bucket list alias the vs buffer");
+static_assert(sizeof(double) * kVsCap + sizeof(int) * 256 >= sizeof(int) * (kSortBuckets + 1 + kBigBuckets + 2),
+              "the bucket-sort histogram and bucket list alias the vs buffer and the 256-int histogram behind it");
 
 struct Slab {
     // predicted map = prior components followed by births
