@@ -202,22 +202,21 @@ void make_layout(ScratchLayout& l, int cap, int Mcap, int cap_pairs, int maxq)
     take(l.bidx, I * (cap_pairs + 2));
     take(l.pkey, U * cap_pairs);     take(l.pt, D * cap_pairs);    take(l.pmean, 3 * D * cap_pairs);
     take(l.pwgt, D * cap_pairs);
-    take(l.crec, 37 * D * l.cap_pred); take(l.cpn, 9 * D * l.cap_pred);
+    take(l.crec, kRecFields * D * l.cap_pred); take(l.cpn, 9 * D * l.cap_pred);
     take(l.hits4, U * l.cap_pred);
     take(l.skey, U * l.cap_sort);    take(l.sval, sizeof(unsigned) * l.cap_sort);
     take(l.skey2, U * l.cap_sort);   take(l.sval2, sizeof(unsigned) * l.cap_sort);
     take(l.tw, D * l.cap_top);       take(l.tm, 3 * D * l.cap_top); take(l.tP, 9 * D * l.cap_top);
     take(l.rho, D * l.cap_top);
-    take(l.ecnt, I * (l.cap_top + 2)); take(l.edst, I * l.cap_edges);
+    take(l.edst, I * l.cap_edges);
     take(l.nstate, I * l.cap_nodes); take(l.nowner, I * l.cap_nodes); take(l.nflag, I * l.cap_nodes);
     take(l.gitems, I * l.cap_nodes);
     take(l.jidx, I * l.cap_j);       take(l.jm, 3 * D * l.cap_j);  take(l.jmp, 3 * D * l.cap_j);
     take(l.jpd, D * l.cap_j);        take(l.vsum, D * l.cap_j);
-    take(l.cinv, 11 * D * l.cap_pred); take(l.cinv2, 11 * D * l.cap_pred); take(l.cnorm, D * l.cap_pred); take(l.crad, D * l.cap_pred);   // exploration bound per component
-    take(l.fat, 16);  take(l.clist, 16); take(l.gx, 16);
+    take(l.cinv, kEvalRecFields * D * l.cap_pred); take(l.cinv2, kEvalRecFields * D * l.cap_pred); take(l.cnorm, D * l.cap_pred); take(l.crad, D * l.cap_pred);   // exploration bound per component
     take(l.llkey, U * l.cap_ll);     take(l.llval, D * l.cap_ll);
     take(l.uf, I * (l.cap_j + Mcap + 2)); take(l.bcnt, I * (l.cap_j + Mcap + 2));
-    take(l.bsum, 16); take(l.bmin, 16); take(l.mslots, murty_workspace_bytes());
+    take(l.mslots, murty_workspace_bytes());
     l.bytes = align_up(off, 256);
 }
 

@@ -92,20 +92,17 @@ struct Slab {
     unsigned long long* pkey;
     double *pt, *pmean, *pwgt;
     unsigned long long* hits4;   // per predicted component: up to four gated measurements packed by the counting walk
-    double *crec, *cpn;    // per gated component: measurement-space record (kRec doubles) and updated covariance (9)
+    double *crec, *cpn;    // per gated component: measurement-space record (kRecFields doubles) and updated covariance (9)
     unsigned long long *skey, *skey2;
     unsigned int *sval, *sval2;
     double *tw, *tm, *tP, *rho;
-    int *ecnt, *edst, *nstate, *nowner, *nflag, *gitems;
+    int *edst, *nstate, *nowner, *nflag, *gitems;
     int *jidx;
     double *jm, *jmp, *jpd, *vsum, *cinv, *cinv2, *cnorm, *crad;
-    int *fat, *clist;
-    double* gx;
     unsigned long long* llkey;
     double* llval;
     int *uf;
-    double* bsum;
-    int *bcnt, *bmin;
+    int* bcnt;
     unsigned char* mslots;
 };
 
@@ -123,16 +120,15 @@ __device__ __forceinline__ Slab make_slab(unsigned char* base, const ScratchLayo
     s.skey2 = (unsigned long long*)(base + l.skey2); s.sval2 = (unsigned int*)(base + l.sval2);
     s.tw = (double*)(base + l.tw); s.tm = (double*)(base + l.tm); s.tP = (double*)(base + l.tP);
     s.rho = (double*)(base + l.rho);
-    s.ecnt = (int*)(base + l.ecnt); s.edst = (int*)(base + l.edst); s.nstate = (int*)(base + l.nstate);
+    s.edst = (int*)(base + l.edst); s.nstate = (int*)(base + l.nstate);
     s.nowner = (int*)(base + l.nowner); s.nflag = (int*)(base + l.nflag); s.gitems = (int*)(base + l.gitems);
     s.jidx = (int*)(base + l.jidx); s.jm = (double*)(base + l.jm); s.jmp = (double*)(base + l.jmp);
     s.jpd = (double*)(base + l.jpd); s.vsum = (double*)(base + l.vsum); s.cinv = (double*)(base + l.cinv);
     s.cinv2 = (double*)(base + l.cinv2);
-    s.cnorm = (double*)(base + l.cnorm); s.crad = (double*)(base + l.crad); s.fat = (int*)(base + l.fat);
-    s.clist = (int*)(base + l.clist); s.gx = (double*)(base + l.gx);
+    s.cnorm = (double*)(base + l.cnorm); s.crad = (double*)(base + l.crad);
     s.llkey = (unsigned long long*)(base + l.llkey); s.llval = (double*)(base + l.llval);
-    s.uf = (int*)(base + l.uf); s.bsum = (double*)(base + l.bsum); s.bcnt = (int*)(base + l.bcnt);
-    s.bmin = (int*)(base + l.bmin); s.mslots = base + l.mslots;
+    s.uf = (int*)(base + l.uf); s.bcnt = (int*)(base + l.bcnt);
+    s.mslots = base + l.mslots;
     return s;
 }
 
@@ -265,9 +261,8 @@ __device__ __forceinline__ unsigned long long hits_close(unsigned long long pack
 // measurement, S^-1 and the Gaussian multiplier, Kalman gain K, updated covariance (I - K H) P.  The
 // reference recomputes these for every (measurement, component) pair; they are the same numbers each
 // time, so they are computed once per gated component and kept in a record the pairs read.
-// record (kRec fields, struct of arrays over the gated components in index order): 0-2 h(m)  3 mult  4-12 S^-1  13-21 K  22 pd*w  23-25 m  26 w  27 mult_P  28-36 P^-1
+// record (kRecFields fields, struct of arrays over the gated components in index order): 0-2 h(m)  3 mult  4-12 S^-1  13-21 K  22 pd*w  23-25 m  26 w  27 mult_P  28-36 P^-1
 // ------------------------------------------------------------------------------------------------
-constexpr int kRec = 37;
 // field f of slot a of a struct-of-arrays record block (consecutive slots are consecutive in memory, so the
 // dense per-slot passes read and write it coalesced)
 template <class T>
@@ -405,7 +400,6 @@ __device__ __forceinline__ void eval_pair(const KParams& p, Smem& sm, const Slab
 // ||P^2||_F^(1/2) = (sum lambda^4)^(1/4), within 32 % of lambda_max (the trace is up to 3x larger).
 // Struct of arrays with stride rs; written where the covariance is in registers anyway (A2, A5, B6).
 constexpr double kEvalD2 = 100.0;   // terms of Map.Evaluate beyond this Mahalanobis distance^2 are < 2e-22 of the peak
-constexpr int kEvalRec = 11;
 __device__ __forceinline__ double eval_record(const double* P, double* rec, size_t rs, int i)
 {
     double Pinv[9], P2[9];
@@ -824,41 +818,10 @@ __device__ __forceinline__ void load_corrected(const KParams& p, const Smem& sm,
         const int t = e - Npred, j = s.bidx[t], capq = p.lay.cap_pairs;
         w = s.pwgt[t];
         m[0] = s.pmean[j]; m[1] = s.pmean[capq + j]; m[2] = s.pmean[2 * capq + j];
-#pragma unroll
         const size_t ca = (size_t)(s.pkey[j] & 0xffffffffu);   // the updated covariance belongs to the component
 #pragma unroll
         for (int f = 0; f < 9; f++) P[f] = s.cpn[(size_t)f * p.lay.cap_pred + ca];
     }
-}
-
-// visit the ranks r' != r whose mean lies within radius rho of (x,y,z); f(r') is called for each
-template <class F>
-__device__ __forceinline__ void for_neighbours(const Smem& sm, const Slab& s, int npts, const double* px,
-                                               const double* py, const double* pz, double x, double y, double z,
-                                               double rho, F f)
-{
-    const CellGrid& g = sm.ctx.grid;
-    int lo[3], hi[3];
-    bool brute = !(rho == rho) || isinf(rho);
-    if (!brute) {
-        if (!grid_range(g, x, y, z, rho, lo, hi)) return;
-        long cells = (long)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
-        if (cells > 128) brute = true;
-    }
-    if (brute) {
-        for (int r = 0; r < npts; r++) f(r);
-        return;
-    }
-    for (int cz = lo[2]; cz <= hi[2]; cz++)
-        for (int cy = lo[1]; cy <= hi[1]; cy++) {
-            int rowc = (cz * g.dim[1] + cy) * g.dim[0];
-            int b = sm.gstart()[rowc + lo[0]], e = sm.gstart()[rowc + hi[0] + 1];
-            for (int t = b; t < e; t++) {
-                int r = s.gitems[t];
-                double dx = px[r] - x, dy = py[r] - y, dz = pz[r] - z;
-                if (fabs(dx) <= rho && fabs(dy) <= rho && fabs(dz) <= rho) f(r);
-            }
-        }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -915,8 +878,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
         __syncthreads();
     }
     const int nc = sm.ctx.ncand;
-    unsigned long long* skey = s.skey;
-    unsigned int* sval = s.sval;
+    unsigned int* sval = s.sval;   // list positions in sorted order (wherever the sort leaves them)
     {
         const bool in_smem = nc <= (int)p.smem_sort_cap;
         unsigned long long* k1 = in_smem ? sm.skey() : s.skey2;
@@ -925,10 +887,10 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
         // degenerate key sets (thousands of equal weights)
         if (block_bucket_sort(sm.sh, s.skey, s.sval, k1, v1, nc, reinterpret_cast<int*>(sm.vs()),
                               reinterpret_cast<int*>(sm.vs()) + kSortBuckets + 1, s.skey, s.sval, in_smem ? nullptr : sm.skey())) {
-            skey = k1; sval = v1;
+            sval = v1;
         }
         else if (block_radix_sort(sm.sh, s.skey, s.sval, k1, v1, nc, reinterpret_cast<int*>(sm.vs()), sm.hist())) {
-            skey = k1; sval = v1;
+            sval = v1;
         }
     }
     PHASE_MARK(sm, 6);
@@ -1458,7 +1420,7 @@ __global__ void __launch_bounds__(kBlock) k_normalize_resample(DevCfg cfg, int P
     }
     // systematic wheel (PHD:724-760), serial
     __shared__ double s_random, s_maxweight;
-    __shared__ int s_k, s_i, s_newbest, s_tilebase;
+    __shared__ int s_k, s_i, s_newbest;
     if (tid == 0) { s_random = u / P; s_maxweight = 0; s_k = 0; s_i = 0; s_newbest = s_best; }
     __syncthreads();
     // walk the weight tiles; for each tile thread 0 advances the wheel as far as the tile allows
@@ -1489,7 +1451,6 @@ __global__ void __launch_bounds__(kBlock) k_normalize_resample(DevCfg cfg, int P
     __syncthreads();
     for (int i = tid; i < P; i += kBlock) weights[i] = 1.0 / P;
     if (tid == 0) { st->best = s_newbest; st->resampled = 1; st->depleted = 1; }
-    (void)s_tilebase;
 }
 
 // ------------------------------------------------------------------------------------------------
