@@ -305,9 +305,38 @@ __device__ inline bool block_bucket_sort(BlockShared& sh, const unsigned long lo
         lo = min(lo, (unsigned long long)__double_as_longlong(sh.warp_d[w]));
         hi = max(hi, (unsigned long long)__double_as_longlong(sh.warp_d[kWarps + w]));
     }
+    // Bucket boundaries follow the key distribution: a coarse histogram over 256 equal slices of the key range
+    // first, then every slice gets fine buckets in proportion to its count (weights are roughly uniform in
+    // value, so equal slices of the bit pattern would put most keys of a large map into one binade's buckets)
     const unsigned long long range = hi - lo;
-    const int shift = max(0, (64 - __clzll((long long)range)) - 12);   // (key - lo) >> shift < 4096
-    for (int e = threadIdx.x; e < n; e += kBlock) atomicAdd(&hist[(int)((kin[e] - lo) >> shift)], 1);
+    const int shift0 = max(0, (64 - __clzll((long long)range)) - 8);   // (key - lo) >> shift0 < 256
+    const int sh2 = max(0, shift0 - 20);                               // offset inside a slice, top 20 bits
+    int* coarse = biglist;          // 256 counts           (the list itself is not in use yet)
+    int* nbk = biglist + 256;       // 256 fine buckets per slice
+    int* cbase = biglist + 512;     // 256 first fine bucket of a slice
+    if (threadIdx.x < 256) coarse[threadIdx.x] = 0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < n; e += kBlock) atomicAdd(&coarse[(int)((kin[e] - lo) >> shift0)], 1);
+    __syncthreads();
+    {
+        int mine = 0;
+        if (threadIdx.x < 256) {
+            mine = (int)(((long long)coarse[threadIdx.x] * (kSortBuckets - 512) + n / 2) / max(n, 1));
+            mine = max(mine, 1);
+            nbk[threadIdx.x] = mine;
+        }
+        int tot;
+        const int ex = block_excl_scan(sh, mine, &tot);   // tot <= kSortBuckets - 512 + 128 + 256
+        if (threadIdx.x < 256) cbase[threadIdx.x] = ex;
+        __syncthreads();
+    }
+    auto bucket_of = [&](unsigned long long k) {
+        const unsigned long long x = k - lo;
+        const int cb = (int)(x >> shift0);
+        const unsigned long long off = x - ((unsigned long long)cb << shift0);
+        return cbase[cb] + (int)(((off >> sh2) * (unsigned long long)nbk[cb]) >> (shift0 - sh2));
+    };
+    for (int e = threadIdx.x; e < n; e += kBlock) atomicAdd(&hist[bucket_of(kin[e])], 1);
     __syncthreads();
     int longest = 0, nlong_mine = 0;
     for (int b = threadIdx.x; b < kSortBuckets; b += kBlock) {
@@ -321,7 +350,7 @@ __device__ inline bool block_bucket_sort(BlockShared& sh, const unsigned long lo
     block_scan_array(sh, hist, kSortBuckets + 1);   // hist[b] = start of bucket b; used as the scatter cursor
     for (int e = threadIdx.x; e < n; e += kBlock) {
         const unsigned long long k = kin[e];
-        const int pos = atomicAdd(&hist[(int)((k - lo) >> shift)], 1);
+        const int pos = atomicAdd(&hist[bucket_of(k)], 1);
         kout[pos] = k;
         vout[pos] = vin[e];
     }
