@@ -277,7 +277,6 @@ __device__ inline int block_radix_sort(BlockShared& sh, unsigned long long* k0, 
 // (kout,vout) are in global memory, kWarps * 1.5 * kBucketWarpMax 64-bit words of shared memory.
 constexpr int kSortBuckets = 4096;
 constexpr int kBucketThreadMax = 6;
-constexpr int kBucketLocalMax = 24;   // thread-sorted through local memory when the output is in global memory
 constexpr int kBucketWarpMax = 128;
 constexpr int kBigBuckets = kSortBuckets + 64;   // every bucket can be listed (medium ones in front, long ones at the back)
 constexpr int kLongBuckets = 64;    // share of the list kept for buckets longer than kBucketWarpMax
@@ -360,22 +359,6 @@ __device__ inline bool block_bucket_sort(BlockShared& sh, const unsigned long lo
         const int beg = (b == 0) ? 0 : hist[b - 1], end = hist[b];
         const int len = end - beg;
         if (len <= 1) continue;
-        if (wscratch && len <= kBucketLocalMax) {
-            // (kout,vout) in global memory: one round trip to fetch the bucket, sort it in local memory, one to store
-            unsigned long long lk[kBucketLocalMax];
-            unsigned int lv[kBucketLocalMax];
-            for (int a = 0; a < len; a++) { lk[a] = kout[beg + a]; lv[a] = vout[beg + a]; }
-            for (int a = 1; a < len; a++) {
-                const unsigned long long k = lk[a];
-                const unsigned int v = lv[a];
-                int q = a - 1;
-                while (q >= 0 && (lk[q] > k || (lk[q] == k && lv[q] > v))) { lk[q + 1] = lk[q]; lv[q + 1] = lv[q]; q--; }
-                lk[q + 1] = k;
-                lv[q + 1] = v;
-            }
-            for (int a = 0; a < len; a++) { kout[beg + a] = lk[a]; vout[beg + a] = lv[a]; }
-            continue;
-        }
         if (len > kBucketThreadMax) {
             // medium buckets are listed from the front, long ones from the back (fixed share) of the same list
             if (len <= kBucketWarpMax) {
