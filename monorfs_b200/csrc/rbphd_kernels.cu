@@ -359,20 +359,28 @@ __device__ __forceinline__ void eval_pair(const KParams& p, Smem& sm, const Slab
     const RecRef<const double> rec{s.crec + a, (size_t)p.lay.cap_pred};
     const double* zk = &sm.zs()[3 * k];
     const double innov[3] = {zk[0] - rec[0], zk[1] - rec[1], zk[2] - rec[2]};
+    // row by row (same operation order as mat3_vec / quadform3), so that only one row of S^-1 or K is live
     {
-        double Sinv[9];
+        double quad = 0;
 #pragma unroll
-        for (int f = 0; f < 9; f++) Sinv[f] = rec[4 + f];
-        const double q = rec[3] * exp(-0.5 * quadform3(Sinv, innov));
+        for (int r = 0; r < 3; r++) {
+            double t = 0;
+            t += rec[4 + 3 * r + 0] * innov[0];
+            t += rec[4 + 3 * r + 1] * innov[1];
+            t += rec[4 + 3 * r + 2] * innov[2];
+            quad += innov[r] * t;
+        }
+        const double q = rec[3] * exp(-0.5 * quad);
         s.pt[j] = rec[22] * q;
     }
     const double m[3] = {rec[23], rec[24], rec[25]};
-    {
-        double K[9], kd[3];
 #pragma unroll
-        for (int f = 0; f < 9; f++) K[f] = rec[13 + f];
-        mat3_vec(K, innov, kd);
-        s.pmean[j] = m[0] + kd[0]; s.pmean[capq + j] = m[1] + kd[1]; s.pmean[2 * capq + j] = m[2] + kd[2];
+    for (int r = 0; r < 3; r++) {
+        double kd = 0;
+        kd += rec[13 + 3 * r + 0] * innov[0];
+        kd += rec[13 + 3 * r + 1] * innov[1];
+        kd += rec[13 + 3 * r + 2] * innov[2];
+        s.pmean[(size_t)r * capq + j] = m[r] + kd;
     }
     if (explore && a < nact_prior && !sm.kflag()[k]) {   // exploration term of a prior component (one term >= threshold decides)
         double Pinv[9], gm;
