@@ -71,12 +71,19 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
     }
     __syncthreads();
     auto term_into = [&](int i, int t) {   // w_i N(jm_t; m_i, P_i) -> vs[t]
-        double Pinv[9];
-#pragma unroll
-        for (int a = 0; a < 9; a++) Pinv[a] = rec[(size_t)a * rs + i];
-        const double mult = rec[9 * rs + i];
         const double d[3] = {jx[t] - c.mx[i], jy[t] - c.my[i], jz[t] - c.mz[i]};   // x - Mean (GAUSS:201)
-        atomicAdd(&vs[t], c.w[i] * (mult * exp(-0.5 * quadform3(Pinv, d))));
+        // quadform3 row by row (same operation order), one row of P^-1 live at a time
+        double quad = 0;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            double u = 0;
+            u += rec[(size_t)(3 * r + 0) * rs + i] * d[0];
+            u += rec[(size_t)(3 * r + 1) * rs + i] * d[1];
+            u += rec[(size_t)(3 * r + 2) * rs + i] * d[2];
+            quad += d[r] * u;
+        }
+        const double mult = rec[9 * rs + i];
+        atomicAdd(&vs[t], c.w[i] * (mult * exp(-0.5 * quad)));
     };
     const int fatcap = p.M;
     if (tid == 0) sm.ctx.nU = 0;
