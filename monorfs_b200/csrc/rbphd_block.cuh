@@ -597,37 +597,40 @@ __device__ inline void grid_build(BlockShared& sh, CellGrid& g, int* start, int*
             if (!(mc[a] > 0)) mc[a] = 1.0;
         }
         // start from the closed-form factor (volume / maxcells, longest axis / kGridMaxDim); the loop only
-        // corrects for axes thinner than one cell (this section is serial: keep the divisions few)
+        // corrects for axes thinner than one cell.  This section runs on one thread: FP64 divisions are the
+        // cost, so the per-axis ratios are formed once and scaled by 1 / f.
+        double da[3];
         double f = 1.0;
         {
             double vol = 1.0;
             for (int a = 0; a < 3; a++) {
-                const double da = ext[a] / mc[a];
-                f = fmax(f, da / (double)kGridMaxDim);
-                vol *= fmax(da, 1.0);
+                da[a] = ext[a] / mc[a];
+                f = fmax(f, da[a] * (1.0 / (double)kGridMaxDim));
+                vol *= fmax(da[a], 1.0);
             }
             f = fmax(f, cbrt(vol / (double)maxcells));
             if (!(f >= 1.0) || isinf(f)) f = 1.0;
         }
+        int dsel[3] = {1, 1, 1};
         for (int it = 0; it < 200; it++) {
+            const double inv_f = 1.0 / f;
             long cells = 1;
             bool ok = true;
             for (int a = 0; a < 3; a++) {
-                double dd = floor(ext[a] / (mc[a] * f));   // cell edge >= mincell * f
+                double dd = floor(da[a] * inv_f);   // cell edge >= mincell * f
                 if (!(dd >= 1.0)) dd = 1.0;
                 if (dd > (double)kGridMaxDim) { ok = false; dd = (double)kGridMaxDim; }
+                dsel[a] = (int)dd;
                 cells *= (long)dd;
             }
             if (ok && cells <= maxcells) break;
             f *= 1.2;
         }
         for (int a = 0; a < 3; a++) {
-            double dd = floor(ext[a] / (mc[a] * f));   // cell edge >= mincell * f
-            int d = (dd >= (double)kGridMaxDim) ? kGridMaxDim : ((dd >= 1.0) ? (int)dd : 1);
-            double cs = ext[a] / d;
-            if (!(cs > 0)) cs = 1.0;
-            cs = cs * (1.0 + 1e-12) + 1e-300;
-            g.dim[a] = d; g.inv[a] = 1.0 / cs;
+            const int d = dsel[a];
+            // (x - org) * inv < d for every x <= hi
+            g.dim[a] = d;
+            g.inv[a] = (ext[a] > 0) ? (double)d / (ext[a] * (1.0 + 1e-12) + 1e-300) : 1.0;
         }
         if ((long)g.dim[0] * g.dim[1] * g.dim[2] > maxcells) { g.dim[0] = g.dim[1] = g.dim[2] = (maxcells >= 4096) ? 16 : 4; 
             for (int a = 0; a < 3; a++) { double cs = ext[a] / g.dim[a]; if (!(cs > 0)) cs = 1.0; g.inv[a] = 1.0 / (cs * (1.0 + 1e-12) + 1e-300); } }
