@@ -139,3 +139,32 @@ def test_async_frames_match_synchronous_calls(env):
     assert a.kernel_launches >= 5 * 5
     a.close()
     b.close()
+
+
+def test_run_to_run_determinism(env):
+    """Two runs on the same inputs: maps, counts, poses, ancestors and decisions are bit-identical (lists built with
+    atomics are sorted before use); particle weights agree to 1e-12 (the Map.Evaluate sums use FP64 atomics)."""
+    capi, synth = env
+
+    def run():
+        sc = synth.make_scene(48, 150, 48, seed=41, min_effective_particle=0.5)
+        h = capi.Handle(sc.params, max_particles=48, max_components=300, max_measurements=48, max_pairs=16 * 48)
+        h.reset(48, sc.poses[0], sc.map_w, sc.map_m, sc.map_P)
+        h.set_poses(sc.poses)
+        out = []
+        for _ in range(6):
+            fr = sc.next_frame()
+            h.update(fr.reading, synth.DT, fr.gauss)
+            out.append(h.slam_update(fr.z, fr.u))
+        res = (out, h.get_map_counts().copy(), h.get_ancestors().copy(), h.get_poses().copy(), h.get_weights().copy(),
+               [h.get_map(i) for i in (0, 17, 47)])
+        h.close()
+        return res
+
+    a, b = run(), run()
+    assert a[0] == b[0]
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    assert np.allclose(a[4], b[4], rtol=1e-12, atol=0)
+    for ma, mb in zip(a[5], b[5]):
+        for x, y in zip(ma, mb):
+            assert np.array_equal(x, y)
