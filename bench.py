@@ -194,7 +194,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "tiny", "c4s"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "tiny", "c4s", "c4m"])
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="frames of the host-buffer pass (default min(steps, 10))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -288,7 +288,7 @@ def main():
         dbgc = h.debug_counters()
         prof = h.profile_read(steps) if do_profile else None
         resampled_frames = None
-        res = dict(P=P, N=N, M=M, phases=phases, dbg=dbgc, ms_total=ms, steps=steps, launches=launches, counters=ctr, prof=prof, clocks=clocks,
+        res = dict(P=P, N=N, M=M, shape=h.launch_shape(), phases=phases, dbg=dbgc, ms_total=ms, steps=steps, launches=launches, counters=ctr, prof=prof, clocks=clocks,
                    mean_components=ctr["comps_out"] / max(1, ctr["particle_frames"]),
                    pairs_per_particle_frame=ctr["pairs"] / max(1, ctr["particle_frames"]))
 
@@ -382,7 +382,8 @@ def main():
                    "gated_pairs_per_particle_frame": main_res["pairs_per_particle_frame"],
                    "l2_policy": "inputs larger than L2 (per-GPU map state %.1f GB read+written per frame)"
                                 % (abytes_local / max(1, args.steps) / 1e9),
-                   "sharding": "particles by rank, weight allgather per frame" if world > 1 else "single GPU"},
+                   "sharding": "particles by rank, weight allgather per frame" if world > 1 else "single GPU",
+                   "launch_shape": main_res["shape"]},
         "component_updates_per_sec": value * N * M,
         "frames_per_sec": args.steps / sec,
         "gpu_launches": int(sum_over_ranks(main_res["launches"])),

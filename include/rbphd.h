@@ -185,6 +185,9 @@ int rbphd_get_counters(rbphd_navigator* nav, int64_t out4[4], int reset);
 /* diagnostics: SM cycles per internal phase of the fused kernel summed over CTAs (32 entries) followed
  * by 16 event counters */
 int rbphd_get_phase_cycles(rbphd_navigator* nav, int64_t out48[48]);
+/* launch geometry of the fused per-particle kernel on this handle: threads per CTA, resident CTAs per SM,
+ * dynamic shared memory per CTA (bytes), scratch slabs (= CTAs launched), bytes per scratch slab */
+int rbphd_launch_shape(const rbphd_navigator* nav, int64_t out5[5]);
 void* rbphd_stream(rbphd_navigator* nav);   /* cudaStream_t of the handle, for event timing by the host */
 
 #ifdef __cplusplus

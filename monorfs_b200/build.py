@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "librbphd.so")
 SOURCES = ["rbphd_kernels.cu", "rbphd_api.cu"]
-HEADERS = ["rbphd_math.cuh", "rbphd_block.cuh", "rbphd_kernels.cuh", "rbphd_weight.cuh",
+HEADERS = ["rbphd_math.cuh", "rbphd_block.cuh", "rbphd_kernels.cuh", "rbphd_weight.cuh", "rbphd_murty.cuh",
            os.path.join("..", "..", "include", "rbphd.h")]
 
 NVCC_FLAGS = [
@@ -41,6 +41,23 @@ def needs_build():
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build_variant(name, defines, verbose=False):
+    """Experiment builds: librbphd_<name>.so with -D overrides of the launch shape (rbphd_block.cuh).
+    Select one at run time with RBPHD_LIB=<path> (capi.py)."""
+    os.makedirs(OUT_DIR, exist_ok=True)
+    lib = os.path.join(OUT_DIR, "librbphd_%s.so" % name)
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-D%s=%s" % kv for kv in defines.items()] + ["-o", lib] + \
+        [os.path.join(CSRC, s) for s in SOURCES]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    with open(os.path.join(OUT_DIR, "build_%s.log" % name), "w") as fh:
+        fh.write(" ".join(cmd) + "\n" + proc.stdout)
+    if verbose or proc.returncode != 0:
+        sys.stderr.write(proc.stdout)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed for variant %s" % name)
+    return lib
 
 
 def build(force=False, verbose=False):

@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "librbphd.so")
+# RBPHD_LIB selects an experiment build of the same library (monorfs_b200.build.build_variant)
+LIB_PATH = os.environ.get("RBPHD_LIB") or os.path.join(_HERE, "_build", "librbphd.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
@@ -47,6 +48,7 @@ EXPORTS = [
     "rbphd_slam_update_local", "rbphd_device_weights", "rbphd_resample_global", "rbphd_pack_particles",
     "rbphd_particle_record_bytes", "rbphd_unpack_particles", "rbphd_commit_resample_local", "rbphd_kernel_launches", "rbphd_profile_enable",
     "rbphd_profile_read", "rbphd_get_counters", "rbphd_get_phase_cycles", "rbphd_stream",
+    "rbphd_launch_shape",
 ]
 
 _lib = None
@@ -372,6 +374,11 @@ class Handle:
     @property
     def kernel_launches(self):
         return int(self.lib.rbphd_kernel_launches(self._h))
+
+    def launch_shape(self):
+        out = (C.c_int64 * 5)()
+        self._ck(self.lib.rbphd_launch_shape(self._h, out))
+        return dict(zip(("block", "ctas_per_sm", "smem_bytes", "slabs", "slab_bytes"), [int(x) for x in out]))
 
     @property
     def stream(self):

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -66,7 +67,7 @@ struct rbphd_navigator {
     int* idxbuf = nullptr;
     int idxcap = 0;
     // launch geometry
-    int nslab = 0;
+    int nslab = 0, ctas_per_sm = 0;
     size_t smem = 0, sort_cap = 0;
     int M_last = 0;
     int slots = 1;
@@ -206,14 +207,14 @@ void make_layout(ScratchLayout& l, int cap, int Mcap, int cap_pairs, int maxq)
     take(l.hits4, U * l.cap_pred);
     take(l.skey, U * l.cap_sort);    take(l.sval, sizeof(unsigned) * l.cap_sort);
     take(l.skey2, U * l.cap_sort);   take(l.sval2, sizeof(unsigned) * l.cap_sort);
-    take(l.tw, D * l.cap_top);       take(l.tm, 3 * D * l.cap_top); take(l.tP, 9 * D * l.cap_top);
+    take(l.tw, D * l.cap_top);       take(l.tm, 3 * D * l.cap_top); take(l.tloc, sizeof(unsigned) * l.cap_top);
     take(l.rho, D * l.cap_top);
     take(l.edst, I * l.cap_edges);
     take(l.nstate, I * l.cap_nodes); take(l.nowner, I * l.cap_nodes); take(l.nflag, I * l.cap_nodes);
     take(l.gitems, I * l.cap_nodes);
     take(l.jidx, I * l.cap_j);       take(l.jm, 3 * D * l.cap_j);  take(l.jmp, 3 * D * l.cap_j);
     take(l.jpd, D * l.cap_j);        take(l.vsum, D * l.cap_j);
-    take(l.cinv, kEvalRecFields * D * l.cap_pred); take(l.cinv2, kEvalRecFields * D * l.cap_pred); take(l.cnorm, D * l.cap_pred); take(l.crad, D * l.cap_pred);   // exploration bound per component
+    take(l.erad, D * l.cap_pred); take(l.erad2, D * l.cap_pred); take(l.cnorm, D * l.cap_pred); take(l.crad, D * l.cap_pred);   // exploration bound per component
     take(l.llkey, U * l.cap_ll);     take(l.llval, D * l.cap_ll);
     take(l.uf, I * (l.cap_j + Mcap + 2)); take(l.bcnt, I * (l.cap_j + Mcap + 2));
     take(l.mslots, murty_workspace_bytes());
@@ -474,7 +475,10 @@ rbphd_navigator* rbphd_new(const rbphd_config* config, const rbphd_limits* limit
         return bail("max_measurements too large for shared memory (" + std::to_string(nav->smem) + " B needed)");
     int per_sm = particle_update_max_ctas_per_sm(nav->smem);
     if (per_sm < 1) return bail("k_particle_update cannot be resident (shared memory / registers)");
+    nav->ctas_per_sm = per_sm;
     nav->nslab = std::max(1, std::min(prop.multiProcessorCount * per_sm, nav->maxP));
+    if (const char* lim_ctas = std::getenv("RBPHD_MAX_CTAS"))   // experiments: fewer persistent CTAs than the device holds
+        nav->nslab = std::max(1, std::min(nav->nslab, std::atoi(lim_ctas)));
     CKN(cudaMalloc(&nav->scratch, nav->lay.bytes * (size_t)nav->nslab));
     CKN(cudaStreamSynchronize(nav->stream));
 #undef CKN
@@ -1192,6 +1196,14 @@ int rbphd_get_counters(rbphd_navigator* nav, int64_t out4[4], int reset)
         CK(cudaMemsetAsync(&nav->st->comps_in, 0, 52 * sizeof(unsigned long long), nav->stream));
         CK(cudaStreamSynchronize(nav->stream));
     }
+    return RBPHD_OK;
+}
+
+int rbphd_launch_shape(const rbphd_navigator* nav, int64_t out5[5])
+{
+    if (!nav || !out5) return RBPHD_ERR_ARGUMENT;
+    out5[0] = kBlock; out5[1] = nav->ctas_per_sm; out5[2] = (int64_t)nav->smem; out5[3] = nav->nslab;
+    out5[4] = (int64_t)nav->lay.bytes;
     return RBPHD_OK;
 }
 

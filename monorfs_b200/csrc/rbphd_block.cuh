@@ -6,10 +6,25 @@
 
 namespace rbphd {
 
-constexpr int kBlock = 1024;         // threads per CTA of the per-particle kernels (one CTA per SM)
+// Launch shape of the per-particle kernels.  The defaults are the production build; build.py can override
+// them (-DRBPHD_BLOCK=... etc.) for occupancy experiments.
+#ifndef RBPHD_BLOCK
+#define RBPHD_BLOCK 1024
+#endif
+#ifndef RBPHD_CTAS_PER_SM
+#define RBPHD_CTAS_PER_SM 1
+#endif
+#ifndef RBPHD_GRID_CELLS
+#define RBPHD_GRID_CELLS 8192
+#endif
+#ifndef RBPHD_SORT_BUCKETS
+#define RBPHD_SORT_BUCKETS 4096
+#endif
+constexpr int kBlock = RBPHD_BLOCK;  // threads per CTA of the per-particle kernels
+constexpr int kCtasPerSm = RBPHD_CTAS_PER_SM;
 constexpr int kWarps = kBlock / 32;
 constexpr int kGridMaxDim = 64;      // cells per axis of a cell grid
-constexpr int kGridMaxCells = 8192;  // cells of a cell grid; the offsets (kGridMaxCells + 1 ints) live in shared memory
+constexpr int kGridMaxCells = RBPHD_GRID_CELLS;  // cells of a cell grid; the offsets (kGridMaxCells + 1 ints) live in shared memory
 
 struct BlockShared {                 // small fixed scratch in shared memory
     int    warp_i[kWarps + 1];
@@ -275,11 +290,12 @@ __device__ inline int block_radix_sort(BlockShared& sh, unsigned long long* k0, 
 // (kout,vout): n entries, ideally shared memory; hist: kSortBuckets + 1 ints of shared memory;
 // biglist: kBigBuckets + 2 ints of shared memory (buckets longer than kBucketThreadMax); wscratch: when
 // (kout,vout) are in global memory, kWarps * 1.5 * kBucketWarpMax 64-bit words of shared memory.
-constexpr int kSortBuckets = 4096;
+constexpr int kSortBuckets = RBPHD_SORT_BUCKETS;
 constexpr int kBucketThreadMax = 6;
 constexpr int kBucketWarpMax = 128;
 constexpr int kBigBuckets = kSortBuckets + 64;   // every bucket can be listed (medium ones in front, long ones at the back)
 constexpr int kLongBuckets = 64;    // share of the list kept for buckets longer than kBucketWarpMax
+constexpr int kInPlaceRows = 8;     // in-place sorts (kin == kout) hold n <= kInPlaceRows * kBlock entries
 
 __device__ inline bool block_bucket_sort(BlockShared& sh, const unsigned long long* kin, const unsigned int* vin,
                                          unsigned long long* kout, unsigned int* vout, int n, int* hist, int* biglist,
@@ -288,6 +304,7 @@ __device__ inline bool block_bucket_sort(BlockShared& sh, const unsigned long lo
 {
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (kin == kout && n > kInPlaceRows * kBlock) return false;
     unsigned long long lo = ~0ull, hi = 0ull;
     for (int e = threadIdx.x; e < n; e += kBlock) { const unsigned long long k = kin[e]; lo = min(lo, k); hi = max(hi, k); }
 #pragma unroll
@@ -347,11 +364,35 @@ __device__ inline bool block_bucket_sort(BlockShared& sh, const unsigned long lo
         if (block_sum_int(sh, nlong_mine) > kLongBuckets) return false;
     }
     block_scan_array(sh, hist, kSortBuckets + 1);   // hist[b] = start of bucket b; used as the scatter cursor
-    for (int e = threadIdx.x; e < n; e += kBlock) {
-        const unsigned long long k = kin[e];
-        const int pos = atomicAdd(&hist[bucket_of(k)], 1);
-        kout[pos] = k;
-        vout[pos] = vin[e];
+    if (kin == kout) {
+        // in place (the input already sits in the shared-memory buffer): every thread takes its entries into
+        // registers, a barrier, then the scatter
+        unsigned long long kr[kInPlaceRows];
+        unsigned int vr[kInPlaceRows];
+#pragma unroll
+        for (int r = 0; r < kInPlaceRows; r++) {
+            const int e = threadIdx.x + r * kBlock;
+            kr[r] = 0; vr[r] = 0;
+            if (e < n) { kr[r] = kin[e]; vr[r] = vin[e]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kInPlaceRows; r++) {
+            const int e = threadIdx.x + r * kBlock;
+            if (e < n) {
+                const int pos = atomicAdd(&hist[bucket_of(kr[r])], 1);
+                kout[pos] = kr[r];
+                vout[pos] = vr[r];
+            }
+        }
+    }
+    else {
+        for (int e = threadIdx.x; e < n; e += kBlock) {
+            const unsigned long long k = kin[e];
+            const int pos = atomicAdd(&hist[bucket_of(k)], 1);
+            kout[pos] = k;
+            vout[pos] = vin[e];
+        }
     }
     __syncthreads();
     // after the scatter hist[b] = end of bucket b = start of bucket b + 1
@@ -668,17 +709,18 @@ __device__ inline void grid_build(BlockShared& sh, CellGrid& g, int* start, int*
     // ... then shift right by one to restore the begin offsets (read the whole run first, then write)
     {
         int prev = (c0 > 0 && c0 - 1 <= ncell) ? start[c0 - 1] : 0;
-        int vals[16];
-        for (int a = 0; a < per && a < 16; a++) { const int cc = c0 + a; vals[a] = (cc <= ncell) ? start[cc] : 0; }
+        constexpr int kPerMax = (kGridMaxCells + kBlock) / kBlock;   // >= per for every grid
+        int vals[kPerMax];
+        for (int a = 0; a < per && a < kPerMax; a++) { const int cc = c0 + a; vals[a] = (cc <= ncell) ? start[cc] : 0; }
         __syncthreads();
-        if (per <= 16) {
+        if (per <= kPerMax) {
             for (int a = 0; a < per; a++) {
                 const int cc = c0 + a;
                 if (cc <= ncell) start[cc] = (a == 0) ? prev : vals[a - 1];
             }
         }
         __syncthreads();
-        if (per > 16) {   // (not reached with kGridMaxCells <= 16 * kBlock; kept for safety)
+        if (per > kPerMax) {   // (never: per <= kPerMax by construction; kept for safety)
             for (int base = (ncell / kBlock) * kBlock; base >= 0; base -= kBlock) {
                 int c = base + threadIdx.x;
                 int v = (c <= ncell && c > 0) ? start[c - 1] : 0;

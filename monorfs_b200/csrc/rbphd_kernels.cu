@@ -43,8 +43,14 @@ struct Ctx {
     } while (0)
 
 
-constexpr int kSortCap = 8192;   // (key,val) pairs the shared-memory sort buffer holds
-constexpr int kVsCap = 4096;
+#ifndef RBPHD_SORT_CAP
+#define RBPHD_SORT_CAP 8192
+#endif
+#ifndef RBPHD_VS_CAP
+#define RBPHD_VS_CAP 4096
+#endif
+constexpr int kSortCap = RBPHD_SORT_CAP;   // (key,val) pairs the shared-memory sort buffer holds
+constexpr int kVsCap = RBPHD_VS_CAP;
 
 // Dynamic shared memory of k_particle_update: this header, then the fixed-size buffers at compile-time
 // offsets, then the per-measurement arrays (sized by the frame's M).  The accessors go through the
@@ -82,6 +88,8 @@ struct Smem {
 };
 
 static_assert(sizeof(double) * kVsCap >= sizeof(int) * kWarps * 256, "the radix-sort histograms alias the vs buffer");
+static_assert(sizeof(unsigned long long) * kSortCap >= sizeof(unsigned long long) * kWarps * (kBucketWarpMax + kBucketWarpMax / 2),
+              "the bucket sort's per-warp staging aliases the shared-memory key buffer");
 static_assert(sizeof(double) * kVsCap + sizeof(int) * 256 >= sizeof(int) * (kSortBuckets + 1 + kBigBuckets + 2),
               "the bucket-sort histogram and bucket list alias the vs buffer and the 256-int histogram behind it");
 
@@ -95,10 +103,11 @@ struct Slab {
     double *crec, *cpn;    // per gated component: measurement-space record (kRecFields doubles) and updated covariance (9)
     unsigned long long *skey, *skey2;
     unsigned int *sval, *sval2;
-    double *tw, *tm, *tP, *rho;
+    double *tw, *tm, *rho;
+    unsigned int* tloc;    // per ranked candidate: where its covariance lives (cov_at)
     int *edst, *nstate, *nowner, *nflag, *gitems;
     int *jidx;
-    double *jm, *jmp, *jpd, *vsum, *cinv, *cinv2, *cnorm, *crad;
+    double *jm, *jmp, *jpd, *vsum, *erad, *erad2, *cnorm, *crad;
     unsigned long long* llkey;
     double* llval;
     int *uf;
@@ -118,13 +127,13 @@ __device__ __forceinline__ Slab make_slab(unsigned char* base, const ScratchLayo
     s.hits4 = (unsigned long long*)(base + l.hits4);
     s.skey = (unsigned long long*)(base + l.skey); s.sval = (unsigned int*)(base + l.sval);
     s.skey2 = (unsigned long long*)(base + l.skey2); s.sval2 = (unsigned int*)(base + l.sval2);
-    s.tw = (double*)(base + l.tw); s.tm = (double*)(base + l.tm); s.tP = (double*)(base + l.tP);
+    s.tw = (double*)(base + l.tw); s.tm = (double*)(base + l.tm); s.tloc = (unsigned int*)(base + l.tloc);
     s.rho = (double*)(base + l.rho);
     s.edst = (int*)(base + l.edst); s.nstate = (int*)(base + l.nstate);
     s.nowner = (int*)(base + l.nowner); s.nflag = (int*)(base + l.nflag); s.gitems = (int*)(base + l.gitems);
     s.jidx = (int*)(base + l.jidx); s.jm = (double*)(base + l.jm); s.jmp = (double*)(base + l.jmp);
-    s.jpd = (double*)(base + l.jpd); s.vsum = (double*)(base + l.vsum); s.cinv = (double*)(base + l.cinv);
-    s.cinv2 = (double*)(base + l.cinv2);
+    s.jpd = (double*)(base + l.jpd); s.vsum = (double*)(base + l.vsum); s.erad = (double*)(base + l.erad);
+    s.erad2 = (double*)(base + l.erad2);
     s.cnorm = (double*)(base + l.cnorm); s.crad = (double*)(base + l.crad);
     s.llkey = (unsigned long long*)(base + l.llkey); s.llval = (double*)(base + l.llval);
     s.uf = (int*)(base + l.uf); s.bcnt = (int*)(base + l.bcnt);
@@ -261,7 +270,10 @@ __device__ __forceinline__ unsigned long long hits_close(unsigned long long pack
 // measurement, S^-1 and the Gaussian multiplier, Kalman gain K, updated covariance (I - K H) P.  The
 // reference recomputes these for every (measurement, component) pair; they are the same numbers each
 // time, so they are computed once per gated component and kept in a record the pairs read.
-// record (kRecFields fields, struct of arrays over the gated components in index order): 0-2 h(m)  3 mult  4-12 S^-1  13-21 K  22 pd*w  23-25 m  26 w  27 mult_P  28-36 P^-1
+// record (kRecFields fields, struct of arrays over the gated components in index order):
+//   0-2 h(m)  3 mult  4-12 S^-1  13-21 K  22 pd*w  23-25 m
+// (Evaluating the pairs in this same thread while K and S^-1 are in registers was tried: with 64 registers
+// the loop runs out of spilled values and costs twice the separate dense pass.)
 // ------------------------------------------------------------------------------------------------
 // field f of slot a of a struct-of-arrays record block (consecutive slots are consecutive in memory, so the
 // dense per-slot passes read and write it coalesced)
@@ -273,7 +285,7 @@ struct RecRef {
 };
 
 __device__ __noinline__ void comp_update(const KParams& p, Smem& sm, const Slab& s, const double* in, int a,
-                                         bool want_explore, int pair_offset, bool grid_in_smem)
+                                         int pair_offset, bool grid_in_smem)
 {
     const DevCfg& c = p.cfg;
     const int N = sm.ctx.N;
@@ -308,16 +320,6 @@ __device__ __noinline__ void comp_update(const KParams& p, Smem& sm, const Slab&
         rec[0] = mp[0]; rec[1] = mp[1]; rec[2] = mp[2];
         rec[22] = s.ppd[i] * w;
         rec[23] = m[0]; rec[24] = m[1]; rec[25] = m[2];
-        rec[26] = w;
-    }
-    // exploration term of a prior component (PHD:956-959): P^-1 and its multiplier.  In a full frame they are
-    // already in the evaluation record A2 wrote (eval_pair reads them there by component index)
-    if (want_explore && i < N && !(p.mode == MODE_FRAME && !p.only_mapping)) {
-        double Pinv[9];
-        const double detp = mat3_inv(P, Pinv);
-        rec[27] = gauss_mult(detp);
-#pragma unroll
-        for (int f = 0; f < 9; f++) rec[28 + f] = Pinv[f];
     }
     mat3_mul_bt(P, H, PH);          // PH = P H^T
     {
@@ -346,13 +348,10 @@ __device__ __noinline__ void comp_update(const KParams& p, Smem& sm, const Slab&
 }
 
 // ------------------------------------------------------------------------------------------------
-// one gated pair: un-normalised weight term and updated mean (PHD:886-902) from the component's record;
-// for prior components the exploration density term w_i N(c_k; m_i, P_i) (PHD:956-959, MAP:210-220)
+// one gated pair: un-normalised weight term and updated mean (PHD:886-902) from the component's record
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void eval_pair(const KParams& p, Smem& sm, const Slab& s, int j, int nact_prior,
-                                          bool explore)
+__device__ __forceinline__ void eval_pair(const KParams& p, Smem& sm, const Slab& s, int j)
 {
-    const DevCfg& c = p.cfg;
     const int capq = p.lay.cap_pairs;
     const unsigned long long key = s.pkey[j];
     const int a = (int)(key & 0xffffffffu), k = (int)(key >> 32);
@@ -373,54 +372,28 @@ __device__ __forceinline__ void eval_pair(const KParams& p, Smem& sm, const Slab
         const double q = rec[3] * exp(-0.5 * quad);
         s.pt[j] = rec[22] * q;
     }
-    const double m[3] = {rec[23], rec[24], rec[25]};
 #pragma unroll
     for (int r = 0; r < 3; r++) {
         double kd = 0;
         kd += rec[13 + 3 * r + 0] * innov[0];
         kd += rec[13 + 3 * r + 1] * innov[1];
         kd += rec[13 + 3 * r + 2] * innov[2];
-        s.pmean[(size_t)r * capq + j] = m[r] + kd;
-    }
-    if (explore && a < nact_prior && !sm.kflag()[k]) {   // exploration term of a prior component (one term >= threshold decides)
-        double Pinv[9], gm;
-        if (p.mode == MODE_FRAME && !p.only_mapping) {
-            const size_t rs = (size_t)p.lay.cap_pred;
-            const double* er = s.cinv + s.cact[a];
-#pragma unroll
-            for (int f = 0; f < 9; f++) Pinv[f] = er[(size_t)f * rs];
-            gm = er[9 * rs];
-        }
-        else {
-#pragma unroll
-            for (int f = 0; f < 9; f++) Pinv[f] = rec[28 + f];
-            gm = rec[27];
-        }
-        const double* ck = &sm.cs()[3 * k];
-        const double dc[3] = {ck[0] - m[0], ck[1] - m[1], ck[2] - m[2]};
-        const double e = rec[26] * (gm * exp(-0.5 * quadform3(Pinv, dc)));
-        if (e >= c.explore_thr) sm.kflag()[k] = 1;
+        s.pmean[(size_t)r * capq + j] = rec[23 + r] + kd;
     }
 }
 
-// Evaluation record of one component (used by Map.Evaluate, MAP:192-202, and the exploration terms): P^-1, the
-// Gaussian multiplier, and the squared cull radius kEvalD2 * bound with bound >= lambda_max(P):
-// ||P^2||_F^(1/2) = (sum lambda^4)^(1/4), within 32 % of lambda_max (the trace is up to 3x larger).
-// Struct of arrays with stride rs; written where the covariance is in registers anyway (A2, A5, B6).
+// Squared cull radius of one component for Map.Evaluate (MAP:192-202): kEvalD2 * bound with
+// bound >= lambda_max(P): ||P^2||_F^(1/2) = (sum lambda^4)^(1/4), within 32 % of lambda_max (the trace is up
+// to 3x larger).  Computed where the covariance is in registers anyway (A2, A5, B6).
 constexpr double kEvalD2 = 100.0;   // terms of Map.Evaluate beyond this Mahalanobis distance^2 are < 2e-22 of the peak
-__device__ __forceinline__ double eval_record(const double* P, double* rec, size_t rs, int i)
+__device__ __forceinline__ double eval_radius2(const double* P)
 {
-    double Pinv[9], P2[9];
-    const double det = mat3_inv(P, Pinv);
-#pragma unroll
-    for (int a = 0; a < 9; a++) rec[(size_t)a * rs + i] = Pinv[a];
-    rec[9 * rs + i] = gauss_mult(det);
+    double P2[9];
     mat3_mul(P, P, P2);
     double f = 0;
 #pragma unroll
     for (int a = 0; a < 9; a++) f += P2[a] * P2[a];
-    rec[10 * rs + i] = kEvalD2 * sqrt(sqrt(f)) * (1.0 + 1e-6);
-    return det;
+    return kEvalD2 * sqrt(sqrt(f)) * (1.0 + 1e-6);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -467,9 +440,9 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         double pdi = detection_probability(c, mp);
         s.ppd[i] = pdi;
         s.pwmd[i] = (1 - pdi) * w;
+        int cnt = 0;
+        unsigned long long packed = 0;
         if (do_correct) {
-            int cnt = 0;
-            unsigned long long packed = 0;
             gate_walk(p, sm, m, local, vgrid_smem, [&](int k) { hits_add(packed, cnt, k); });
             s.nflag[i] = cnt;
             s.nstate[i] = (cnt > 0) ? 1 : 0;
@@ -480,14 +453,34 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
             double P[9];
 #pragma unroll
             for (int a = 0; a < 9; a++) P[a] = mfield(in, p.cap, 4 + a)[i];
-            // (frames that go on to WeightAlpha also need the component's evaluation record; same determinant)
-            const double det = eval_recs ? eval_record(P, s.cinv, (size_t)capp, i)
-                                         : P[0] * (P[4] * P[8] - P[5] * P[7]) - P[1] * (P[3] * P[8] - P[5] * P[6]) +
-                                               P[2] * (P[3] * P[7] - P[4] * P[6]);
+            const double det = P[0] * (P[4] * P[8] - P[5] * P[7]) - P[1] * (P[3] * P[8] - P[5] * P[6]) +
+                               P[2] * (P[3] * P[7] - P[4] * P[6]);
             const double tr = P[0] + P[4] + P[8];
             const bool spd = (det > 0) && (tr > 0) && (w >= 0);
             s.cnorm[i] = spd ? log(w * gauss_mult(det)) : INFINITY;
             s.crad[i] = spd ? 1.0 / (2.0 * tr) : 0.0;
+            // (frames that go on to WeightAlpha also need the component's cull radius for Map.Evaluate)
+            if (eval_recs) s.erad[i] = eval_radius2(P);
+            // Early exploration decisions (PHD:956-959, MAP:210-220): one term w_i N(c_k; m_i, P_i) >= threshold
+            // decides measurement k (all terms are >= 0).  Only the component's first gated measurements are
+            // tried; whatever stays undecided gets the exact sum in A4.
+            if (do_correct && cnt > 0) {
+                const int nt = min(cnt, 4);
+                bool need = false;
+                for (int t = 0; t < nt; t++) need |= !sm.kflag()[(int)((packed >> (15 * t)) & 0x7fffull)];
+                if (need && M <= 32767) {
+                    double Pinv[9];
+                    const double gm = gauss_mult(mat3_inv(P, Pinv));
+                    for (int t = 0; t < nt; t++) {
+                        const int k = (int)((packed >> (15 * t)) & 0x7fffull);
+                        if (sm.kflag()[k]) continue;
+                        const double* ck = &sm.cs()[3 * k];
+                        const double dc[3] = {ck[0] - m[0], ck[1] - m[1], ck[2] - m[2]};
+                        const double e = w * (gm * exp(-0.5 * quadform3(Pinv, dc)));
+                        if (e >= c.explore_thr) sm.kflag()[k] = 1;
+                    }
+                }
+            }
         }
     }
     __syncthreads();
@@ -515,17 +508,14 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
     // A round of comp_update costs about the same whether 1024 or 100 threads take part (a long dependent
     // FP64 chain), so a short last round is put off and shares the round of the births (A7).  Its pairs then
     // miss the early exploration flags; those measurements are decided by the exact sum of A4 instead.
-    int a_split = nact_prior, j_split = npairs_prior;
-    if (do_births && nact_prior > kBlock && (nact_prior % kBlock) != 0 && (nact_prior % kBlock) <= kBlock / 2) {
+    // (The pairs themselves are all evaluated in one dense pass after the births' components, A7: the early
+    // exploration decisions they used to feed are made in A2.)
+    int a_split = nact_prior;
+    if (do_births && nact_prior > kBlock && (nact_prior % kBlock) != 0 && (nact_prior % kBlock) <= kBlock / 2)
         a_split = (nact_prior / kBlock) * kBlock;
-        j_split = min(s.nflag[s.cact[a_split]], npairs_prior);
-    }
-    for (int a = tid; a < a_split; a += kBlock) comp_update(p, sm, s, in, a, do_births, 0, vgrid_smem);
+    for (int a = tid; a < a_split; a += kBlock) comp_update(p, sm, s, in, a, 0, vgrid_smem);
     __syncthreads();
     PHASE_MARK(sm, 31);
-    for (int j = tid; j < j_split; j += kBlock) eval_pair(p, sm, s, j, nact_prior, true);
-    __syncthreads();
-    PHASE_MARK(sm, 2);
 
     int B = 0;
     if (do_births) {
@@ -667,7 +657,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
                     int i = N + b;
                     s.pm[i] = sm.cs()[3 * k]; s.pm[capp + i] = sm.cs()[3 * k + 1]; s.pm[2 * capp + i] = sm.cs()[3 * k + 2];
                     s.pwt[i] = c.birth_w;
-                    if (eval_recs) eval_record(c.birth_cov, s.cinv, (size_t)capp, i);
+                    if (eval_recs) s.erad[i] = eval_radius2(c.birth_cov);
                 }
             }
         }
@@ -716,10 +706,12 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         __syncthreads();
     }
     for (int a = a_split + tid; a < nact; a += kBlock)
-        comp_update(p, sm, s, in, a, false, (a < nact_prior) ? 0 : npairs_prior, false);
+        comp_update(p, sm, s, in, a, (a < nact_prior) ? 0 : npairs_prior, false);
     __syncthreads();
-    for (int j = j_split + tid; j < sm.ctx.npairs; j += kBlock) eval_pair(p, sm, s, j, nact_prior, false);
+    PHASE_MARK(sm, 4);
+    for (int j = tid; j < sm.ctx.npairs; j += kBlock) eval_pair(p, sm, s, j);
     __syncthreads();
+    PHASE_MARK(sm, 2);
 
     PHASE_MARK(sm, 4);
     // A8: order the pairs by (measurement, component) -- the reference's output order (PHD:881-903):
@@ -832,6 +824,27 @@ __device__ __forceinline__ void load_corrected(const KParams& p, const Smem& sm,
     }
 }
 
+// Where the covariance of entry e of the corrected list lives, as one word: a prior component (its index in the
+// particle's map), a birth (the configured birth covariance) or a detection (slot of the gated component whose
+// updated covariance it shares).  The ranked candidates keep this word instead of a copy of the covariance.
+constexpr unsigned kLocBirth = 0x80000000u, kLocDet = 0x40000000u;
+__device__ __forceinline__ void cov_at(const KParams& p, const Slab& s, const double* in, unsigned loc, double* P)
+{
+    if (loc & kLocBirth) {
+#pragma unroll
+        for (int f = 0; f < 9; f++) P[f] = p.cfg.birth_cov[f];
+    }
+    else if (loc & kLocDet) {
+        const size_t ca = loc & ~kLocDet;
+#pragma unroll
+        for (int f = 0; f < 9; f++) P[f] = s.cpn[(size_t)f * p.lay.cap_pred + ca];
+    }
+    else {
+#pragma unroll
+        for (int f = 0; f < 9; f++) P[f] = mfield(in, p.cap, 4 + f)[loc];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Phase B: PruneModel (PHD:913-948): stable weight-descending order, MinWeight / MaxQuantity cut,
 // greedy Mahalanobis clustering, moment-matched merge (GAUSS:243-246, 297-347)
@@ -865,6 +878,10 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
         int total;
         int wbase = block_excl_scan(sm.sh, (lane == 0) ? cnt : 0, &total);
         wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        // the candidates go straight into the shared-memory sort buffer when they fit (the sort then runs in place)
+        const bool direct = total <= (int)p.smem_sort_cap && total <= kInPlaceRows * kBlock;
+        unsigned long long* ck = direct ? sm.skey() : s.skey;
+        unsigned int* cv = direct ? sm.sval() : s.sval;
         for (int base = beg; base < end; base += 32 * kRows) {
             double w[kRows];
 #pragma unroll
@@ -876,8 +893,8 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
                 const unsigned m = __ballot_sync(0xffffffffu, keep);
                 if (keep) {
                     const int idx = wbase + __popc(m & ((1u << lane) - 1u));
-                    s.skey[idx] = weight_desc_key(w[r]);
-                    s.sval[idx] = (unsigned)e;
+                    ck[idx] = weight_desc_key(w[r]);
+                    cv[idx] = (unsigned)e;
                 }
                 wbase += __popc(m);
             }
@@ -888,17 +905,21 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
     const int nc = sm.ctx.ncand;
     unsigned int* sval = s.sval;   // list positions in sorted order (wherever the sort leaves them)
     {
+        const bool direct = nc <= (int)p.smem_sort_cap && nc <= kInPlaceRows * kBlock;
         const bool in_smem = nc <= (int)p.smem_sort_cap;
-        unsigned long long* k1 = in_smem ? sm.skey() : s.skey2;
-        unsigned int* v1 = in_smem ? sm.sval() : s.sval2;
+        unsigned long long* k0 = direct ? sm.skey() : s.skey;
+        unsigned int* v0 = direct ? sm.sval() : s.sval;
+        unsigned long long* k1 = direct ? s.skey : (in_smem ? sm.skey() : s.skey2);
+        unsigned int* v1 = direct ? s.sval : (in_smem ? sm.sval() : s.sval2);
         // weights are spread out: one bucket pass + tiny per-bucket sorts; the radix sort is the fallback for
         // degenerate key sets (thousands of equal weights)
-        if (block_bucket_sort(sm.sh, s.skey, s.sval, k1, v1, nc, reinterpret_cast<int*>(sm.vs()),
-                              reinterpret_cast<int*>(sm.vs()) + kSortBuckets + 1, s.skey, s.sval, in_smem ? nullptr : sm.skey())) {
-            sval = v1;
+        if (block_bucket_sort(sm.sh, k0, v0, direct ? k0 : k1, direct ? v0 : v1, nc, reinterpret_cast<int*>(sm.vs()),
+                              reinterpret_cast<int*>(sm.vs()) + kSortBuckets + 1, direct ? s.skey : s.skey,
+                              direct ? s.sval : s.sval, (direct || in_smem) ? nullptr : sm.skey())) {
+            sval = direct ? v0 : v1;
         }
-        else if (block_radix_sort(sm.sh, s.skey, s.sval, k1, v1, nc, reinterpret_cast<int*>(sm.vs()), sm.hist())) {
-            sval = v1;
+        else {
+            sval = block_radix_sort(sm.sh, k0, v0, k1, v1, nc, reinterpret_cast<int*>(sm.vs()), sm.hist()) ? v1 : v0;
         }
     }
     PHASE_MARK(sm, 6);
@@ -906,21 +927,43 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
     const int W0 = min(min(c.maxq, nc), capw);
     if (tid == 0) { sm.ctx.W0 = W0; if (min(c.maxq, nc) > capw) sm.ctx.status |= ST_OVER_COMPONENTS; }
 
-    // B2: materialise the W0 heaviest entries in rank order; merge radius bound per candidate:
-    // d2 = D^T P^-1 D >= |D|^2 / trace(P), so d2 < t^2 needs |D|^2 < t^2 trace(P)
+    // B2: weight, mean and covariance locator of the W0 heaviest entries in rank order; merge radius bound per
+    // candidate: d2 = D^T P^-1 D >= |D|^2 / trace(P), so d2 < t^2 needs |D|^2 < t^2 trace(P)
     double rsum = 0;
-    for (int r = tid; r < W0; r += kBlock) {
-        double w, m[3], P[9];
-        load_corrected(p, sm, s, in, (int)sval[r], w, m, P);
-        s.tw[r] = w;
-        s.tm[r] = m[0]; s.tm[capw + r] = m[1]; s.tm[2 * capw + r] = m[2];
-#pragma unroll
-        for (int a = 0; a < 9; a++) s.tP[(size_t)a * capw + r] = P[a];
-        double tr = P[0] + P[4] + P[8];
-        double rho = c.merge_t * sqrt(tr) * (1.0 + 1e-9);
-        if (!(tr > 0) || !(rho == rho)) rho = INFINITY;
-        s.rho[r] = rho;
-        if (!isinf(rho)) rsum += rho;
+    {
+        const int N = sm.ctx.N, capp = p.lay.cap_pred, capq = p.lay.cap_pairs;
+        for (int r = tid; r < W0; r += kBlock) {
+            const int e = (int)sval[r];
+            double w, m[3], tr;
+            unsigned loc;
+            if (e < Npred) {
+                w = s.pwmd[e];
+                m[0] = s.pm[e]; m[1] = s.pm[capp + e]; m[2] = s.pm[2 * capp + e];
+                if (e < N) {
+                    loc = (unsigned)e;
+                    tr = mfield(in, p.cap, 4)[e] + mfield(in, p.cap, 8)[e] + mfield(in, p.cap, 12)[e];
+                }
+                else {
+                    loc = kLocBirth;
+                    tr = c.birth_cov[0] + c.birth_cov[4] + c.birth_cov[8];
+                }
+            }
+            else {
+                const int t = e - Npred, j = s.bidx[t];
+                w = s.pwgt[t];
+                m[0] = s.pmean[j]; m[1] = s.pmean[capq + j]; m[2] = s.pmean[2 * capq + j];
+                const size_t ca = (size_t)(s.pkey[j] & 0xffffffffu);   // the updated covariance belongs to the component
+                loc = kLocDet | (unsigned)ca;
+                tr = s.cpn[ca] + s.cpn[(size_t)4 * capp + ca] + s.cpn[(size_t)8 * capp + ca];
+            }
+            s.tw[r] = w;
+            s.tm[r] = m[0]; s.tm[capw + r] = m[1]; s.tm[2 * capw + r] = m[2];
+            s.tloc[r] = loc;
+            double rho = c.merge_t * sqrt(tr) * (1.0 + 1e-9);
+            if (!(tr > 0) || !(rho == rho)) rho = INFINITY;
+            s.rho[r] = rho;
+            if (!isinf(rho)) rsum += rho;
+        }
     }
     double rmean = block_sum(sm.sh, rsum) / (W0 > 0 ? W0 : 1);
     __syncthreads();
@@ -961,8 +1004,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
             const double d[3] = {x - tx[r2], y - ty[r2], z - tz[r2]};   // a.Mean - b.Mean (GAUSS:367)
             if (rho == rho && !isinf(rho) && (fabs(d[0]) > rho || fabs(d[1]) > rho || fabs(d[2]) > rho)) return;
             double P[9], Pinv[9];
-#pragma unroll
-            for (int a = 0; a < 9; a++) P[a] = s.tP[(size_t)a * capw + r];
+            cov_at(p, s, in, s.tloc[r], P);
             mat3_inv(P, Pinv);
             if (quadform3(Pinv, d) < t2) {
                 int idx = atomicAdd(&sm.ctx.nedges, 1);
@@ -1084,6 +1126,8 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
         while (true) {
             double w = s.tw[member];
             double m[3] = {tx[member], ty[member], tz[member]};
+            double Pm[9];
+            cov_at(p, s, in, s.tloc[member], Pm);
             weight += w;
 #pragma unroll
             for (int i = 0; i < 3; i++) mean[i] = mean[i] + w * m[i];
@@ -1091,7 +1135,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
             for (int i = 0; i < 3; i++)
 #pragma unroll
                 for (int k = 0; k < 3; k++)
-                    cov[i * 3 + k] = cov[i * 3 + k] + w * (s.tP[(size_t)(i * 3 + k) * capw + member] + m[i] * m[k]);
+                    cov[i * 3 + k] = cov[i * 3 + k] + w * (Pm[i * 3 + k] + m[i] * m[k]);
             // next member owned by r
             a++;
             while (a < e && s.nowner[(int)(ekey[a] & 0xffffffffu)] != r) a++;
@@ -1120,7 +1164,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
         mfield(out, p.cap, 1)[o] = om[0]; mfield(out, p.cap, 2)[o] = om[1]; mfield(out, p.cap, 3)[o] = om[2];
 #pragma unroll
         for (int i = 0; i < 9; i++) mfield(out, p.cap, 4 + i)[o] = oP[i];
-        if (p.mode == MODE_FRAME && !p.only_mapping) eval_record(oP, s.cinv2, (size_t)p.lay.cap_pred, o);
+        if (p.mode == MODE_FRAME && !p.only_mapping) s.erad2[o] = eval_radius2(oP);
     }
     if (tid == 0) sm.ctx.nout = nout;
     __syncthreads();
@@ -1153,7 +1197,7 @@ __device__ __forceinline__ void dump_comp(const KParams& p, int o, double w, con
 // ------------------------------------------------------------------------------------------------
 // the fused per-particle kernel (persistent: CTA b processes particles b, b+grid, ...)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock, 1) k_particle_update(const __grid_constant__ KParams p)
+__global__ void __launch_bounds__(kBlock, kCtasPerSm) k_particle_update(const __grid_constant__ KParams p)
 {
     Smem& sm = *reinterpret_cast<Smem*>(g_smem);
     if (threadIdx.x == 0) sm.Mc = ((p.M + 1) & ~1) > 0 ? ((p.M + 1) & ~1) : 2;

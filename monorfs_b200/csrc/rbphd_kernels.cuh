@@ -42,18 +42,18 @@ struct FrameGrid {
 };
 
 // byte offsets inside one CTA's scratch slab
-constexpr int kRecFields = 37;       // Kalman record of a gated component (rbphd_kernels.cu: comp_update)
-constexpr int kEvalRecFields = 11;   // evaluation record of a component (rbphd_kernels.cu: eval_record)
+
+constexpr int kRecFields = 26;       // Kalman record of a gated component (rbphd_kernels.cu: comp_update)
 
 struct ScratchLayout {
     int cap_pred, cap_pairs, cap_list, cap_sort, cap_top, cap_edges, cap_j, cap_ll, cap_nodes;
     size_t pm, pwt, pwmd, ppd, cact, bidx;
     size_t pkey, pt, pmean, pwgt, crec, cpn, hits4;
     size_t skey, sval, skey2, sval2;
-    size_t tw, tm, tP, rho;
+    size_t tw, tm, tloc, rho;
     size_t edst, nstate, nowner, nflag, gitems;
     // weight stage
-    size_t jidx, jm, jmp, jpd, vsum, cinv, cinv2, cnorm, crad, llkey, llval, uf, bcnt, mslots;
+    size_t jidx, jm, jmp, jpd, vsum, erad, erad2, cnorm, crad, llkey, llval, uf, bcnt, mslots;
     size_t bytes;
 };
 

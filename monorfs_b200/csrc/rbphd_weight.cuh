@@ -48,7 +48,7 @@ __device__ inline double eval_term_full(const CompSrc& c, int i, double x, doubl
 // over the J points (sm.ctx.grid / sm.gstart() / s.gitems, built by the caller) and accumulates into
 // vs[t] with double atomics.  Returns sum_t ln v[t].
 __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, const CompSrc& c, int J,
-                                     double* vs, double* rec, bool rec_ready)
+                                     double* vs, double* erad, bool erad_ready)
 {
     const int tid = threadIdx.x, capj = p.lay.cap_j;
     const double* jx = s.jm; const double* jy = s.jm + capj; const double* jz = s.jm + 2 * capj;
@@ -59,31 +59,24 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
     for (int t = tid; t < J; t += kBlock) vs[t] = 0.0;
     __syncthreads();
     PHASE_MARK(sm, 20);
-    // per-component evaluation records (eval_record): in a frame they were written where the covariances were
-    // in registers (A2 / A5 for the predicted map, B6 for the corrected one); the stage entry point makes them here
-    const size_t rs = (size_t)p.lay.cap_pred;
-    if (!rec_ready) {
+    // per-component cull radius (eval_radius2): in a frame it was computed where the covariances were in
+    // registers (A2 / A5 for the predicted map, B6 for the corrected one); the stage entry point makes it here
+    if (!erad_ready) {
         for (int i = tid; i < c.n; i += kBlock) {
             double P[9];
             comp_cov(c, i, P);
-            eval_record(P, rec, rs, i);
+            erad[i] = eval_radius2(P);
         }
     }
     __syncthreads();
-    auto term_into = [&](int i, int t) {   // w_i N(jm_t; m_i, P_i) -> vs[t]
+    // w_i N(jm_t; m_i, P_i) -> vs[t]; the inverse is formed per term (a few thousand terms per particle: cheaper
+    // than keeping an inverse per component in the slab)
+    auto term_into = [&](int i, int t) {
         const double d[3] = {jx[t] - c.mx[i], jy[t] - c.my[i], jz[t] - c.mz[i]};   // x - Mean (GAUSS:201)
-        // quadform3 row by row (same operation order), one row of P^-1 live at a time
-        double quad = 0;
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            double u = 0;
-            u += rec[(size_t)(3 * r + 0) * rs + i] * d[0];
-            u += rec[(size_t)(3 * r + 1) * rs + i] * d[1];
-            u += rec[(size_t)(3 * r + 2) * rs + i] * d[2];
-            quad += d[r] * u;
-        }
-        const double mult = rec[9 * rs + i];
-        atomicAdd(&vs[t], c.w[i] * (mult * exp(-0.5 * quad)));
+        double P[9], Pinv[9];
+        comp_cov(c, i, P);
+        const double mult = gauss_mult(mat3_inv(P, Pinv));
+        atomicAdd(&vs[t], c.w[i] * (mult * exp(-0.5 * quadform3(Pinv, d))));
     };
     const int fatcap = p.M;
     if (tid == 0) sm.ctx.nU = 0;
@@ -93,7 +86,7 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
         p.lay.cap_edges / 2,
         [&](int i, auto emit) {
             const double x = c.mx[i], y = c.my[i], z = c.mz[i];
-            const double r2 = rec[10 * rs + i];
+            const double r2 = erad[i];
             bool brute = !(r2 >= 0) || isinf(r2);   // NaN covariance: never cull
             int lo[3], hi[3];
             if (!brute) {
@@ -149,7 +142,7 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
             if (f < nfat) {
                 const int i = sm.kidx()[f];
                 const double x = c.mx[i], y = c.my[i], z = c.mz[i];
-                const double r2 = rec[10 * rs + i];
+                const double r2 = erad[i];
                 int lo[3], hi[3];
                 if (grid_range(g, x, y, z, sqrt(r2), lo, hi)) {
                     const int ny = hi[1] - lo[1] + 1, rows = ny * (hi[2] - lo[2] + 1);
@@ -532,29 +525,44 @@ __device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const 
     __syncthreads();
     int total = block_scan_array(sm.sh, s.nflag, ncorr);
     if (total > p.lay.cap_sort) { if (tid == 0) sm.ctx.status |= ST_OVER_JMAP; }
-    // expanded multiset in the slab, then only its `size` largest values are sorted
+    // expanded multiset (straight into the shared-memory sort buffer when it fits: the sort then runs in place),
+    // then only its `size` largest values are needed in order
     const int gcap = p.lay.cap_sort;
-    for (int i = tid; i < ncorr; i += kBlock) {
-        double w = mfield(corr, p.cap, 0)[i];
-        int off = s.nflag[i];
-        int g = ((i + 1 < ncorr) ? s.nflag[i + 1] : total) - off;
-        for (int j = 0; j < g; j++) {
-            if (off + j < gcap) {
-                s.skey[off + j] = weight_desc_key(w - (double)j);
-                s.sval[off + j] = (unsigned)j * (unsigned)p.cap + (unsigned)i;
+    const bool direct = total <= (int)p.smem_sort_cap && total <= kInPlaceRows * kBlock;
+    {
+        unsigned long long* ek = direct ? sm.skey() : s.skey;
+        unsigned int* ev = direct ? sm.sval() : s.sval;
+        for (int i = tid; i < ncorr; i += kBlock) {
+            double w = mfield(corr, p.cap, 0)[i];
+            int off = s.nflag[i];
+            int g = ((i + 1 < ncorr) ? s.nflag[i + 1] : total) - off;
+            for (int j = 0; j < g; j++) {
+                if (off + j < gcap) {
+                    ek[off + j] = weight_desc_key(w - (double)j);
+                    ev[off + j] = (unsigned)j * (unsigned)p.cap + (unsigned)i;
+                }
             }
         }
     }
     __syncthreads();
     const int tot = min(total, gcap);
     const int wantj = min(size, tot);
-    unsigned long long* skey = s.skey;
-    unsigned int* sval = s.sval;
+    unsigned long long* skey = direct ? sm.skey() : s.skey;
+    unsigned int* sval = direct ? sm.sval() : s.sval;
     int nsort = tot;
     if (wantj > 0) {
         // the whole multiset fits the shared-memory buffer: bucket sort (weights are spread out)
         bool sorted = false;
-        if (tot <= (int)p.smem_sort_cap) {
+        if (direct) {
+            sorted = block_bucket_sort(sm.sh, sm.skey(), sm.sval(), sm.skey(), sm.sval(), tot, reinterpret_cast<int*>(sm.vs()),
+                                       reinterpret_cast<int*>(sm.vs()) + kSortBuckets + 1, s.skey, s.sval);
+            if (!sorted) {   // degenerate keys: the general path below works from the slab copy
+                for (int j = tid; j < tot; j += kBlock) { s.skey[j] = sm.skey()[j]; s.sval[j] = sm.sval()[j]; }
+                __syncthreads();
+                skey = s.skey; sval = s.sval;
+            }
+        }
+        else if (tot <= (int)p.smem_sort_cap) {
             sorted = block_bucket_sort(sm.sh, s.skey, s.sval, sm.skey(), sm.sval(), tot, reinterpret_cast<int*>(sm.vs()),
                                        reinterpret_cast<int*>(sm.vs()) + kSortBuckets + 1, s.skey, s.sval);
             if (sorted) { skey = sm.skey(); sval = sm.sval(); }
@@ -603,11 +611,11 @@ __device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const 
         __syncthreads();
     }
     PHASE_MARK(sm, 23);
-    const double plog = eval_map_at_points(p, sm, s, pred, J, vs, s.cinv, recs_ready);
+    const double plog = eval_map_at_points(p, sm, s, pred, J, vs, s.erad, recs_ready);
     PHASE_MARK(sm, 12);
     CompSrc cor{mfield(corr, p.cap, 0), mfield(corr, p.cap, 1), mfield(corr, p.cap, 2), mfield(corr, p.cap, 3),
                 mfield(corr, p.cap, 4), (size_t)p.cap, ncorr, p.cfg.birth_cov, ncorr};
-    const double clog = eval_map_at_points(p, sm, s, cor, J, vs, s.cinv2, recs_ready);
+    const double clog = eval_map_at_points(p, sm, s, cor, J, vs, s.erad2, recs_ready);
     PHASE_MARK(sm, 13);
 
     const double setll = phase_set_loglikelihood(p, sm, s, J);

@@ -20,6 +20,7 @@ WORKLOADS = {
     "c4": dict(P=20000, N=2000, M=500),
     "tiny": dict(P=64, N=60, M=24),
     "c4s": dict(P=1480, N=2000, M=500),   # config 4's per-particle shape on 1480 particles (profiling runs)
+    "c4m": dict(P=2960, N=2000, M=500),   # the same on 2960 particles (10 per CTA at two CTAs per SM)
 }
 
 MEASURER = [575.8156, 0.1, 10.0, -320, -240, 640, 480]   # range clip widened to 10 m (section 8d)
