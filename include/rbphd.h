@@ -100,6 +100,14 @@ int rbphd_get_poses(rbphd_navigator* nav, const double** poses, int* particles);
  * best / resampled may be NULL. */
 int rbphd_slam_update(rbphd_navigator* nav, const double* z, int m, int only_mapping, double u_resample,
                       int* best, int* resampled);
+/* SlamUpdate in two steps, for hosts that must consume their random stream exactly as the reference does:
+ * PHD:355-357 calls ResampleParticles() -- and with it Util.Uniform.Next() at PHD:727 -- only when
+ * ParticleDepleted() is true.  _begin runs the frame up to that decision and reports it; when *depleted comes back
+ * 1 the host draws the uniform and calls _finish(u), which runs the wheel and the particle copy (PHD:724-760).
+ * When *depleted is 0 the frame is complete and _finish is a no-op.  Same results as rbphd_slam_update. */
+int rbphd_slam_update_begin(rbphd_navigator* nav, const double* z, int m, int only_mapping, int* best,
+                            int* depleted);
+int rbphd_slam_update_finish(rbphd_navigator* nav, double u_resample, int* best);
 /* Device-resident frame loop: Update + SlamUpdate enqueued on the handle's stream with nothing copied
  * back and no host synchronisation.  The frame's inputs (gauss: particles x 6, z: m x 3) are uploaded
  * beforehand into input slot `slot` (0 <= slot < resident_frames); either pointer may be NULL to keep
@@ -147,27 +155,46 @@ int rbphd_stage_weight_alpha(rbphd_navigator* nav, const double* pose7, const do
 /* SetLogLikelihood (PHD:462-515) on an explicit landmark list (the IMap of Gaussian(mean, I, 1)) */
 int rbphd_stage_set_loglikelihood(rbphd_navigator* nav, const double* pose7, int j, const double* jmean,
                                   const double* z, int m, double* loglik);
+/* The static likelihood functions of PHDNavigator over a landmark list (jmean: j x 3) seen from pose7:
+ * SetLikelihood (PHD:402-406) = exp(SetLogLikelihood); QuasiSetLogLikelihood (PHD:526-532, 561-713 without the
+ * gradient: full visibility PD_i = PD, association gate d < 12) -- what LoopyPHDNavigator evaluates hundreds of
+ * times per smoothing pass (LoopyPHDNavigator.cs:810-815, 891-897, 948); SetLogLikeMatrix (PHD:415-460) as
+ * (row, column, value) triplets sorted by (row, column): rows/columns 0..j-1 landmarks / measurements-then-misses
+ * exactly as the reference indexes its SparseMatrix (library-owned buffers, valid until the next call). */
+int rbphd_set_likelihood(rbphd_navigator* nav, const double* pose7, int j, const double* jmean, const double* z,
+                         int m, double* likelihood);
+int rbphd_quasi_set_loglikelihood(rbphd_navigator* nav, const double* pose7, int j, const double* jmean,
+                                  const double* z, int m, double* loglik);
+int rbphd_set_loglike_matrix(rbphd_navigator* nav, const double* pose7, int j, const double* jmean, const double* z,
+                             int m, const int** rows, const int** cols, const double** vals, int* nnz);
 
-/* ---- multi-GPU plumbing (particles sharded by rank).  The data-path
- * collectives themselves are issued by the host runtime on these DEVICE buffers. ---- */
-/* SlamUpdate split at the coupling point PHD:343: phase 1 = the Parallel.For body + w *= alpha
- * (inputs from slot `slot`, enqueued without synchronisation) */
-int rbphd_slam_update_local(rbphd_navigator* nav, int slot, int m, int only_mapping);
-/* device pointer to this rank's un-normalised weights (particles doubles) for the allgather */
-int rbphd_device_weights(rbphd_navigator* nav, void** dev_ptr, int* particles);
-/* phase 2: normalise / best / ESS / wheel over the GLOBAL weight vector (device pointer, all ranks'
- * weights in rank order); fills global ancestors; returns this rank's slice decisions */
-int rbphd_resample_global(rbphd_navigator* nav, const void* dev_global_weights, int global_particles,
-                          int rank_offset, double u_resample, int* best_global, int* resampled,
-                          const int** ancestors_global);
-/* pack / unpack particles (pose + map) to flat device records of rbphd_particle_record_bytes() each */
-int64_t rbphd_particle_record_bytes(const rbphd_navigator* nav);
-int rbphd_pack_particles(rbphd_navigator* nav, const int* local_indices, int count, void** dev_buf,
-                         int64_t* bytes);
-/* record records[j] of dev_buf becomes local particle slots[j] (a record may be used several times) */
-int rbphd_unpack_particles(rbphd_navigator* nav, const void* dev_buf, const int* records, const int* slots,
-                           int count);
-int rbphd_commit_resample_local(rbphd_navigator* nav, const int* local_sources, int count);
+/* ---- multi-GPU: particles sharded by rank, collectives inside the library.
+ * One navigator per GPU / rank; rank g owns the block [g*P/G, (g+1)*P/G) of the P global particles.  NCCL is
+ * bound at run time (libnccl.so.2), so a single-GPU host does not need it.  After rbphd_comm_init_rank the frame
+ * entry points (rbphd_frame_async, rbphd_slam_update) run SlamUpdate's coupled tail (PHD:343-358) over all ranks:
+ * one ncclAllGather of the un-normalised weights, the identical serial normalise / ESS / wheel on every rank (so all
+ * ranks hold the same ancestors), one small read-back of the decision, and -- only on resampling frames -- an
+ * allgather of the component counts plus grouped ncclSend / ncclRecv of the ancestors' (pose, map) records,
+ * 8 + 13 n doubles each, every remote ancestor once per destination rank.  Particle indices reported by these
+ * calls (best, ancestors) are GLOBAL.  Replaces the Parallel.For / shared-memory coupling of PHD:326-358. ---- */
+/* a fresh NCCL unique id (call on one rank, hand the 128 bytes to the others by any out-of-band means) */
+int rbphd_comm_unique_id(unsigned char out128[128]);
+/* join the communicator; the navigator must have been reset with this rank's block of `total_particles`.
+ * Sets the local weights to 1 / total_particles (PHD:245-266) and allocates the exchange buffers. */
+int rbphd_comm_init_rank(rbphd_navigator* nav, const unsigned char id128[128], int rank, int world,
+                         int total_particles);
+int rbphd_comm_destroy(rbphd_navigator* nav);
+/* best particle and resampling flag of the most recent frame (multi-GPU: already on the host; single GPU: one
+ * synchronising read of the device state) */
+int rbphd_frame_result(rbphd_navigator* nav, int* best, int* resampled);
+/* since rbphd_comm_init_rank: resampling frames, bytes sent, bytes received, records sent */
+int rbphd_comm_stats(const rbphd_navigator* nav, int64_t out4[4]);
+/* test hook: the exchange plan rank `rank` of `world` derives on the device from global ancestors and counts
+ * (host arrays).  local_src / rec_off: one entry per local particle; send_idx / send_off: local particles + world
+ * entries; hdr: 2 * world + 3 entries (doubles to send per rank, doubles to receive per rank, records to pack,
+ * records to receive, 1 if the ancestors were sorted). */
+int rbphd_debug_migration_plan(int device, const int* ancestors, const int* counts, int total, int world, int rank,
+                               int* local_src, int64_t* rec_off, int* send_idx, int64_t* send_off, int64_t* hdr);
 
 /* ---- instrumentation ---- */
 /* number of kernel launches issued on this handle since creation */
@@ -188,6 +215,10 @@ int rbphd_get_phase_cycles(rbphd_navigator* nav, int64_t out48[48]);
 /* launch geometry of the fused per-particle kernel on this handle: threads per CTA, resident CTAs per SM,
  * dynamic shared memory per CTA (bytes), scratch slabs (= CTAs launched), bytes per scratch slab */
 int rbphd_launch_shape(const rbphd_navigator* nav, int64_t out5[5]);
+/* FP64 pipe microbenchmark on `device` (needs no navigator): out6 = { DFMA TFLOP/s, unfused DMUL+DADD TFLOP/s,
+ * DADD TFLOP/s, FP64 thread-instructions/s fused (1e12), the same unfused (1e12), SM count }.  The frame path is
+ * compiled without contraction, so the unfused figures are its FP64 roofline. */
+int rbphd_bench_fp64(int device, int outer_iterations, double out6[6]);
 void* rbphd_stream(rbphd_navigator* nav);   /* cudaStream_t of the handle, for event timing by the host */
 
 #ifdef __cplusplus

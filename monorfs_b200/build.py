@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "librbphd.so")
-SOURCES = ["rbphd_kernels.cu", "rbphd_api.cu"]
+SOURCES = ["rbphd_kernels.cu", "rbphd_api.cu", "rbphd_microbench.cu"]
 HEADERS = ["rbphd_math.cuh", "rbphd_block.cuh", "rbphd_kernels.cuh", "rbphd_weight.cuh", "rbphd_murty.cuh",
            os.path.join("..", "..", "include", "rbphd.h")]
 
@@ -26,6 +26,18 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
     "--shared",
 ]
+
+
+def source_hash():
+    """Hash of the device sources + the C ABI header: ties ncu-derived counters under profiles/ to a tree."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(SOURCES + HEADERS):
+        path = os.path.join(CSRC, f)
+        if os.path.exists(path):
+            with open(path, "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 def nvcc_path():

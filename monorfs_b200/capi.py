@@ -45,10 +45,11 @@ EXPORTS = [
     "rbphd_particle_depleted", "rbphd_get_weights", "rbphd_set_weights", "rbphd_get_alphas", "rbphd_get_best",
     "rbphd_get_ancestors", "rbphd_get_map_counts", "rbphd_get_map", "rbphd_set_map", "rbphd_stage_predict",
     "rbphd_stage_correct", "rbphd_stage_prune", "rbphd_stage_weight_alpha", "rbphd_stage_set_loglikelihood",
-    "rbphd_slam_update_local", "rbphd_device_weights", "rbphd_resample_global", "rbphd_pack_particles",
-    "rbphd_particle_record_bytes", "rbphd_unpack_particles", "rbphd_commit_resample_local", "rbphd_kernel_launches", "rbphd_profile_enable",
+    "rbphd_comm_unique_id", "rbphd_comm_init_rank", "rbphd_comm_destroy", "rbphd_frame_result", "rbphd_comm_stats",
+    "rbphd_debug_migration_plan", "rbphd_kernel_launches", "rbphd_profile_enable",
     "rbphd_profile_read", "rbphd_get_counters", "rbphd_get_phase_cycles", "rbphd_stream",
-    "rbphd_launch_shape",
+    "rbphd_launch_shape", "rbphd_bench_fp64", "rbphd_slam_update_begin", "rbphd_slam_update_finish",
+    "rbphd_set_likelihood", "rbphd_quasi_set_loglikelihood", "rbphd_set_loglike_matrix",
 ]
 
 _lib = None
@@ -76,12 +77,56 @@ def load():
         lib.rbphd_last_error.argtypes = [C.c_void_p]
         lib.rbphd_kernel_launches.restype = C.c_int64
         lib.rbphd_kernel_launches.argtypes = [C.c_void_p]
-        lib.rbphd_particle_record_bytes.restype = C.c_int64
-        lib.rbphd_particle_record_bytes.argtypes = [C.c_void_p]
         lib.rbphd_stream.restype = C.c_void_p
         lib.rbphd_stream.argtypes = [C.c_void_p]
         _lib = lib
     return _lib
+
+
+def comm_unique_id():
+    """A fresh NCCL unique id (128 bytes) for rbphd_comm_init_rank; call on one rank and distribute."""
+    lib = load()
+    buf = (C.c_ubyte * 128)()
+    rc = lib.rbphd_comm_unique_id(buf)
+    if rc != OK:
+        raise RbphdError(rc, lib.rbphd_last_error(None).decode())
+    return bytes(buf)
+
+
+def debug_migration_plan(ancestors, counts, world, rank, device=0):
+    """The exchange plan the device derives for `rank` (test hook, rbphd_debug_migration_plan)."""
+    lib = load()
+    anc = np.ascontiguousarray(ancestors, dtype=np.int32)
+    cnt = np.ascontiguousarray(counts, dtype=np.int32)
+    total = len(anc)
+    lo, hi = (total * rank) // world, (total * (rank + 1)) // world
+    pl = hi - lo
+    local_src = np.zeros(max(pl, 1), np.int32)
+    rec_off = np.zeros(max(pl, 1), np.int64)
+    send_idx = np.zeros(pl + world, np.int32)
+    send_off = np.zeros(pl + world, np.int64)
+    hdr = np.zeros(2 * world + 3, np.int64)
+    ip = lambda a: a.ctypes.data_as(c_int_p)
+    lp = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+    rc = lib.rbphd_debug_migration_plan(int(device), ip(anc), ip(cnt), total, int(world), int(rank), ip(local_src),
+                                        lp(rec_off), ip(send_idx), lp(send_off), lp(hdr))
+    if rc != OK:
+        raise RbphdError(rc, lib.rbphd_last_error(None).decode())
+    nsend = int(hdr[2 * world])
+    return dict(local_src=local_src[:pl], rec_off=rec_off[:pl], send_idx=send_idx[:nsend], send_off=send_off[:nsend],
+                send_doubles=hdr[:world].copy(), recv_doubles=hdr[world:2 * world].copy(), n_send=nsend,
+                n_recv=int(hdr[2 * world + 1]), sorted=bool(hdr[2 * world + 2]))
+
+
+def bench_fp64(device=0, outer=2000):
+    """FP64 pipe microbenchmark (rbphd_microbench.cu): dict of measured peaks on `device`."""
+    lib = load()
+    out = (C.c_double * 6)()
+    rc = lib.rbphd_bench_fp64(int(device), int(outer), out)
+    if rc != OK:
+        raise RbphdError(rc, "rbphd_bench_fp64 failed")
+    keys = ("dfma_tflops", "dmul_dadd_tflops", "dadd_tflops", "fp64_tinst_per_s_fused", "fp64_tinst_per_s_unfused", "sms")
+    return dict(zip(keys, [float(x) for x in out]))
 
 
 def make_config(p):
@@ -228,6 +273,17 @@ class Handle:
                                             C.byref(best), C.byref(res)))
         return best.value, bool(res.value)
 
+    def slam_update_begin(self, z, only_mapping=False):
+        z = _d(z).reshape(-1, 3)
+        best, dep = C.c_int(), C.c_int()
+        self._ck(self.lib.rbphd_slam_update_begin(self._h, _p(z), len(z), int(only_mapping), C.byref(best), C.byref(dep)))
+        return best.value, bool(dep.value)
+
+    def slam_update_finish(self, u):
+        best = C.c_int()
+        self._ck(self.lib.rbphd_slam_update_finish(self._h, C.c_double(u), C.byref(best)))
+        return best.value
+
     def upload_frame_inputs(self, gauss, z, slot=0):
         g = _d(gauss).reshape(-1, 6) if gauss is not None else None
         zz = _d(z).reshape(-1, 3) if z is not None else None
@@ -296,42 +352,45 @@ class Handle:
                                                         C.byref(out)))
         return out.value
 
-    # ---- multi-GPU plumbing
-    def slam_update_local(self, m, only_mapping=False, slot=0):
-        self._ck(self.lib.rbphd_slam_update_local(self._h, int(slot), int(m), int(only_mapping)))
+    def set_likelihood(self, pose, jm, z):
+        jm, z = _d(jm).reshape(-1, 3), _d(z).reshape(-1, 3)
+        out = C.c_double()
+        self._ck(self.lib.rbphd_set_likelihood(self._h, _p(_d(pose)), len(jm), _p(jm), _p(z), len(z), C.byref(out)))
+        return out.value
 
-    def device_weights(self):
-        ptr, n = C.c_void_p(), C.c_int()
-        self._ck(self.lib.rbphd_device_weights(self._h, C.byref(ptr), C.byref(n)))
-        return ptr.value, n.value
+    def quasi_set_loglikelihood(self, pose, jm, z):
+        jm, z = _d(jm).reshape(-1, 3), _d(z).reshape(-1, 3)
+        out = C.c_double()
+        self._ck(self.lib.rbphd_quasi_set_loglikelihood(self._h, _p(_d(pose)), len(jm), _p(jm), _p(z), len(z),
+                                                        C.byref(out)))
+        return out.value
 
-    def resample_global(self, dev_ptr, global_particles, rank_offset, u):
-        best, res, anc = C.c_int(), C.c_int(), c_int_p()
-        self._ck(self.lib.rbphd_resample_global(self._h, C.c_void_p(dev_ptr), int(global_particles),
-                                                int(rank_offset), C.c_double(u), C.byref(best), C.byref(res),
-                                                C.byref(anc)))
-        return best.value, bool(res.value), _view(anc, global_particles, np.int32)
+    def set_loglike_matrix(self, pose, jm, z):
+        """SetLogLikeMatrix (PHD:415-460) as sorted (row, col, value) triplets."""
+        jm, z = _d(jm).reshape(-1, 3), _d(z).reshape(-1, 3)
+        rows, cols, vals, n = c_int_p(), c_int_p(), c_double_p(), C.c_int()
+        self._ck(self.lib.rbphd_set_loglike_matrix(self._h, _p(_d(pose)), len(jm), _p(jm), _p(z), len(z),
+                                                   C.byref(rows), C.byref(cols), C.byref(vals), C.byref(n)))
+        return _view(rows, n.value, np.int32), _view(cols, n.value, np.int32), _view(vals, n.value)
 
-    def pack_particles(self, idx):
-        idx = np.ascontiguousarray(idx, dtype=np.int32)
-        ptr, nbytes = C.c_void_p(), C.c_int64()
-        self._ck(self.lib.rbphd_pack_particles(self._h, idx.ctypes.data_as(c_int_p), len(idx), C.byref(ptr),
-                                               C.byref(nbytes)))
-        return ptr.value, nbytes.value
+    # ---- multi-GPU (collectives inside the library)
+    def comm_init(self, unique_id, rank, world, total_particles):
+        """Join the NCCL communicator (unique_id: 128 bytes from comm_unique_id() on one rank)."""
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        self._ck(self.lib.rbphd_comm_init_rank(self._h, buf, int(rank), int(world), int(total_particles)))
 
-    def record_doubles(self):
-        return int(self.lib.rbphd_particle_record_bytes(self._h)) // 8
+    def comm_destroy(self):
+        self._ck(self.lib.rbphd_comm_destroy(self._h))
 
-    def unpack_particles(self, dev_ptr, records, slots):
-        records = np.ascontiguousarray(records, dtype=np.int32)
-        slots = np.ascontiguousarray(slots, dtype=np.int32)
-        assert len(records) == len(slots)
-        self._ck(self.lib.rbphd_unpack_particles(self._h, C.c_void_p(dev_ptr), records.ctypes.data_as(c_int_p),
-                                                 slots.ctypes.data_as(c_int_p), len(slots)))
+    def comm_stats(self):
+        out = (C.c_int64 * 4)()
+        self._ck(self.lib.rbphd_comm_stats(self._h, out))
+        return dict(resampling_frames=int(out[0]), sent_bytes=int(out[1]), recv_bytes=int(out[2]), records=int(out[3]))
 
-    def commit_resample_local(self, sources):
-        sources = np.ascontiguousarray(sources, dtype=np.int32)
-        self._ck(self.lib.rbphd_commit_resample_local(self._h, sources.ctypes.data_as(c_int_p), len(sources)))
+    def frame_result(self):
+        best, res = C.c_int(), C.c_int()
+        self._ck(self.lib.rbphd_frame_result(self._h, C.byref(best), C.byref(res)))
+        return best.value, bool(res.value)
 
     # ---- instrumentation
     STAGES = ("pose", "prep", "particle_update", "normalize_resample", "copy_particles")

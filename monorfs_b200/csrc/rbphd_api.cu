@@ -4,8 +4,12 @@
 #include "../../include/rbphd.h"
 #include "rbphd_kernels.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cmath>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -59,13 +63,18 @@ struct rbphd_navigator {
     double* dump = nullptr;
     int* dump_count = nullptr;
     int dump_cap = 0;
-    double* gweights = nullptr;   // multi-GPU: global weight vector workspace
-    int* ganc = nullptr;
-    int gcap = 0;
-    double* packbuf = nullptr;
-    size_t packbytes = 0;
-    int* idxbuf = nullptr;
-    int idxcap = 0;
+    // multi-GPU (rbphd_comm_init_rank): communicator, this rank's block, global work vectors, exchange buffers
+    void* comm = nullptr;         // ncclComm_t
+    int rank = 0, world = 1, total = 0;
+    double* gweights = nullptr;   // all ranks' weights in rank order
+    int *ganc = nullptr, *gcounts = nullptr;
+    int *local_src = nullptr, *send_idx = nullptr;
+    long long *rec_off = nullptr, *send_off = nullptr, *plan_hdr = nullptr;
+    double *sendbuf = nullptr, *recvbuf = nullptr;
+    size_t sendcap = 0, recvcap = 0;   // doubles
+    int last_best = 0, last_resampled = 0;
+    int pending_wheel = 0;        // rbphd_slam_update_begin found the particles depleted; _finish runs the wheel
+    int64_t comm_resamples = 0, comm_sent_bytes = 0, comm_recv_bytes = 0, comm_records = 0;
     // launch geometry
     int nslab = 0, ctas_per_sm = 0;
     size_t smem = 0, sort_cap = 0;
@@ -76,9 +85,10 @@ struct rbphd_navigator {
     std::vector<cudaEvent_t> pev;
     int prof_frames = 0, prof_max = 0;
     // host mirrors (library-owned outputs)
-    PinnedBuf h_in, h_out, h_state, h_map;
+    PinnedBuf h_in, h_out, h_state, h_map, h_plan;
     std::vector<double> o_w, o_m, o_P;
-    std::vector<int> o_anc;
+    std::vector<int> o_anc, o_rows, o_cols;
+    int ll_flags = 0;
     int64_t launches = 0;
     std::string error;
     rbphd_navigator* stage = nullptr;   // lazily created 2-slot navigator for the stage entry points
@@ -92,6 +102,9 @@ int fail(rbphd_navigator* nav, int code, const std::string& msg)
     g_last_error = msg;
     return code;
 }
+
+void comm_free(rbphd_navigator* nav);
+int comm_slam_tail(rbphd_navigator* nav, double u, cudaEvent_t* ev);
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -229,8 +242,7 @@ void free_device(rbphd_navigator* nav)
     cudaFree(nav->alpha_parts); cudaFree(nav->z); cudaFree(nav->gauss); cudaFree(nav->pts);
     cudaFree(nav->ancestors); cudaFree(nav->st); cudaFree(nav->vgrid); cudaFree(nav->zgrid);
     cudaFree(nav->vitems); cudaFree(nav->zitems); cudaFree(nav->scratch); cudaFree(nav->dump);
-    cudaFree(nav->dump_count); cudaFree(nav->gweights); cudaFree(nav->ganc); cudaFree(nav->packbuf);
-    cudaFree(nav->idxbuf);
+    cudaFree(nav->dump_count);
     for (auto& e : nav->pev) cudaEventDestroy(e);
     if (nav->stream) cudaStreamDestroy(nav->stream);
 }
@@ -268,6 +280,7 @@ KParams base_params(rbphd_navigator* nav, int mode, int M, int only_mapping, int
     k.dump_count = nav->dump_count;
     k.dump_cap = nav->dump_cap;
     k.smem_sort_cap = nav->sort_cap;
+    k.ll_flags = nav->ll_flags;
     return k;
 }
 
@@ -492,6 +505,7 @@ void rbphd_delete(rbphd_navigator* nav)
     if (nav->stage) rbphd_delete(nav->stage);
     cudaSetDevice(nav->device);
     if (nav->stream) cudaStreamSynchronize(nav->stream);
+    comm_free(nav);
     free_device(nav);
     delete nav;
 }
@@ -504,6 +518,8 @@ int rbphd_reset(rbphd_navigator* nav, int particles, const double* pose7, int n,
     if (!nav) return RBPHD_ERR_ARGUMENT;
     if (particles < 1 || particles > nav->maxP) return fail(nav, RBPHD_ERR_ARGUMENT, "particle count out of range");
     if (n < 0 || n > nav->cap) return fail(nav, RBPHD_ERR_CAPACITY, "map larger than max_components");
+    if (nav->comm && particles != nav->P)
+        return fail(nav, RBPHD_ERR_ARGUMENT, "particle count differs from the communicator's block: rbphd_comm_destroy first");
     if (int r = set_device(nav)) return r;
     nav->P = particles;
     const int cap = nav->cap;
@@ -520,7 +536,9 @@ int rbphd_reset(rbphd_navigator* nav, int particles, const double* pose7, int n,
                            nav->stream));
         filled += cnt;
     }
-    std::vector<double> hp(7 * (size_t)particles), hw(particles, 1.0 / particles);
+    // PHD:245-266: every particle starts at 1 / P (the GLOBAL particle count when the particles are sharded)
+    std::vector<double> hp(7 * (size_t)particles),
+        hw(particles, 1.0 / ((nav->comm && nav->world > 1) ? nav->total : particles));
     for (int i = 0; i < particles; i++) std::memcpy(&hp[7 * (size_t)i], pose7, 7 * sizeof(double));
     if (int r = upload(nav, nav->poses, hp.data(), hp.size() * sizeof(double))) return r;
     CK(cudaStreamSynchronize(nav->stream));
@@ -549,8 +567,10 @@ int rbphd_upload_frame_inputs(rbphd_navigator* nav, int slot, const double* gaus
     if (int r = set_device(nav)) return r;
     size_t gb = gauss ? sizeof(double) * 6 * (size_t)nav->P : 0;
     size_t zb = z ? sizeof(double) * 3 * (size_t)m : 0;
-    // the pinned staging buffer may still be in flight from the previous frame
+    // the pinned staging buffer may still be in flight from the previous frame; size it for both copies
+    // first so that the second cannot reallocate it under the first
     CK(cudaStreamSynchronize(nav->stream));
+    if (!nav->h_in.get(gb + zb + 16)) return fail(nav, RBPHD_ERR_CUDA, "pinned allocation failed");
     if (gauss) if (int r = upload(nav, nav->gauss + nav->gstride * (size_t)slot, gauss, gb, 0)) return r;
     if (z) if (int r = upload(nav, nav->z + nav->zstride * (size_t)slot, z, zb, gb)) return r;
     return RBPHD_OK;
@@ -778,6 +798,7 @@ int rbphd_frame_async(rbphd_navigator* nav, int slot, const double* reading6, do
     }
     if (ev) cudaEventRecord(ev[1], nav->stream);
     if (int r = enqueue_map_update(nav, m, only_mapping, MODE_FRAME, slot, ev ? ev + 2 : nullptr)) return r;
+    if (nav->comm && nav->world > 1 && !only_mapping) return comm_slam_tail(nav, u_resample, ev ? ev + 4 : nullptr);
     return enqueue_slam_tail(nav, only_mapping, u_resample, 0, ev ? ev + 4 : nullptr);
 }
 
@@ -791,7 +812,8 @@ int rbphd_slam_update(rbphd_navigator* nav, const double* z, int m, int only_map
     if (int r = set_device(nav)) return r;
     if (int r = rbphd_upload_frame_inputs(nav, 0, nullptr, z, m)) return r;
     if (int r = enqueue_map_update(nav, m, only_mapping, MODE_FRAME)) return r;
-    if (int r = enqueue_slam_tail(nav, only_mapping, u_resample, 0)) return r;
+    if (nav->comm && nav->world > 1 && !only_mapping) { if (int r = comm_slam_tail(nav, u_resample, nullptr)) return r; }
+    else if (int r = enqueue_slam_tail(nav, only_mapping, u_resample, 0)) return r;
     DeviceState st;
     if (int r = read_state(nav, &st)) return r;
     if (best) *best = st.best;
@@ -805,11 +827,66 @@ int rbphd_slam_update(rbphd_navigator* nav, const double* z, int m, int only_map
     return RBPHD_OK;
 }
 
+// SlamUpdate in two steps, so that the host draws the wheel's uniform exactly when the reference does
+// (PHD:355-357 calls ResampleParticles, and with it Util.Uniform.Next() at PHD:727, only when depleted)
+int rbphd_slam_update_begin(rbphd_navigator* nav, const double* z, int m, int only_mapping, int* best, int* depleted)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (nav->P < 1) return fail(nav, RBPHD_ERR_ARGUMENT, "navigator not reset");
+    if (m < 0 || m > nav->Mcap) return fail(nav, RBPHD_ERR_ARGUMENT, "m > max_measurements");
+    if (m > 0 && !z) return RBPHD_ERR_ARGUMENT;
+    if (nav->comm && nav->world > 1) return fail(nav, RBPHD_ERR_ARGUMENT, "two-step SlamUpdate is single-GPU: use rbphd_slam_update");
+    if (int r = set_device(nav)) return r;
+    if (int r = rbphd_upload_frame_inputs(nav, 0, nullptr, z, m)) return r;
+    if (int r = enqueue_map_update(nav, m, only_mapping, MODE_FRAME)) return r;
+    if (only_mapping) { launch_flip(nav->stream, nav->st); nav->launches += 1; }
+    else {
+        launch_normalize_resample(nav->stream, nav->dcfg, nav->P, nav->weights, 0.0, 3, nav->ancestors, nav->st);
+        nav->launches += 1;
+    }
+    if (int r = check_async(nav, "slam update (begin)")) return r;
+    DeviceState st;
+    if (int r = read_state(nav, &st)) return r;
+    if (best) *best = st.best;
+    if (depleted) *depleted = only_mapping ? 0 : st.depleted;
+    nav->pending_wheel = (!only_mapping && st.depleted && !st.status) ? 1 : 0;
+    if (st.status) {
+        int status = st.status;
+        CK(cudaMemsetAsync(&nav->st->status, 0, sizeof(int), nav->stream));
+        CK(cudaStreamSynchronize(nav->stream));
+        return status_to_error(nav, status);
+    }
+    return RBPHD_OK;
+}
+
+int rbphd_slam_update_finish(rbphd_navigator* nav, double u_resample, int* best)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    if (nav->pending_wheel) {
+        nav->pending_wheel = 0;
+        launch_normalize_resample(nav->stream, nav->dcfg, nav->P, nav->weights, u_resample, 2, nav->ancestors, nav->st);
+        launch_copy_particles(nav->stream, nav->P, nav->cap, nav->maps, nav->counts, nav->poses, nav->poses_tmp,
+                              nav->ancestors, nav->st);
+        nav->launches += 3;
+        if (int r = check_async(nav, "slam update (finish)")) return r;
+    }
+    DeviceState st;
+    if (int r = read_state(nav, &st)) return r;
+    if (best) *best = st.best;
+    return RBPHD_OK;
+}
+
 int rbphd_resample(rbphd_navigator* nav, double u_resample)
 {
     if (!nav) return RBPHD_ERR_ARGUMENT;
     if (nav->P < 1) return fail(nav, RBPHD_ERR_ARGUMENT, "navigator not reset");
     if (int r = set_device(nav)) return r;
+    {
+        DeviceState st;   // an unacknowledged capacity error leaves the maps unpublished: report it first
+        if (int r = read_state(nav, &st)) return r;
+        if (st.status) return status_to_error(nav, st.status);
+    }
     // the copy kernel moves particles from buffer 1-cur to buffer cur: make the current maps "1-cur" first
     launch_flip(nav->stream, nav->st);
     launch_normalize_resample(nav->stream, nav->dcfg, nav->P, nav->weights, u_resample, 2, nav->ancestors, nav->st);
@@ -949,16 +1026,20 @@ int rbphd_stage_weight_alpha(rbphd_navigator* nav, const double* pose7, const do
     return RBPHD_OK;
 }
 
-int rbphd_stage_set_loglikelihood(rbphd_navigator* nav, const double* pose7, int j, const double* jmean,
-                                  const double* z, int m, double* loglik)
+// the static likelihood functions of PHDNavigator over a landmark list (PHD:395-460, 526-559)
+static int stage_setll(rbphd_navigator* nav, const double* pose7, int j, const double* jmean, const double* z, int m,
+                       int flags, double* loglik, rbphd_navigator** sp)
 {
-    if (!nav) return RBPHD_ERR_ARGUMENT;
     std::vector<double> w(std::max(j, 1), 1.0), P(9 * (size_t)std::max(j, 1), 0.0);
     for (int i = 0; i < j; i++) P[9 * (size_t)i] = P[9 * (size_t)i + 4] = P[9 * (size_t)i + 8] = 1.0;
     rbphd_navigator* s;
     if (int r = stage_run(nav, &s, pose7, j, w.data(), jmean, P.data(), z, m)) return r;
+    if (sp) *sp = s;
     if (j > s->lay.cap_j) return fail(nav, RBPHD_ERR_CAPACITY, "landmark list larger than the map-estimate capacity");
-    if (int r = enqueue_map_update(s, m, 0, MODE_STAGE_SETLL)) return fail(nav, r, s->error);
+    s->ll_flags = flags;
+    int rc = enqueue_map_update(s, m, 0, MODE_STAGE_SETLL);
+    s->ll_flags = 0;
+    if (rc) return fail(nav, rc, s->error);
     DeviceState st;
     if (int r = read_state(s, &st)) return fail(nav, r, s->error);
     void* h;
@@ -972,171 +1053,337 @@ int rbphd_stage_set_loglikelihood(rbphd_navigator* nav, const double* pose7, int
     return RBPHD_OK;
 }
 
-// ------------------------------------------------------------------ multi-GPU plumbing
-int rbphd_slam_update_local(rbphd_navigator* nav, int slot, int m, int only_mapping)
+int rbphd_set_likelihood(rbphd_navigator* nav, const double* pose7, int j, const double* jmean, const double* z, int m,
+                         double* likelihood)
 {
     if (!nav) return RBPHD_ERR_ARGUMENT;
-    if (nav->P < 1) return fail(nav, RBPHD_ERR_ARGUMENT, "navigator not reset");
-    if (m < 0 || m > nav->Mcap) return fail(nav, RBPHD_ERR_ARGUMENT, "m > max_measurements");
-    if (slot < 0 || slot >= nav->slots) return fail(nav, RBPHD_ERR_ARGUMENT, "input slot out of range");
-    if (int r = set_device(nav)) return r;
-    cudaEvent_t* ev = nullptr;   // stage timing: the pose and the global tail are separate calls on this path
-    if (nav->prof_frames < nav->prof_max) ev = &nav->pev[6 * (size_t)nav->prof_frames++];
-    if (ev) { cudaEventRecord(ev[0], nav->stream); cudaEventRecord(ev[1], nav->stream); }
-    if (int r = enqueue_map_update(nav, m, only_mapping, MODE_FRAME, slot, ev ? ev + 2 : nullptr)) return r;
-    if (only_mapping) { launch_flip(nav->stream, nav->st); nav->launches += 1; }
-    if (ev) { cudaEventRecord(ev[4], nav->stream); cudaEventRecord(ev[5], nav->stream); }
-    return check_async(nav, "local slam update");
-}
-
-int rbphd_device_weights(rbphd_navigator* nav, void** dev_ptr, int* particles)
-{
-    if (!nav) return RBPHD_ERR_ARGUMENT;
-    if (dev_ptr) *dev_ptr = nav->weights;
-    if (particles) *particles = nav->P;
+    double ll = 0;
+    if (int r = stage_setll(nav, pose7, j, jmean, z, m, 0, &ll, nullptr)) return r;
+    if (likelihood) *likelihood = std::exp(ll);   // PHD:405
     return RBPHD_OK;
 }
 
-int rbphd_resample_global(rbphd_navigator* nav, const void* dev_global_weights, int global_particles,
-                          int rank_offset, double u_resample, int* best_global, int* resampled,
-                          const int** ancestors_global)
+int rbphd_quasi_set_loglikelihood(rbphd_navigator* nav, const double* pose7, int j, const double* jmean,
+                                  const double* z, int m, double* loglik)
 {
-    if (!nav || !dev_global_weights) return RBPHD_ERR_ARGUMENT;
-    if (rank_offset < 0 || rank_offset + nav->P > global_particles)
-        return fail(nav, RBPHD_ERR_ARGUMENT, "rank slice outside the global particle range");
-    if (int r = set_device(nav)) return r;
-    if (global_particles > nav->gcap) {
-        CK(cudaStreamSynchronize(nav->stream));
-        cudaFree(nav->gweights); cudaFree(nav->ganc);
-        nav->gweights = nullptr; nav->ganc = nullptr;
-        CK(cudaMalloc(&nav->gweights, sizeof(double) * (size_t)global_particles));
-        CK(cudaMalloc(&nav->ganc, sizeof(int) * (size_t)global_particles));
-        nav->gcap = global_particles;
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    return stage_setll(nav, pose7, j, jmean, z, m, LL_QUASI, loglik, nullptr);
+}
+
+int rbphd_set_loglike_matrix(rbphd_navigator* nav, const double* pose7, int j, const double* jmean, const double* z,
+                             int m, const int** rows, const int** cols, const double** vals, int* nnz)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    rbphd_navigator* s = nullptr;
+    if (int r = stage_setll(nav, pose7, j, jmean, z, m, LL_DUMP_MATRIX, nullptr, &s)) return r;
+    void* hc;
+    if (int r = download(s, s->dump_count, sizeof(int), &hc)) return fail(nav, r, s->error);
+    const int cnt = *(int*)hc;
+    if (cnt < 0) return fail(nav, RBPHD_ERR_CAPACITY, "likelihood matrix larger than the dump buffer");
+    void* h;
+    if (int r = download(s, s->dump, sizeof(double) * 3 * (size_t)std::max(cnt, 1), &h)) return fail(nav, r, s->error);
+    const double* t = (const double*)h;
+    // detection entries come off the device in arbitrary order: sort by (row, column)
+    std::vector<int> order(cnt);
+    for (int e = 0; e < cnt; e++) order[e] = e;
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        if (t[3 * (size_t)a] != t[3 * (size_t)b]) return t[3 * (size_t)a] < t[3 * (size_t)b];
+        return t[3 * (size_t)a + 1] < t[3 * (size_t)b + 1];
+    });
+    nav->o_rows.resize(std::max(cnt, 1));
+    nav->o_cols.resize(std::max(cnt, 1));
+    nav->o_w.resize(std::max(cnt, 1));
+    for (int e = 0; e < cnt; e++) {
+        const size_t q = 3 * (size_t)order[e];
+        nav->o_rows[e] = (int)t[q]; nav->o_cols[e] = (int)t[q + 1]; nav->o_w[e] = t[q + 2];
     }
-    CK(cudaMemcpyAsync(nav->gweights, dev_global_weights, sizeof(double) * (size_t)global_particles,
-                       cudaMemcpyDeviceToDevice, nav->stream));
-    // identical code on the identical vector on every rank -> identical ancestors, no further exchange
-    launch_normalize_resample(nav->stream, nav->dcfg, global_particles, nav->gweights, u_resample, 0, nav->ganc,
-                              nav->st);
-    nav->launches += 1;
-    CK(cudaMemcpyAsync(nav->weights, nav->gweights + rank_offset, sizeof(double) * (size_t)nav->P,
-                       cudaMemcpyDeviceToDevice, nav->stream));
-    if (int r = check_async(nav, "global resample")) return r;
-    DeviceState st;
-    if (int r = read_state(nav, &st)) return r;
-    if (best_global) *best_global = st.best;
-    if (resampled) *resampled = st.resampled;
-    if (ancestors_global) {
-        nav->o_anc.resize(global_particles);
-        if (st.resampled) {
-            void* h;
-            if (int r = download(nav, nav->ganc, sizeof(int) * (size_t)global_particles, &h)) return r;
-            std::memcpy(nav->o_anc.data(), h, sizeof(int) * (size_t)global_particles);
+    if (rows) *rows = nav->o_rows.data();
+    if (cols) *cols = nav->o_cols.data();
+    if (vals) *vals = nav->o_w.data();
+    if (nnz) *nnz = cnt;
+    return RBPHD_OK;
+}
+
+int rbphd_stage_set_loglikelihood(rbphd_navigator* nav, const double* pose7, int j, const double* jmean,
+                                  const double* z, int m, double* loglik)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    return stage_setll(nav, pose7, j, jmean, z, m, 0, loglik, nullptr);
+}
+
+// ------------------------------------------------------------------ multi-GPU: particles sharded by rank
+// NCCL is bound at run time (dlopen of libnccl.so.2: the copy already in the process, e.g. the one a host
+// runtime loaded, or the system's), so a single-GPU host needs no NCCL at all.
+}  // extern "C"
+
+namespace {
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+};
+
+NcclApi* nccl_api()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
         }
-        else
-            for (int i = 0; i < global_particles; i++) nav->o_anc[i] = i;
-        *ancestors_global = nav->o_anc.data();
+        if (!api.lib) { api.error = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+        auto sym = [&](const char* nm) {
+            void* p = dlsym(api.lib, nm);
+            if (!p && api.error.empty()) api.error = std::string("libnccl lacks ") + nm;
+            return p;
+        };
+        api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+        api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+        api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+        api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
+        api.Send = (decltype(api.Send))sym("ncclSend");
+        api.Recv = (decltype(api.Recv))sym("ncclRecv");
+        api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+        api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    });
+    return &api;
+}
+
+#define CKNCCL(call)                                                                                     \
+    do {                                                                                                 \
+        ncclResult_t e__ = (call);                                                                       \
+        if (e__ != ncclSuccess)                                                                          \
+            return fail(nav, RBPHD_ERR_CUDA, std::string(#call) + ": " + nccl_api()->GetErrorString(e__)); \
+    } while (0)
+
+int part_lo_host(int r, int world, int total) { return (int)(((long long)total * r) / world); }
+
+void comm_free(rbphd_navigator* nav)
+{
+    if (!nav->comm) return;
+    cudaSetDevice(nav->device);
+    if (nav->stream) cudaStreamSynchronize(nav->stream);
+    nccl_api()->CommDestroy((ncclComm_t)nav->comm);
+    nav->comm = nullptr;
+    cudaFree(nav->gweights); cudaFree(nav->ganc); cudaFree(nav->gcounts); cudaFree(nav->local_src);
+    cudaFree(nav->rec_off); cudaFree(nav->send_idx); cudaFree(nav->send_off); cudaFree(nav->plan_hdr);
+    cudaFree(nav->sendbuf); cudaFree(nav->recvbuf);
+    nav->gweights = nullptr; nav->ganc = nullptr; nav->gcounts = nullptr; nav->local_src = nullptr;
+    nav->rec_off = nullptr; nav->send_idx = nullptr; nav->send_off = nullptr; nav->plan_hdr = nullptr;
+    nav->sendbuf = nullptr; nav->recvbuf = nullptr;
+    nav->world = 1; nav->rank = 0; nav->total = 0;
+}
+
+// allgather of a per-particle array over the block partition (even partition: one ncclAllGather; otherwise one
+// broadcast per rank in a group)
+template <class T>
+int comm_allgather(rbphd_navigator* nav, const T* local, T* global, ncclDataType_t dt)
+{
+    NcclApi* nc = nccl_api();
+    ncclComm_t comm = (ncclComm_t)nav->comm;
+    if (nav->total % nav->world == 0) {
+        CKNCCL(nc->AllGather(local, global, (size_t)nav->P, dt, comm, nav->stream));
+    }
+    else {
+        CKNCCL(nc->GroupStart());
+        for (int r = 0; r < nav->world; r++) {
+            const int lo = part_lo_host(r, nav->world, nav->total), hi = part_lo_host(r + 1, nav->world, nav->total);
+            CKNCCL(nc->Broadcast(local, global + lo, (size_t)(hi - lo), dt, r, comm, nav->stream));
+        }
+        CKNCCL(nc->GroupEnd());
     }
     return RBPHD_OK;
 }
 
-// One migration record = [count as double][pose 7][13 * cap map slab], 8 + 13*cap doubles.
-static size_t record_doubles(const rbphd_navigator* nav) { return 8 + (size_t)kFields * nav->cap; }
-
-int64_t rbphd_particle_record_bytes(const rbphd_navigator* nav)
+// the coupled tail of SlamUpdate over all ranks (PHD:343-358): weight allgather, identical normalise / ESS /
+// wheel on every rank, and -- only when resampling fired -- the exchange of the ancestors' records
+int comm_slam_tail(rbphd_navigator* nav, double u, cudaEvent_t* ev)
 {
-    return nav ? (int64_t)(record_doubles(nav) * sizeof(double)) : 0;
-}
-
-static int upload_ints(rbphd_navigator* nav, const int* a, const int* b, int count, int** da, int** db)
-{
-    int need = 2 * std::max(count, 1);
-    if (need > nav->idxcap) {
-        CK(cudaStreamSynchronize(nav->stream));
-        cudaFree(nav->idxbuf);
-        nav->idxbuf = nullptr;
-        CK(cudaMalloc(&nav->idxbuf, sizeof(int) * (size_t)need * 2));
-        nav->idxcap = need * 2;
-    }
-    CK(cudaStreamSynchronize(nav->stream));   // staging buffer reuse
-    int* h = (int*)nav->h_in.get(sizeof(int) * (size_t)need);
-    if (!h) return fail(nav, RBPHD_ERR_CUDA, "pinned allocation failed");
-    std::memcpy(h, a, sizeof(int) * (size_t)count);
-    if (b) std::memcpy(h + count, b, sizeof(int) * (size_t)count);
-    CK(cudaMemcpyAsync(nav->idxbuf, h, sizeof(int) * (size_t)(b ? 2 * count : count), cudaMemcpyHostToDevice,
+    NcclApi* nc = nccl_api();
+    ncclComm_t comm = (ncclComm_t)nav->comm;
+    const int world = nav->world, rank = nav->rank, total = nav->total;
+    if (int r = comm_allgather<double>(nav, nav->weights, nav->gweights, ncclDouble)) return r;
+    launch_normalize_resample(nav->stream, nav->dcfg, total, nav->gweights, u, 0, nav->ganc, nav->st);
+    const int lo = part_lo_host(rank, world, total);
+    CK(cudaMemcpyAsync(nav->weights, nav->gweights + lo, sizeof(double) * (size_t)nav->P, cudaMemcpyDeviceToDevice,
                        nav->stream));
-    *da = nav->idxbuf;
-    if (db) *db = nav->idxbuf + count;
-    return RBPHD_OK;
-}
-
-int rbphd_pack_particles(rbphd_navigator* nav, const int* local_indices, int count, void** dev_buf, int64_t* bytes)
-{
-    if (!nav || count < 0) return RBPHD_ERR_ARGUMENT;
-    if (int r = set_device(nav)) return r;
-    DeviceState st;
-    if (int r = read_state(nav, &st)) return r;
-    const int src = st.resampled ? 1 - st.cur : st.cur;   // after a resampling decision the posterior is in 1-cur
-    size_t need = record_doubles(nav) * sizeof(double) * (size_t)std::max(count, 1);
-    if (need > nav->packbytes) {
-        cudaFree(nav->packbuf);
-        nav->packbuf = nullptr;
-        CK(cudaMalloc(&nav->packbuf, need));
-        nav->packbytes = need;
-    }
-    for (int j = 0; j < count; j++)
-        if (local_indices[j] < 0 || local_indices[j] >= nav->P) return fail(nav, RBPHD_ERR_ARGUMENT, "pack index out of range");
-    if (count > 0) {
-        int* didx;
-        if (int r = upload_ints(nav, local_indices, nullptr, count, &didx, nullptr)) return r;
-        launch_pack_particles(nav->stream, nav->cap, nav->maps[src], nav->counts[src], nav->poses, didx, count,
-                              nav->packbuf);
-        nav->launches += 1;
-        if (int r = check_async(nav, "pack launch")) return r;
-    }
-    CK(cudaStreamSynchronize(nav->stream));
-    if (dev_buf) *dev_buf = nav->packbuf;
-    if (bytes) *bytes = (int64_t)(record_doubles(nav) * sizeof(double) * (size_t)count);
-    return RBPHD_OK;
-}
-
-int rbphd_unpack_particles(rbphd_navigator* nav, const void* dev_buf, const int* records, const int* slots, int count)
-{
-    if (!nav || count < 0) return RBPHD_ERR_ARGUMENT;
-    if (count == 0) return RBPHD_OK;
-    if (int r = set_device(nav)) return r;
-    DeviceState st;
-    if (int r = read_state(nav, &st)) return r;
-    const int dst = st.cur;   // new particles are assembled in buffer cur (see k_copy_particles)
-    for (int j = 0; j < count; j++)
-        if (slots[j] < 0 || slots[j] >= nav->P) return fail(nav, RBPHD_ERR_ARGUMENT, "unpack slot out of range");
-    int *drec, *dslot;
-    if (int r = upload_ints(nav, records, slots, count, &drec, &dslot)) return r;
-    launch_unpack_particles(nav->stream, nav->cap, (const double*)dev_buf, drec, dslot, count, nav->maps[dst],
-                            nav->counts[dst], nav->poses_tmp);
     nav->launches += 1;
-    if (int r = check_async(nav, "unpack launch")) return r;
-    CK(cudaStreamSynchronize(nav->stream));
+    if (ev) cudaEventRecord(ev[0], nav->stream);
+    // the host has to know whether the exchange is needed: one small read-back per frame
+    DeviceState st;
+    if (int r = read_state(nav, &st)) return r;
+    nav->last_best = st.best;
+    nav->last_resampled = st.resampled;
+    if (st.resampled) {
+        const int post = 1 - st.cur;   // the wheel does not publish: the posterior maps are in buffer 1-cur
+        if (int r = comm_allgather<int>(nav, nav->counts[post], nav->gcounts, ncclInt32)) return r;
+        launch_migration_plan(nav->stream, nav->ganc, nav->gcounts, total, world, rank, nav->local_src, nav->rec_off,
+                              nav->send_idx, nav->send_off, nav->plan_hdr);
+        long long* hdr = (long long*)nav->h_plan.get(sizeof(long long) * (2 * kMaxCommRanks + 4));
+        if (!hdr) return fail(nav, RBPHD_ERR_CUDA, "pinned allocation failed");
+        CK(cudaMemcpyAsync(hdr, nav->plan_hdr, sizeof(long long) * (2 * world + 3), cudaMemcpyDeviceToHost, nav->stream));
+        CK(cudaStreamSynchronize(nav->stream));
+        if (!hdr[2 * world + 2]) return fail(nav, RBPHD_ERR_GENERIC, "migration plan: ancestors are not sorted");
+        long long send_total = 0, recv_total = 0;
+        for (int r = 0; r < world; r++) { send_total += hdr[r]; recv_total += hdr[world + r]; }
+        if ((size_t)send_total > nav->sendcap || (size_t)recv_total > nav->recvcap)
+            return fail(nav, RBPHD_ERR_CAPACITY, "migration buffers too small");
+        launch_pack_records(nav->stream, nav->cap, nav->maps[post], nav->counts[post], nav->poses, nav->send_idx,
+                            nav->send_off, (int)hdr[2 * world], nav->sendbuf);
+        CKNCCL(nc->GroupStart());
+        long long soff = 0, roff = 0;
+        for (int r = 0; r < world; r++) {
+            if (hdr[r] > 0) CKNCCL(nc->Send(nav->sendbuf + soff, (size_t)hdr[r], ncclDouble, r, comm, nav->stream));
+            if (hdr[world + r] > 0) CKNCCL(nc->Recv(nav->recvbuf + roff, (size_t)hdr[world + r], ncclDouble, r, comm, nav->stream));
+            soff += hdr[r];
+            roff += hdr[world + r];
+        }
+        CKNCCL(nc->GroupEnd());
+        launch_unpack_records(nav->stream, nav->P, nav->cap, nav->maps[post], nav->counts[post], nav->maps[st.cur],
+                              nav->counts[st.cur], nav->poses, nav->poses_tmp, nav->local_src, nav->rec_off, nav->recvbuf);
+        launch_copy_doubles(nav->stream, 7 * (size_t)nav->P, nav->poses, nav->poses_tmp);
+        nav->launches += 4;
+        nav->comm_resamples += 1;
+        nav->comm_sent_bytes += 8 * send_total;
+        nav->comm_recv_bytes += 8 * recv_total;
+        nav->comm_records += hdr[2 * world];
+    }
+    if (ev) cudaEventRecord(ev[1], nav->stream);
+    return check_async(nav, "multi-GPU slam tail");
+}
+
+}  // namespace
+
+extern "C" {
+
+int rbphd_comm_unique_id(unsigned char out128[128])
+{
+    if (!out128) return RBPHD_ERR_ARGUMENT;
+    NcclApi* nc = nccl_api();
+    if (!nc->error.empty()) { g_last_error = nc->error; return RBPHD_ERR_GENERIC; }
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclResult_t e = nc->GetUniqueId(&id);
+    if (e != ncclSuccess) { g_last_error = std::string("ncclGetUniqueId: ") + nc->GetErrorString(e); return RBPHD_ERR_GENERIC; }
+    std::memcpy(out128, &id, 128);
     return RBPHD_OK;
 }
 
-int rbphd_commit_resample_local(rbphd_navigator* nav, const int* local_sources, int count)
+int rbphd_comm_init_rank(rbphd_navigator* nav, const unsigned char id128[128], int rank, int world, int total_particles)
 {
-    if (!nav || count != nav->P) return fail(nav, RBPHD_ERR_ARGUMENT, "one source per local particle expected");
+    if (!nav || !id128) return RBPHD_ERR_ARGUMENT;
+    if (world < 1 || world > kMaxCommRanks || rank < 0 || rank >= world)
+        return fail(nav, RBPHD_ERR_ARGUMENT, "rank / world out of range");
+    const int lo = part_lo_host(rank, world, total_particles), hi = part_lo_host(rank + 1, world, total_particles);
+    if (hi - lo != nav->P || nav->P < 1)
+        return fail(nav, RBPHD_ERR_ARGUMENT, "reset the navigator with this rank's block of particles first (block partition)");
+    NcclApi* nc = nccl_api();
+    if (!nc->error.empty()) return fail(nav, RBPHD_ERR_GENERIC, nc->error);
+    if (int r = set_device(nav)) return r;
+    comm_free(nav);
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    ncclComm_t comm;
+    CKNCCL(nc->CommInitRank(&comm, world, id, rank));
+    nav->comm = comm;
+    nav->rank = rank; nav->world = world; nav->total = total_particles;
+    const size_t rec = 8 + (size_t)kFields * nav->cap;
+    nav->sendcap = rec * ((size_t)nav->P + world);
+    nav->recvcap = rec * (size_t)nav->P;
+    CK(cudaMalloc(&nav->gweights, sizeof(double) * (size_t)total_particles));
+    CK(cudaMalloc(&nav->ganc, sizeof(int) * (size_t)total_particles));
+    CK(cudaMalloc(&nav->gcounts, sizeof(int) * (size_t)total_particles));
+    CK(cudaMalloc(&nav->local_src, sizeof(int) * (size_t)nav->P));
+    CK(cudaMalloc(&nav->rec_off, sizeof(long long) * (size_t)nav->P));
+    CK(cudaMalloc(&nav->send_idx, sizeof(int) * ((size_t)nav->P + world)));
+    CK(cudaMalloc(&nav->send_off, sizeof(long long) * ((size_t)nav->P + world)));
+    CK(cudaMalloc(&nav->plan_hdr, sizeof(long long) * (2 * kMaxCommRanks + 4)));
+    CK(cudaMalloc(&nav->sendbuf, sizeof(double) * nav->sendcap));
+    CK(cudaMalloc(&nav->recvbuf, sizeof(double) * nav->recvcap));
+    if (!nav->h_plan.get(sizeof(long long) * (2 * kMaxCommRanks + 4))) return fail(nav, RBPHD_ERR_CUDA, "pinned allocation failed");
+    // the reference starts every particle at 1 / P_total (PHD:245-266), whatever the size of this rank's block
+    launch_fill_doubles(nav->stream, (size_t)nav->P, nav->weights, 1.0 / total_particles);
+    CK(cudaStreamSynchronize(nav->stream));
+    nav->comm_resamples = nav->comm_sent_bytes = nav->comm_recv_bytes = nav->comm_records = 0;
+    return RBPHD_OK;
+}
+
+int rbphd_comm_destroy(rbphd_navigator* nav)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    comm_free(nav);
+    return RBPHD_OK;
+}
+
+int rbphd_comm_stats(const rbphd_navigator* nav, int64_t out4[4])
+{
+    if (!nav || !out4) return RBPHD_ERR_ARGUMENT;
+    out4[0] = nav->comm_resamples; out4[1] = nav->comm_sent_bytes; out4[2] = nav->comm_recv_bytes;
+    out4[3] = nav->comm_records;
+    return RBPHD_OK;
+}
+
+int rbphd_frame_result(rbphd_navigator* nav, int* best, int* resampled)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (nav->world > 1 && nav->comm) {   // known to the host since the frame's read-back
+        if (best) *best = nav->last_best;
+        if (resampled) *resampled = nav->last_resampled;
+        return RBPHD_OK;
+    }
     if (int r = set_device(nav)) return r;
     DeviceState st;
     if (int r = read_state(nav, &st)) return r;
-    const int src = 1 - st.cur, dst = st.cur;
-    for (int i = 0; i < count; i++)
-        if (local_sources[i] >= nav->P) return fail(nav, RBPHD_ERR_ARGUMENT, "local source out of range");
-    int* dsrc;
-    if (int r = upload_ints(nav, local_sources, nullptr, count, &dsrc, nullptr)) return r;
-    launch_commit_local(nav->stream, nav->P, nav->cap, nav->maps[src], nav->counts[src], nav->maps[dst],
-                        nav->counts[dst], nav->poses, nav->poses_tmp, dsrc);
-    launch_copy_doubles(nav->stream, 7 * (size_t)nav->P, nav->poses, nav->poses_tmp);
-    nav->launches += 2;
-    if (int r = check_async(nav, "commit launch")) return r;
-    CK(cudaStreamSynchronize(nav->stream));
+    if (best) *best = st.best;
+    if (resampled) *resampled = st.resampled;
+    return RBPHD_OK;
+}
+
+// the migration plan of one rank for a given global ancestor / count vector (host arrays in, host arrays out):
+// what the frame path computes on the device, exposed for tests
+int rbphd_debug_migration_plan(int device, const int* ancestors, const int* counts, int total, int world, int rank,
+                               int* local_src, int64_t* rec_off, int* send_idx, int64_t* send_off, int64_t* hdr)
+{
+    if (!ancestors || !counts || !local_src || !rec_off || !send_idx || !send_off || !hdr) return RBPHD_ERR_ARGUMENT;
+    if (world < 1 || world > kMaxCommRanks || rank < 0 || rank >= world || total < world) return RBPHD_ERR_ARGUMENT;
+    rbphd_navigator* nav = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return RBPHD_ERR_NO_DEVICE;
+    const int lo = part_lo_host(rank, world, total), hi = part_lo_host(rank + 1, world, total), Pl = hi - lo;
+    int *d_anc = nullptr, *d_cnt = nullptr, *d_ls = nullptr, *d_si = nullptr;
+    long long *d_ro = nullptr, *d_so = nullptr, *d_hdr = nullptr;
+    CK(cudaMalloc(&d_anc, sizeof(int) * total));
+    CK(cudaMalloc(&d_cnt, sizeof(int) * total));
+    CK(cudaMalloc(&d_ls, sizeof(int) * std::max(Pl, 1)));
+    CK(cudaMalloc(&d_ro, sizeof(long long) * std::max(Pl, 1)));
+    CK(cudaMalloc(&d_si, sizeof(int) * (Pl + world)));
+    CK(cudaMalloc(&d_so, sizeof(long long) * (Pl + world)));
+    CK(cudaMalloc(&d_hdr, sizeof(long long) * (2 * world + 3)));
+    CK(cudaMemcpy(d_anc, ancestors, sizeof(int) * total, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_cnt, counts, sizeof(int) * total, cudaMemcpyHostToDevice));
+    CK(cudaMemset(d_si, 0xff, sizeof(int) * (Pl + world)));
+    CK(cudaMemset(d_so, 0xff, sizeof(long long) * (Pl + world)));
+    launch_migration_plan(nullptr, d_anc, d_cnt, total, world, rank, d_ls, d_ro, d_si, d_so, d_hdr);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(local_src, d_ls, sizeof(int) * Pl, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rec_off, d_ro, sizeof(long long) * Pl, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(send_idx, d_si, sizeof(int) * (Pl + world), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(send_off, d_so, sizeof(long long) * (Pl + world), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hdr, d_hdr, sizeof(long long) * (2 * world + 3), cudaMemcpyDeviceToHost));
+    cudaFree(d_anc); cudaFree(d_cnt); cudaFree(d_ls); cudaFree(d_ro); cudaFree(d_si); cudaFree(d_so); cudaFree(d_hdr);
     return RBPHD_OK;
 }
 

@@ -1416,6 +1416,15 @@ __global__ void __launch_bounds__(kBlock) k_normalize_resample(DevCfg cfg, int P
     __shared__ int s_maxi[kWarps];
     const int tid = threadIdx.x;
 
+    // a capacity error in this frame's map update (status bits set by k_particle_update): the frame's results
+    // are not trustworthy -- leave the weights un-normalised, do not resample, do not publish the new maps;
+    // rbphd_synchronize / rbphd_slam_update report the error
+    if (force != 2 && st->status != 0) {
+        for (int i = tid; i < P; i += kBlock) ancestors[i] = i;
+        if (tid == 0) { st->resampled = 0; st->depleted = 0; }
+        return;
+    }
+
     if (force != 2) {
         // sum (serial order)
         if (tid == 0) s_sum = 0;
@@ -1457,7 +1466,7 @@ __global__ void __launch_bounds__(kBlock) k_normalize_resample(DevCfg cfg, int P
             if (tid == 0) { double cacc = s_cum; for (int i = 0; i < n; i++) cacc += tile[i] * tile[i]; s_cum = cacc; }
             __syncthreads();
         }
-        if (tid == 0) s_dep = ((1.0 / s_cum < cfg.min_eff * P) || force) ? 1 : 0;
+        if (tid == 0) s_dep = ((1.0 / s_cum < cfg.min_eff * P) || force == 1) ? 1 : 0;
         __syncthreads();
     }
     else {
@@ -1468,6 +1477,14 @@ __global__ void __launch_bounds__(kBlock) k_normalize_resample(DevCfg cfg, int P
     if (!dep) {
         for (int i = tid; i < P; i += kBlock) ancestors[i] = i;
         if (tid == 0) { st->best = s_best; st->resampled = 0; st->depleted = 0; st->cur = 1 - st->cur; }
+        return;
+    }
+    if (force == 3) {
+        // decision only (rbphd_slam_update_begin): the particles are depleted, the host now draws the wheel's
+        // uniform (PHD:727 draws it only in this case) and calls back with force = 2; the posterior maps stay
+        // unpublished in buffer 1-cur, which is where the wheel's copy expects them
+        for (int i = tid; i < P; i += kBlock) ancestors[i] = i;
+        if (tid == 0) { st->best = s_best; st->resampled = 0; st->depleted = 1; }
         return;
     }
     // systematic wheel (PHD:724-760), serial
@@ -1541,50 +1558,182 @@ __global__ void k_commit_poses(int P, double* poses, const double* poses_tmp, co
     if (i < P * 7) poses[i] = poses_tmp[i];
 }
 
-// ---- multi-GPU migration: flat particle records [count][pose 7][13 * cap map slab] ----
-__global__ void __launch_bounds__(256) k_pack_particles(int cap, const double* maps, const int* counts,
-                                                        const double* poses, const int* idx, double* rec)
+// ------------------------------------------------------------------------------------------------
+// multi-GPU migration after a resampling decision (particles block-partitioned over the ranks).
+// Every rank holds the identical global ancestor vector (the wheel gives NON-DECREASING ancestors, PHD:736)
+// and the allgathered component counts of the posterior maps.  One record = [n][pose 7][13 fields x n],
+// 8 + 13 n doubles: only the components that exist travel.  An ancestor goes once to each destination rank
+// that needs it; both sides order the records of a (source, destination) pair by ancestor index, so no index
+// lists are exchanged.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int part_lo(int r, int world, int total) { return (int)(((long long)total * r) / world); }
+__device__ __forceinline__ int part_owner(int idx, int world, int total)
 {
-    const int j = blockIdx.x, i = idx[j];
-    const size_t rd = 8 + (size_t)kFields * cap;
-    double* r = rec + rd * j;
+    int g = (int)(((long long)idx * world) / total);
+    while (part_lo(g + 1, world, total) <= idx) g++;
+    while (part_lo(g, world, total) > idx) g--;
+    return g;
+}
+
+// exclusive scan of one long long per thread over the CTA (any kBlock); total in *tot
+__device__ __forceinline__ long long block_excl_scan_ll(BlockShared& sh, long long v, long long* tot)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    long long* wsum = reinterpret_cast<long long*>(sh.warp_d);   // kWarps + 1 entries
+    __syncthreads();
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const long long w = (lane < kWarps) ? wsum[lane] : 0;
+        long long wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        if (lane < kWarps) wsum[lane] = wi - w;
+        if (lane == kWarps - 1) wsum[kWarps] = wi;
+    }
+    __syncthreads();
+    const long long res = incl - v + wsum[warp];
+    *tot = wsum[kWarps];
+    return res;
+}
+
+// The exchange plan of rank `rank`, from the global ancestors and counts (one CTA; identical arithmetic on
+// every rank, so senders and receivers agree without talking):
+//   local_src[slot]  local index of the ancestor of new local particle `slot`, or -1 if it arrives by record
+//   rec_off[slot]    offset (doubles) of that record in the receive buffer (records in slot order = source-major)
+//   send_idx/off[t]  t-th record to pack: local particle and offset in the send buffer (destination-major)
+//   hdr              [0..world) doubles to send to each rank, [world..2 world) doubles to receive from each rank,
+//                    [2 world] records to pack, [2 world + 1] records to receive, [2 world + 2] 1 if the ancestors
+//                    were non-decreasing (the plan is only valid then)
+constexpr int kMaxRanks = 64;
+__global__ void __launch_bounds__(kBlock) k_migration_plan(const int* ganc, const int* gcounts, int total, int world,
+                                                          int rank, int* local_src, long long* rec_off,
+                                                          int* send_idx, long long* send_off, long long* hdr)
+{
+    __shared__ BlockShared sh;
+    __shared__ unsigned long long s_send[kMaxRanks], s_recv[kMaxRanks];
+    __shared__ int s_mono;
+    const int tid = threadIdx.x;
+    const int lo = part_lo(rank, world, total), hi = part_lo(rank + 1, world, total);
+    if (tid < kMaxRanks) { s_send[tid] = 0; s_recv[tid] = 0; }
+    if (tid == 0) s_mono = 1;
+    __syncthreads();
+    // receiver side: my new particles lo..hi-1 in order
+    long long carry = 0;
+    int nrec = 0;
+    for (int base = lo; base < hi; base += kBlock) {
+        const int i = base + tid;
+        long long size = 0;
+        int a = 0, src = rank;
+        bool first = false;
+        if (i < hi) {
+            a = ganc[i];
+            src = part_owner(a, world, total);
+            first = (src != rank) && (i == lo || ganc[i - 1] != a);
+            if (first) size = 8 + 13ll * gcounts[a];
+        }
+        long long tot;
+        const long long off = carry + block_excl_scan_ll(sh, size, &tot);
+        carry += tot;
+        nrec += __syncthreads_count(first);
+        if (i < hi) {
+            local_src[i - lo] = (src == rank) ? a - lo : -1;
+            rec_off[i - lo] = first ? off : -1;
+            if (first) atomicAdd(&s_recv[src], (unsigned long long)size);
+        }
+    }
+    __syncthreads();
+    // later copies of a remote ancestor share the record of its first occurrence in my range (binary search:
+    // the ancestors are sorted)
+    for (int i = lo + tid; i < hi; i += kBlock) {
+        if (local_src[i - lo] >= 0 || rec_off[i - lo] >= 0) continue;
+        const int a = ganc[i];
+        int l = lo, h = i;
+        while (l < h) { const int mid = (l + h) >> 1; if (ganc[mid] < a) l = mid + 1; else h = mid; }
+        rec_off[i - lo] = rec_off[l - lo];
+    }
+    // sender side: every new particle of every OTHER rank whose ancestor I own, first occurrence per destination
+    carry = 0;
+    int nsend = 0;
+    for (int base = 0; base < total; base += kBlock) {
+        const int i = base + tid;
+        long long size = 0;
+        bool first = false;
+        int a = 0, d = 0;
+        if (i < total) {
+            a = ganc[i];
+            if (i > 0 && ganc[i - 1] > a) s_mono = 0;
+            if (a >= lo && a < hi) {
+                d = part_owner(i, world, total);
+                first = (d != rank) && (i == part_lo(d, world, total) || ganc[i - 1] != a);
+                if (first) size = 8 + 13ll * gcounts[a];
+            }
+        }
+        long long tot;
+        const long long off = carry + block_excl_scan_ll(sh, size, &tot);
+        carry += tot;
+        int cnt;
+        const int idx = nsend + block_excl_scan(sh, first ? 1 : 0, &cnt);
+        nsend += cnt;
+        if (first) {
+            send_idx[idx] = a - lo;
+            send_off[idx] = off;
+            atomicAdd(&s_send[d], (unsigned long long)size);
+        }
+    }
+    __syncthreads();
+    if (tid < world) { hdr[tid] = (long long)s_send[tid]; hdr[world + tid] = (long long)s_recv[tid]; }
+    if (tid == 0) { hdr[2 * world] = nsend; hdr[2 * world + 1] = nrec; hdr[2 * world + 2] = s_mono; }
+}
+
+// record t of the send buffer <- local particle send_idx[t] of the posterior buffer (CTA per record)
+__global__ void __launch_bounds__(256) k_pack_records(int cap, const double* maps, const int* counts,
+                                                      const double* poses, const int* send_idx,
+                                                      const long long* send_off, double* sendbuf)
+{
+    const int i = send_idx[blockIdx.x];
+    double* r = sendbuf + send_off[blockIdx.x];
     const int n = counts[i];
     if (threadIdx.x == 0) r[0] = (double)n;
     if (threadIdx.x < 7) r[1 + threadIdx.x] = poses[(size_t)i * 7 + threadIdx.x];
     const double* src = maps + (size_t)i * kFields * cap;
     for (int f = 0; f < kFields; f++)
-        for (int t = threadIdx.x; t < n; t += blockDim.x) r[8 + (size_t)f * cap + t] = src[(size_t)f * cap + t];
+        for (int t = threadIdx.x; t < n; t += blockDim.x) r[8 + (size_t)f * n + t] = src[(size_t)f * cap + t];
 }
 
-__global__ void __launch_bounds__(256) k_unpack_particles(int cap, const double* rec, const int* recidx,
-                                                          const int* slots, double* maps, int* counts,
-                                                          double* poses_tmp)
+// new local particle `slot` <- its local ancestor (posterior buffer) or its record (CTA per particle)
+__global__ void __launch_bounds__(256) k_unpack_records(int cap, const double* src_maps, const int* src_counts,
+                                                        double* dst_maps, int* dst_counts, const double* poses,
+                                                        double* poses_tmp, const int* local_src,
+                                                        const long long* rec_off, const double* recvbuf)
 {
-    const int j = blockIdx.x, i = slots[j];
-    const size_t rd = 8 + (size_t)kFields * cap;
-    const double* r = rec + rd * recidx[j];
-    const int n = (int)r[0];
-    if (threadIdx.x == 0) counts[i] = n;
-    if (threadIdx.x < 7) poses_tmp[(size_t)i * 7 + threadIdx.x] = r[1 + threadIdx.x];
-    double* dst = maps + (size_t)i * kFields * cap;
-    for (int f = 0; f < kFields; f++)
-        for (int t = threadIdx.x; t < n; t += blockDim.x) dst[(size_t)f * cap + t] = r[8 + (size_t)f * cap + t];
-}
-
-// new local particle i <- local ancestor sources[i] (>= 0) from the posterior buffer; -1 = filled by unpack
-__global__ void __launch_bounds__(256) k_commit_local(int cap, const double* src_maps, const int* src_counts,
-                                                      double* dst_maps, int* dst_counts, const double* poses,
-                                                      double* poses_tmp, const int* sources)
-{
-    const int i = blockIdx.x, a = sources[i];
-    if (a < 0) return;
-    const int n = src_counts[a];
-    if (threadIdx.x == 0) dst_counts[i] = n;
-    if (threadIdx.x < 7) poses_tmp[(size_t)i * 7 + threadIdx.x] = poses[(size_t)a * 7 + threadIdx.x];
-    const double* src = src_maps + (size_t)a * kFields * cap;
+    const int i = blockIdx.x, a = local_src[i];
     double* dst = dst_maps + (size_t)i * kFields * cap;
-    for (int f = 0; f < kFields; f++)
-        for (int t = threadIdx.x; t < n; t += blockDim.x) dst[(size_t)f * cap + t] = src[(size_t)f * cap + t];
+    if (a >= 0) {
+        const int n = src_counts[a];
+        if (threadIdx.x == 0) dst_counts[i] = n;
+        if (threadIdx.x < 7) poses_tmp[(size_t)i * 7 + threadIdx.x] = poses[(size_t)a * 7 + threadIdx.x];
+        const double* src = src_maps + (size_t)a * kFields * cap;
+        for (int f = 0; f < kFields; f++)
+            for (int t = threadIdx.x; t < n; t += blockDim.x) dst[(size_t)f * cap + t] = src[(size_t)f * cap + t];
+    }
+    else {
+        const double* r = recvbuf + rec_off[i];
+        const int n = min((int)r[0], cap);
+        if (threadIdx.x == 0) dst_counts[i] = n;
+        if (threadIdx.x < 7) poses_tmp[(size_t)i * 7 + threadIdx.x] = r[1 + threadIdx.x];
+        for (int f = 0; f < kFields; f++)
+            for (int t = threadIdx.x; t < n; t += blockDim.x) dst[(size_t)f * cap + t] = r[8 + (size_t)f * n + t];
+    }
 }
 
 __global__ void k_copy_doubles(size_t n, double* dst, const double* src)
@@ -1593,27 +1742,45 @@ __global__ void k_copy_doubles(size_t n, double* dst, const double* src)
     if (i < n) dst[i] = src[i];
 }
 
-void launch_pack_particles(cudaStream_t s, int cap, const double* maps, const int* counts, const double* poses,
-                           const int* idx, int count, double* rec)
+__global__ void k_fill_doubles(size_t n, double* dst, double v)
 {
-    if (count > 0) k_pack_particles<<<count, 256, 0, s>>>(cap, maps, counts, poses, idx, rec);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = v;
 }
-void launch_unpack_particles(cudaStream_t s, int cap, const double* rec, const int* recidx, const int* slots,
-                             int count, double* maps, int* counts, double* poses_tmp)
+
+void launch_migration_plan(cudaStream_t s, const int* ganc, const int* gcounts, int total, int world, int rank,
+                           int* local_src, long long* rec_off, int* send_idx, long long* send_off, long long* hdr)
 {
-    if (count > 0) k_unpack_particles<<<count, 256, 0, s>>>(cap, rec, recidx, slots, maps, counts, poses_tmp);
+    k_migration_plan<<<1, kBlock, 0, s>>>(ganc, gcounts, total, world, rank, local_src, rec_off, send_idx, send_off, hdr);
 }
-void launch_commit_local(cudaStream_t s, int P, int cap, const double* src_maps, const int* src_counts,
-                         double* dst_maps, int* dst_counts, double* poses, double* poses_tmp, const int* sources)
+void launch_pack_records(cudaStream_t s, int cap, const double* maps, const int* counts, const double* poses,
+                         const int* send_idx, const long long* send_off, int count, double* sendbuf)
 {
-    k_commit_local<<<P, 256, 0, s>>>(cap, src_maps, src_counts, dst_maps, dst_counts, poses, poses_tmp, sources);
+    if (count > 0) k_pack_records<<<count, 256, 0, s>>>(cap, maps, counts, poses, send_idx, send_off, sendbuf);
+}
+void launch_unpack_records(cudaStream_t s, int P, int cap, const double* src_maps, const int* src_counts,
+                           double* dst_maps, int* dst_counts, const double* poses, double* poses_tmp,
+                           const int* local_src, const long long* rec_off, const double* recvbuf)
+{
+    if (P > 0)
+        k_unpack_records<<<P, 256, 0, s>>>(cap, src_maps, src_counts, dst_maps, dst_counts, poses, poses_tmp, local_src,
+                                           rec_off, recvbuf);
 }
 void launch_copy_doubles(cudaStream_t s, size_t n, double* dst, const double* src)
 {
     if (n > 0) k_copy_doubles<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, dst, src);
 }
+void launch_fill_doubles(cudaStream_t s, size_t n, double* dst, double v)
+{
+    if (n > 0) k_fill_doubles<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, dst, v);
+}
 
-__global__ void k_flip(DeviceState* st) { st->cur = 1 - st->cur; st->resampled = 0; }
+// publish the maps written to buffer 1-cur (mapping-only frames, stage calls); not after a capacity error
+__global__ void k_flip(DeviceState* st)
+{
+    st->resampled = 0;
+    if (st->status == 0) st->cur = 1 - st->cur;
+}
 
 // ------------------------------------------------------------------------------------------------
 // host-side launchers

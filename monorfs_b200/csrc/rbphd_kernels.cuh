@@ -83,7 +83,10 @@ struct KParams {
     int* dump_count;
     int dump_cap;
     size_t smem_sort_cap;  // elements of the shared-memory sort buffer
+    int ll_flags;          // LikelihoodFlags of a MODE_STAGE_SETLL call
 };
+
+enum LikelihoodFlags { LL_QUASI = 1, LL_DUMP_MATRIX = 2 };   // KParams::ll_flags (MODE_STAGE_SETLL)
 
 struct Reading6 { double v[6]; };
 void launch_predict_pose(cudaStream_t s, const DevCfg& cfg, int P, double* poses, Reading6 reading, double dt,
@@ -91,19 +94,23 @@ void launch_predict_pose(cudaStream_t s, const DevCfg& cfg, int P, double* poses
 void launch_frame_prep(cudaStream_t s, const DevCfg& cfg, const double* z, int M, FrameGrid* vg, int* vitems,
                        FrameGrid* zg, int* zitems, double* pts);
 void launch_particle_update(cudaStream_t s, const KParams& prm, int grid, size_t smem);
-// force: 0 = SlamUpdate tail (PHD:343-358); 1 = same but always resample; 2 = ResampleParticles() alone (PHD:724-760)
+// force: 0 = SlamUpdate tail (PHD:343-358); 1 = same but always resample; 2 = ResampleParticles() alone (PHD:724-760);
+// 3 = SlamUpdate tail up to the depletion decision (the wheel follows later with force = 2)
 void launch_normalize_resample(cudaStream_t s, const DevCfg& cfg, int P, double* weights, double u, int force,
                                int* ancestors, DeviceState* st);
 void launch_copy_particles(cudaStream_t s, int P, int cap, double* const maps[2], int* const counts[2],
                            double* poses, double* poses_tmp, const int* ancestors, DeviceState* st);
 void launch_flip(cudaStream_t s, DeviceState* st);
-void launch_pack_particles(cudaStream_t s, int cap, const double* maps, const int* counts, const double* poses,
-                           const int* idx, int count, double* rec);
-void launch_unpack_particles(cudaStream_t s, int cap, const double* rec, const int* recidx, const int* slots,
-                             int count, double* maps, int* counts, double* poses_tmp);
-void launch_commit_local(cudaStream_t s, int P, int cap, const double* src_maps, const int* src_counts,
-                         double* dst_maps, int* dst_counts, double* poses, double* poses_tmp, const int* sources);
+constexpr int kMaxCommRanks = 64;
+void launch_migration_plan(cudaStream_t s, const int* ganc, const int* gcounts, int total, int world, int rank,
+                           int* local_src, long long* rec_off, int* send_idx, long long* send_off, long long* hdr);
+void launch_pack_records(cudaStream_t s, int cap, const double* maps, const int* counts, const double* poses,
+                         const int* send_idx, const long long* send_off, int count, double* sendbuf);
+void launch_unpack_records(cudaStream_t s, int P, int cap, const double* src_maps, const int* src_counts,
+                           double* dst_maps, int* dst_counts, const double* poses, double* poses_tmp,
+                           const int* local_src, const long long* rec_off, const double* recvbuf);
 void launch_copy_doubles(cudaStream_t s, size_t n, double* dst, const double* src);
+void launch_fill_doubles(cudaStream_t s, size_t n, double* dst, double v);
 size_t particle_update_smem(int max_measurements, size_t* sort_cap);
 size_t murty_workspace_bytes();
 int particle_update_max_ctas_per_sm(size_t smem);

@@ -394,14 +394,18 @@ __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab
 
     // PHD:426-442: predicted measurement and detection probability per landmark, then the d < 5 gate
     const CellGrid& zg = p.zgrid->g;
-    const double rad[3] = {5.0 * sqrt(c.R[0]) * (1 + 1e-9), 5.0 * sqrt(c.R[4]) * (1 + 1e-9),
-                           5.0 * sqrt(c.R[8]) * (1 + 1e-9)};
+    // QuasiSetLogLikelihood (PHD:561-713) is the same computation with full visibility (PD_i = PD) and a wider
+    // association gate (d < 12 instead of d < 5)
+    const bool quasi = (p.ll_flags & LL_QUASI) != 0;
+    const double gate = quasi ? 12.0 : 5.0;
+    const double rad[3] = {gate * sqrt(c.R[0]) * (1 + 1e-9), gate * sqrt(c.R[4]) * (1 + 1e-9),
+                           gate * sqrt(c.R[8]) * (1 + 1e-9)};
     for (int t = tid; t < J; t += kBlock) {
         double m[3] = {jx[t], jy[t], jz[t]}, diff[3], mp[3];
         Quat local;
         to_local(pose, m, diff, local);
         measure_from_local(c, diff, local, mp);
-        double pdt = detection_probability(c, mp);
+        double pdt = quasi ? c.pd : detection_probability(c, mp);
         s.jpd[t] = pdt;
         s.jmp[t] = mp[0]; s.jmp[capj + t] = mp[1]; s.jmp[2 * capj + t] = mp[2];
         int lo[3], hi[3];
@@ -415,7 +419,7 @@ __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab
                     int k = __ldg(&p.zitems[q]);
                     double d3[3] = {mp[0] - sm.zs()[3 * k], mp[1] - sm.zs()[3 * k + 1], mp[2] - sm.zs()[3 * k + 2]};
                     double d = sqrt(quadform3(c.Rinv, d3));
-                    if (d < 5) {
+                    if (d < gate) {
                         int idx = atomicAdd(&s_nll, 1);
                         if (idx < capll) {
                             s.llkey[idx] = ((unsigned long long)t << 32) | (unsigned)k;
@@ -432,6 +436,21 @@ __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab
     __syncthreads();
     const int nll = s_nll;
     if (tid == 0) { sm.ctx.dbg[9] += nll; sm.ctx.dbg[10] += J; }
+    if (p.ll_flags & LL_DUMP_MATRIX) {
+        // SetLogLikeMatrix (PHD:415-460) as (row, column, value) triplets: detections, misses, clutter
+        const int total = nll + J + M;
+        if (3 * (long long)total <= (long long)kFields * p.dump_cap) {
+            for (int e = tid; e < total; e += kBlock) {
+                double r, cc, v;
+                if (e < nll) { r = (double)(s.llkey[e] >> 32); cc = (double)(s.llkey[e] & 0xffffffffu); v = s.llval[e]; }
+                else if (e < nll + J) { const int i = e - nll; r = i; cc = M + i; v = log(1 - s.jpd[i]); }
+                else { const int k = e - nll - J; r = J + k; cc = k; v = c.logclutter; }
+                p.dump[3 * (size_t)e] = r; p.dump[3 * (size_t)e + 1] = cc; p.dump[3 * (size_t)e + 2] = v;
+            }
+            if (tid == 0) *p.dump_count = total;
+        }
+        else if (tid == 0) { *p.dump_count = -1; sm.ctx.status |= ST_OVER_LL; }
+    }
 
     PHASE_MARK(sm, 24);
     // GC:358-425: connected components by min-label propagation over the detection edges
@@ -511,7 +530,23 @@ __device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const 
     for (int i = tid; i < Npred; i += kBlock) a += s.pwt[i];
     for (int i = tid; i < ncorr; i += kBlock) b += mfield(corr, p.cap, 0)[i];
     const double pcount = block_sum(sm.sh, a);
-    const double ccount = block_sum(sm.sh, b);
+    double ccount = block_sum(sm.sh, b);
+    // size = (int)ccount truncates: when the tree sum lands within rounding distance of an integer, the
+    // reference's in-order sum (MAP:61-71) decides which side it falls on -- replay it serially (rare)
+    {
+        const double nearest = floor(ccount + 0.5);
+        if (fabs(ccount - nearest) <= 1e-9 * fmax(1.0, fabs(ccount))) {
+            __shared__ double s_serial;
+            if (tid == 0) {
+                double acc = 0;
+                for (int i = 0; i < ncorr; i++) acc += mfield(corr, p.cap, 0)[i];
+                s_serial = acc;
+            }
+            __syncthreads();
+            ccount = s_serial;
+            __syncthreads();
+        }
+    }
     int size = (ccount > 0) ? ((ccount < 2.0e9) ? (int)ccount : 2000000000) : 0;
 
     // MAP:119-142 BestMapEstimate: the `size` largest values of the multiset {w_i - j : j = 0,1,..},

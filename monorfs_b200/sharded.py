@@ -1,17 +1,18 @@
-"""Particle sharding across the GPUs of one box (one process per GPU, torch.distributed for plumbing).
+"""Particle sharding across the GPUs of one box (one process per GPU).
 
 Particles are independent inside Update and the Parallel.For body of SlamUpdate (PHD:326-339); the only
 coupling is the weight normalisation / ESS test / resampling at PHD:343-358.  Rank g owns the block
-[g*P/G, (g+1)*P/G).  Per frame:
+[g*P/G, (g+1)*P/G).  The data path is entirely inside librbphd.so (rbphd_comm_init_rank, include/rbphd.h):
   1. every rank runs the fused per-particle kernel on its block (no communication);
-  2. ONE allgather of the un-normalised weights (8 B per particle);
+  2. ONE ncclAllGather of the un-normalised weights (8 B per particle);
   3. every rank runs the identical serial normalise / argmax / ESS / wheel code on the identical global
      vector, so all ranks obtain the same ancestors without a second exchange;
-  4. only when resampling fired: ancestors' (pose, map) records move between ranks (send/recv), each
-     distinct remote ancestor once per destination rank.
-
-The exchange plan (which records go where) is pure index arithmetic and is unit-tested on CPU with the
-gloo backend (tests/test_sharded_gloo.py); on GPUs the same plan drives NCCL send/recv on device buffers.
+  4. only when resampling fired: an allgather of the component counts, then grouped ncclSend / ncclRecv of
+     the ancestors' (pose, map) records of 8 + 13 n doubles, each distinct remote ancestor once per
+     destination rank.
+This module only bootstraps the communicator (the NCCL unique id travels over torch.distributed, or any
+other side channel a host has) and holds a pure-Python model of the exchange plan that the tests compare
+the device plan with (tests/test_sharded_gloo.py on CPU, tests/test_gpu_comm.py on the GPU).
 """
 import numpy as np
 
@@ -35,7 +36,8 @@ def owner_of(index, world, total):
 
 
 def migration_plan(ancestors, rank, world):
-    """What this rank must send / receive / copy locally after a resampling decision.
+    """What this rank must send / receive / copy locally after a resampling decision (reference model of
+    k_migration_plan).
 
     ancestors: global array, new particle i takes ancestor ancestors[i] (identical on all ranks).
     Returns dict with
@@ -68,88 +70,51 @@ def migration_plan(ancestors, rank, world):
     return dict(local_sources=local_sources, send=send, recv=recv)
 
 
-class DevArray:
-    """Exposes a raw device pointer through __cuda_array_interface__ so torch can alias it."""
+def record_doubles(n):
+    """Doubles of one migration record: [n][pose 7][13 fields x n]."""
+    return 8 + 13 * int(n)
 
-    def __init__(self, ptr, shape, typestr="<f8"):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
-                                         "version": 2}
+
+def bootstrap_unique_id(rank, world):
+    """NCCL unique id from rank 0 to everybody over an already initialised torch.distributed group."""
+    import torch
+    import torch.distributed as dist
+    from . import capi
+    if dist.get_backend() == "nccl":
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    else:
+        t = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().numpy().tobytes())
 
 
 class ShardedNavigator:
-    """Update / SlamUpdate over particles sharded across ranks; wraps one capi.Handle per process."""
+    """Update / SlamUpdate over particles sharded across ranks; wraps one capi.Handle per process.
 
-    def __init__(self, handle, total_particles, rank=0, world=1, device=0):
+    The handle must already hold this rank's block (reset with hi - lo particles).  With world > 1 the
+    constructor joins the library's NCCL communicator; frame() then is a single library call."""
+
+    def __init__(self, handle, total_particles, rank=0, world=1, device=0, unique_id=None):
         self.h = handle
         self.rank, self.world, self.total = rank, world, total_particles
         self.lo, self.hi = block_range(rank, world, total_particles)
         self.device = device
-        self._torch = None
-        self._stream = None
-        self._gw = None
         if world > 1:
-            import torch
-            self._torch = torch
-            self._stream = torch.cuda.ExternalStream(handle.stream, device=device)
-            self._gw = torch.empty(total_particles, dtype=torch.float64, device="cuda:%d" % device)
-            counts = [block_range(r, world, total_particles) for r in range(world)]
-            self._even = all(c[1] - c[0] == counts[0][1] - counts[0][0] for c in counts)
-            self._parts = [self._gw[c[0]:c[1]] for c in counts]
-        self.resamples = 0
+            if unique_id is None:
+                unique_id = bootstrap_unique_id(rank, world)
+            handle.comm_init(unique_id, rank, world, total_particles)
 
     def frame(self, reading, dt, m, u, slot=0, only_mapping=False):
-        """One Update + SlamUpdate; inputs must already be in input slot `slot`."""
-        if self.world == 1:
-            self.h.frame_async(reading, dt, m, u, only_mapping=only_mapping, slot=slot)
+        """One Update + SlamUpdate; inputs must already be in input slot `slot`.  Returns (best, resampled)
+        with GLOBAL particle indices when sharded (known to the host as soon as the call returns), None on a
+        single GPU (fully asynchronous; ask handle.frame_result() when needed)."""
+        self.h.frame_async(reading, dt, m, u, only_mapping=only_mapping, slot=slot)
+        if self.world == 1 or only_mapping:
             return None
-        torch = self._torch
-        import torch.distributed as dist
-        # local phase: poses + fused per-particle kernel (weights *= alpha), nothing copied back
-        self.h.update_async(reading, dt, slot)
-        self.h.slam_update_local(m, only_mapping=only_mapping, slot=slot)
-        if only_mapping:
-            return None
-        ptr, n = self.h.device_weights()
-        lw = torch.as_tensor(DevArray(ptr, (n,)), device="cuda:%d" % self.device)
-        with torch.cuda.stream(self._stream):
-            if self._even:
-                dist.all_gather_into_tensor(self._gw, lw)
-            else:
-                dist.all_gather(self._parts, lw)
-        best, res, anc = self.h.resample_global(self._gw.data_ptr(), self.total, self.lo, u)
-        if res:
-            self.resamples += 1
-            self._migrate(anc)
-        return best, res
+        return self.h.frame_result()
 
-    def _migrate(self, ancestors):
-        torch = self._torch
-        import torch.distributed as dist
-        plan = migration_plan(ancestors, self.rank, self.world)
-        rd = self.h.record_doubles()
-        ops, recv_bufs = [], {}
-        dests = sorted(plan["send"].items())
-        send_all = [i for _, idx in dests for i in idx]
-        with torch.cuda.stream(self._stream):
-            if send_all:
-                ptr, nbytes = self.h.pack_particles(send_all)      # one buffer, records in destination order
-                sendbuf = torch.as_tensor(DevArray(ptr, (nbytes // 8,)), device="cuda:%d" % self.device)
-                off = 0
-                for dest, idx in dests:
-                    ops.append(dist.P2POp(dist.isend, sendbuf[off:off + rd * len(idx)], dest))
-                    off += rd * len(idx)
-            for src, items in sorted(plan["recv"].items()):
-                buf = torch.empty(len(items) * rd, dtype=torch.float64, device="cuda:%d" % self.device)
-                recv_bufs[src] = buf
-                ops.append(dist.P2POp(dist.irecv, buf, src))
-            if ops:
-                for req in dist.batch_isend_irecv(ops):
-                    req.wait()
-        self._torch.cuda.current_stream(self.device).synchronize()
-        self._stream.synchronize()
-        for src, items in sorted(plan["recv"].items()):
-            buf = recv_bufs[src]
-            records = [k for k, (_, slots) in enumerate(items) for _ in slots]
-            targets = [slot for _, slots in items for slot in slots]
-            self.h.unpack_particles(buf.data_ptr(), records, targets)
-        self.h.commit_resample_local(plan["local_sources"])
+    @property
+    def resamples(self):
+        return self.h.comm_stats()["resampling_frames"] if self.world > 1 else 0

@@ -21,6 +21,8 @@ WORKLOADS = {
     "tiny": dict(P=64, N=60, M=24),
     "c4s": dict(P=1480, N=2000, M=500),   # config 4's per-particle shape on 1480 particles (profiling runs)
     "c4m": dict(P=2960, N=2000, M=500),   # the same on 2960 particles (10 per CTA at two CTAs per SM)
+    "c2x": dict(P=20000, N=500, M=100),   # config 2's per-particle shape on config 4's particle count: resamples
+                                          # every frame, so it exercises the multi-GPU map migration
 }
 
 MEASURER = [575.8156, 0.1, 10.0, -320, -240, 640, 480]   # range clip widened to 10 m (section 8d)

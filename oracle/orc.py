@@ -61,6 +61,7 @@ def lib():
         _lib.orc_fuzzy_visible.restype = C.c_double
         _lib.orc_gaussian_evaluate.restype = C.c_double
         _lib.orc_set_loglikelihood.restype = C.c_double
+        _lib.orc_quasi_set_loglikelihood.restype = C.c_double
         _lib.orc_nav_new.restype = C.c_void_p
     return _lib
 
@@ -293,6 +294,24 @@ def set_loglikelihood(cfg, pose, jm, z):
     jm = np.ascontiguousarray(jm, dtype=np.float64).reshape(-1, 3)
     z = _z(z)
     return lib().orc_set_loglikelihood(C.byref(cfg), _pose(pose)[1], len(jm), _p(jm), len(z), _p(z))
+
+
+def quasi_set_loglikelihood(cfg, pose, jm, z):
+    jm = np.ascontiguousarray(jm, dtype=np.float64).reshape(-1, 3)
+    z = _z(z)
+    return lib().orc_quasi_set_loglikelihood(C.byref(cfg), _pose(pose)[1], len(jm), _p(jm), len(z), _p(z))
+
+
+def set_loglike_matrix(cfg, pose, jm, z, quasi=False):
+    """(rows, cols, vals) of SetLogLikeMatrix, sorted by (row, col)."""
+    jm = np.ascontiguousarray(jm, dtype=np.float64).reshape(-1, 3)
+    z = _z(z)
+    cap = len(jm) * len(z) + len(jm) + len(z) + 1
+    rows, cols, vals = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap)
+    n = lib().orc_set_loglike_matrix(C.byref(cfg), _pose(pose)[1], len(jm), _p(jm), len(z), _p(z), int(quasi), cap,
+                                     rows.ctypes.data_as(c_int_p), cols.ctypes.data_as(c_int_p), _p(vals))
+    order = np.lexsort((cols[:n], rows[:n]))
+    return rows[:n][order], cols[:n][order], vals[:n][order]
 
 
 def weight_alpha(cfg, pose, z, pred, corr):

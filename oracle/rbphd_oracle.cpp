@@ -952,9 +952,10 @@ double log_sum_exp(const double* v, int begin, int end)
     return mx + std::log(value);
 }
 
-/* PHD:415-453 */
+/* PHD:415-453; quasi = the matrix of QuasiSetLogLikelihood (PHD:561-640): every landmark fully visible
+ * (zprobs weight 1, log PD / log(1 - PD) constants) and the association gate d < 12 instead of d < 5 */
 Sparse set_loglike_matrix(const orc_config* c, const double* pose, int J, const double* jm, int M,
-                          const double* z)
+                          const double* z, bool quasi = false)
 {
     const int dz = meas_dim(c);
     Sparse logprobs(J + M, J + M, -kInf);
@@ -963,23 +964,34 @@ Sparse set_loglike_matrix(const orc_config* c, const double* pose, int J, const 
     for (int i = 0; i < J; i++) {
         double ml[3];
         measure_perfect(c, pose, jm + 3 * i, ml);
-        zprobs[i] = make_gaussian(ml, c->R, detection_probability_m(c, ml), dz);
+        zprobs[i] = make_gaussian(ml, c->R, quasi ? 1.0 : detection_probability_m(c, ml), dz);
     }
-    for (int i = 0; i < J; i++)
-        for (int k = 0; k < M; k++) {
-            double d = mahalanobis(zprobs[i], z + 3 * k);
-            if (d < 5) logprobs.set(i, k, std::log(zprobs[i].w) + std::log(zprobs[i].mult) - 0.5 * d * d);
-        }
-    for (int i = 0; i < J; i++) logprobs.set(i, M + i, std::log(1 - zprobs[i].w));
+    if (quasi) {
+        const double logPD = std::log(c->pd), log1PD = std::log(1 - c->pd);
+        for (int i = 0; i < J; i++)
+            for (int k = 0; k < M; k++) {
+                double d = mahalanobis(zprobs[i], z + 3 * k);
+                if (d < 12) logprobs.set(i, k, logPD + std::log(zprobs[i].mult) - 0.5 * d * d);
+            }
+        for (int i = 0; i < J; i++) logprobs.set(i, M + i, log1PD);
+    }
+    else {
+        for (int i = 0; i < J; i++)
+            for (int k = 0; k < M; k++) {
+                double d = mahalanobis(zprobs[i], z + 3 * k);
+                if (d < 5) logprobs.set(i, k, std::log(zprobs[i].w) + std::log(zprobs[i].mult) - 0.5 * d * d);
+            }
+        for (int i = 0; i < J; i++) logprobs.set(i, M + i, std::log(1 - zprobs[i].w));
+    }
     for (int i = 0; i < M; i++) logprobs.set(J + i, i, logclutter);
     return logprobs;
 }
 
-/* PHD:462-515, including the stale-buffer early exit (quirk A9.4) */
+/* PHD:462-515, including the stale-buffer early exit (quirk A9.4); quasi: PHD:561-713 without the gradient */
 double set_loglikelihood(const orc_config* c, const double* pose, int J, const double* jm, int M,
-                         const double* z)
+                         const double* z, bool quasi = false)
 {
-    Sparse llmatrix = set_loglike_matrix(c, pose, J, jm, M, z);
+    Sparse llmatrix = set_loglike_matrix(c, pose, J, jm, M, z, quasi);
     std::vector<Sparse> connected = connected_components(llmatrix);
     double logcomp[200];
     for (int i = 0; i < 200; i++) logcomp[i] = 0;
@@ -1305,6 +1317,23 @@ double orc_set_loglikelihood(const orc_config* c, const double* pose, int J, con
                              const double* z)
 {
     return set_loglikelihood(c, pose, J, jm, M, z);
+}
+double orc_quasi_set_loglikelihood(const orc_config* c, const double* pose, int J, const double* jm, int M,
+                                   const double* z)
+{
+    return set_loglikelihood(c, pose, J, jm, M, z, true);
+}
+int orc_set_loglike_matrix(const orc_config* c, const double* pose, int J, const double* jm, int M, const double* z,
+                           int quasi, int cap, int* rows, int* cols, double* vals)
+{
+    Sparse mx = set_loglike_matrix(c, pose, J, jm, M, z, quasi != 0);
+    int n = 0;
+    for (const SparseRow& r : mx.rows)
+        for (const auto& it : r.items) {
+            if (n < cap) { rows[n] = r.key; cols[n] = it.first; vals[n] = it.second; }
+            n++;
+        }
+    return n;
 }
 void orc_weight_alpha(const orc_config* c, const double* pose, int M, const double* z, int np,
                       const double* pw, const double* pm, const double* pP, int nc, const double* cw,

@@ -86,6 +86,12 @@ int orc_prune(const orc_config* c, int n, const double* w, const double* m, cons
 int orc_best_map_estimate(int n, const double* w, int cap, int* picks);
 double orc_set_loglikelihood(const orc_config* c, const double* pose, int J, const double* jm, int M,
                              const double* z);
+/* PHD:526-532, 561-713 (value only): full visibility, gate d < 12 */
+double orc_quasi_set_loglikelihood(const orc_config* c, const double* pose, int J, const double* jm, int M,
+                                   const double* z);
+/* PHD:415-460 (quasi: PHD:561-640) as triplets in insertion order; returns the number of entries */
+int orc_set_loglike_matrix(const orc_config* c, const double* pose, int J, const double* jm, int M, const double* z,
+                           int quasi, int cap, int* rows, int* cols, double* vals);
 /* out[0]=alpha, out[1]=setloglik, out[2]=ploglik, out[3]=cloglik, out[4]=pcount, out[5]=ccount, out[6]=J */
 void orc_weight_alpha(const orc_config* c, const double* pose, int M, const double* z, int np,
                       const double* pw, const double* pm, const double* pP, int nc, const double* cw,

@@ -1,0 +1,123 @@
+"""Boundary entry points added in round 2, through the C ABI against the oracle: the static likelihood functions
+of PHDNavigator (SetLikelihood, SetLogLikeMatrix, QuasiSetLogLikelihood: PHD:395-460, 526-713) and the two-step
+SlamUpdate that lets the host draw the wheel's uniform only when the reference does (PHD:355-357, 727)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from monorfs_b200 import capi as c
+    return c
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import orc as o
+    return o
+
+
+@pytest.fixture(scope="module")
+def synth():
+    from monorfs_b200 import synth as s
+    return s
+
+
+@pytest.fixture(scope="module")
+def ctx(capi, orc, synth):
+    sc = synth.make_scene(4, 40, 16, seed=3)
+    h = capi.Handle(sc.params, max_particles=4, max_components=256, max_measurements=64, max_pairs=2048)
+    h.reset(4, sc.poses[0], sc.map_w, sc.map_m, sc.map_P)
+    yield dict(h=h, sc=sc, ocfg=orc.make_config(sc.params))
+    h.close()
+
+
+def scenes(ctx, orc):
+    """(pose, landmarks, measurements) cases: the scene's own frame, competing landmarks, dense random blocks."""
+    sc, ocfg = ctx["sc"], ctx["ocfg"]
+    fr = sc.next_frame()
+    yield sc.poses[0], sc.map_m, fr.z
+    yield sc.poses[1], sc.map_m[:7], fr.z
+    yield sc.poses[0], sc.map_m[:0], fr.z
+    pose = [0, 0, 0, 1, 0, 0, 0]
+    lm = np.array([[0.2, 0.1, 3.0], [0.21, 0.1, 3.0], [-1.0, 0.5, 5.0]])
+    z = np.array([orc.measure_perfect(ocfg, pose, l) for l in lm])
+    yield pose, lm, np.concatenate([z + [0.5, -0.5, 0.01], [[100.0, 100.0, 4.0]]])
+    for seed in range(4):
+        rng = np.random.default_rng(300 + seed)
+        J, M = 18, 14
+        zc = np.stack([rng.uniform(-60, 60, J), rng.uniform(-40, 40, J), rng.uniform(2.0, 2.8, J)], axis=1)
+        lms = np.array([orc.measure_to_map(ocfg, pose, zz) for zz in zc])
+        zs = zc[rng.integers(0, J, M)] + rng.normal(size=(M, 3)) * [2.5, 2.5, 0.05]
+        yield pose, lms, zs
+
+
+def test_quasi_set_loglikelihood(ctx, orc):
+    """Full visibility, gate d < 12: wider blocks than SetLogLikelihood on the same inputs (PHD:561-713)."""
+    h, ocfg = ctx["h"], ctx["ocfg"]
+    n = 0
+    for pose, lm, z in scenes(ctx, orc):
+        exp = orc.quasi_set_loglikelihood(ocfg, pose, lm, z)
+        got = h.quasi_set_loglikelihood(pose, lm, z)
+        assert np.isfinite(exp)
+        assert abs(got - exp) <= RTOL * max(1.0, abs(exp)), (n, got, exp)
+        n += 1
+    assert n >= 8
+
+
+def test_set_likelihood_is_exp_of_the_log(ctx, orc):
+    h, ocfg = ctx["h"], ctx["ocfg"]
+    for pose, lm, z in scenes(ctx, orc):
+        exp = np.exp(orc.set_loglikelihood(ocfg, pose, lm, z))
+        got = h.set_likelihood(pose, lm, z)
+        assert abs(got - exp) <= 1e-9 * abs(exp) + 1e-300, (got, exp)
+
+
+def test_set_loglike_matrix(ctx, orc):
+    """Same entries at the same (row, column) positions as the reference's SparseMatrix (PHD:415-460)."""
+    h, ocfg = ctx["h"], ctx["ocfg"]
+    for pose, lm, z in scenes(ctx, orc):
+        er, ec, ev = orc.set_loglike_matrix(ocfg, pose, lm, z)
+        gr, gc, gv = h.set_loglike_matrix(pose, lm, z)
+        assert np.array_equal(gr, er) and np.array_equal(gc, ec)
+        assert np.allclose(gv, ev, rtol=RTOL, atol=0)
+        assert len(gr) >= len(lm) + len(z)   # one miss entry per landmark, one clutter entry per measurement
+
+
+@pytest.mark.parametrize("meff", [0.95, 0.05])
+def test_two_step_slam_update_equals_one_step(capi, synth, meff):
+    """_begin reports ParticleDepleted; _finish(u) runs the wheel: identical to rbphd_slam_update(u)."""
+    P, N, M = 12, 50, 20
+    sc = synth.make_scene(P, N, M, seed=11, min_effective_particle=meff)
+    frames = [sc.next_frame() for _ in range(5)]
+    a = capi.Handle(sc.params, max_particles=P, max_components=256, max_measurements=M)
+    b = capi.Handle(sc.params, max_particles=P, max_components=256, max_measurements=M)
+    for h in (a, b):
+        h.reset(P, sc.poses[0], sc.map_w, sc.map_m, sc.map_P)
+        h.set_poses(sc.poses)
+    ndep = 0
+    for fr in frames:
+        a.update(fr.reading, synth.DT, fr.gauss)
+        b.update(fr.reading, synth.DT, fr.gauss)
+        best1, res1 = a.slam_update(fr.z, fr.u)
+        best2, dep = b.slam_update_begin(fr.z)
+        assert dep == res1
+        if dep:
+            ndep += 1
+            best2 = b.slam_update_finish(fr.u)
+        else:
+            assert b.slam_update_finish(fr.u) == best2     # no-op
+        assert best2 == best1
+        assert np.allclose(a.get_weights(), b.get_weights(), rtol=1e-12, atol=0)   # (Map.Evaluate sums use atomics)
+        assert np.array_equal(a.get_ancestors(), b.get_ancestors())
+        assert np.array_equal(a.get_poses(), b.get_poses())
+        assert np.array_equal(a.get_map_counts(), b.get_map_counts())
+        for i in range(P):
+            for x, y in zip(a.get_map(i), b.get_map(i)):
+                assert np.array_equal(x, y)
+    assert (ndep > 0) == (meff > 0.5)
+    a.close()
+    b.close()

@@ -22,7 +22,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for (P, N, M, frames, seed, meff) in [(64, 60, 24, 8, 5, 0.5), (96, 150, 48, 5, 6, 0.3)]:
+    # (the third case has an uneven block partition: 97 particles)
+    for (P, N, M, frames, seed, meff) in [(64, 60, 24, 8, 5, 0.5), (96, 150, 48, 5, 6, 0.3), (97, 60, 24, 6, 9, 0.5)]:
         sc = synth.make_scene(P, N, M, seed=seed, min_effective_particle=meff)
         fr = [sc.next_frame() for _ in range(frames)]
         lo, hi = sharded.block_range(rank, world, P)
