@@ -8,6 +8,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <mutex>
 #include <cstdio>
@@ -55,6 +56,7 @@ struct rbphd_navigator {
     int* counts[2] = {nullptr, nullptr};
     double *poses = nullptr, *poses_tmp = nullptr, *weights = nullptr, *alphas = nullptr, *alpha_parts = nullptr;
     double *z = nullptr, *gauss = nullptr, *pts = nullptr;
+    double* cumw = nullptr;       // maxP + 1: prefix sums of the wheel
     int* ancestors = nullptr;
     DeviceState* st = nullptr;
     FrameGrid *vgrid = nullptr, *zgrid = nullptr;
@@ -67,6 +69,7 @@ struct rbphd_navigator {
     void* comm = nullptr;         // ncclComm_t
     int rank = 0, world = 1, total = 0;
     double* gweights = nullptr;   // all ranks' weights in rank order
+    double* gcum = nullptr;       // total + 1: prefix sums of the wheel over the global vector
     int *ganc = nullptr, *gcounts = nullptr;
     int *local_src = nullptr, *send_idx = nullptr;
     long long *rec_off = nullptr, *send_off = nullptr, *plan_hdr = nullptr;
@@ -240,7 +243,7 @@ void free_device(rbphd_navigator* nav)
     for (int b = 0; b < 2; b++) { cudaFree(nav->maps[b]); cudaFree(nav->counts[b]); }
     cudaFree(nav->poses); cudaFree(nav->poses_tmp); cudaFree(nav->weights); cudaFree(nav->alphas);
     cudaFree(nav->alpha_parts); cudaFree(nav->z); cudaFree(nav->gauss); cudaFree(nav->pts);
-    cudaFree(nav->ancestors); cudaFree(nav->st); cudaFree(nav->vgrid); cudaFree(nav->zgrid);
+    cudaFree(nav->ancestors); cudaFree(nav->cumw); cudaFree(nav->st); cudaFree(nav->vgrid); cudaFree(nav->zgrid);
     cudaFree(nav->vitems); cudaFree(nav->zitems); cudaFree(nav->scratch); cudaFree(nav->dump);
     cudaFree(nav->dump_count);
     for (auto& e : nav->pev) cudaEventDestroy(e);
@@ -471,6 +474,7 @@ rbphd_navigator* rbphd_new(const rbphd_config* config, const rbphd_limits* limit
     CKN(cudaMalloc(&nav->gauss, sizeof(double) * nav->gstride * nav->slots));
     CKN(cudaMalloc(&nav->pts, sizeof(double) * 6 * nav->Mcap + 64));
     CKN(cudaMalloc(&nav->ancestors, sizeof(int) * nav->maxP));
+    CKN(cudaMalloc(&nav->cumw, sizeof(double) * ((size_t)nav->maxP + 1)));
     CKN(cudaMalloc(&nav->st, sizeof(DeviceState)));
     CKN(cudaMemsetAsync(nav->st, 0, sizeof(DeviceState), nav->stream));
     CKN(cudaMemsetAsync(nav->alphas, 0, sizeof(double) * nav->maxP, nav->stream));
@@ -768,7 +772,7 @@ static int enqueue_slam_tail(rbphd_navigator* nav, int only_mapping, double u, i
         if (ev) { cudaEventRecord(ev[0], nav->stream); cudaEventRecord(ev[1], nav->stream); }
     }
     else {
-        launch_normalize_resample(nav->stream, nav->dcfg, nav->P, nav->weights, u, force, nav->ancestors, nav->st);
+        launch_normalize_resample(nav->stream, nav->dcfg, nav->P, nav->weights, u, force, nav->ancestors, nav->st, nav->cumw);
         if (ev) cudaEventRecord(ev[0], nav->stream);
         launch_copy_particles(nav->stream, nav->P, nav->cap, nav->maps, nav->counts, nav->poses, nav->poses_tmp,
                               nav->ancestors, nav->st);
@@ -841,7 +845,7 @@ int rbphd_slam_update_begin(rbphd_navigator* nav, const double* z, int m, int on
     if (int r = enqueue_map_update(nav, m, only_mapping, MODE_FRAME)) return r;
     if (only_mapping) { launch_flip(nav->stream, nav->st); nav->launches += 1; }
     else {
-        launch_normalize_resample(nav->stream, nav->dcfg, nav->P, nav->weights, 0.0, 3, nav->ancestors, nav->st);
+        launch_normalize_resample(nav->stream, nav->dcfg, nav->P, nav->weights, 0.0, 3, nav->ancestors, nav->st, nav->cumw);
         nav->launches += 1;
     }
     if (int r = check_async(nav, "slam update (begin)")) return r;
@@ -865,7 +869,7 @@ int rbphd_slam_update_finish(rbphd_navigator* nav, double u_resample, int* best)
     if (int r = set_device(nav)) return r;
     if (nav->pending_wheel) {
         nav->pending_wheel = 0;
-        launch_normalize_resample(nav->stream, nav->dcfg, nav->P, nav->weights, u_resample, 2, nav->ancestors, nav->st);
+        launch_normalize_resample(nav->stream, nav->dcfg, nav->P, nav->weights, u_resample, 2, nav->ancestors, nav->st, nav->cumw);
         launch_copy_particles(nav->stream, nav->P, nav->cap, nav->maps, nav->counts, nav->poses, nav->poses_tmp,
                               nav->ancestors, nav->st);
         nav->launches += 3;
@@ -889,7 +893,7 @@ int rbphd_resample(rbphd_navigator* nav, double u_resample)
     }
     // the copy kernel moves particles from buffer 1-cur to buffer cur: make the current maps "1-cur" first
     launch_flip(nav->stream, nav->st);
-    launch_normalize_resample(nav->stream, nav->dcfg, nav->P, nav->weights, u_resample, 2, nav->ancestors, nav->st);
+    launch_normalize_resample(nav->stream, nav->dcfg, nav->P, nav->weights, u_resample, 2, nav->ancestors, nav->st, nav->cumw);
     launch_copy_particles(nav->stream, nav->P, nav->cap, nav->maps, nav->counts, nav->poses, nav->poses_tmp,
                           nav->ancestors, nav->st);
     nav->launches += 4;
@@ -1179,10 +1183,10 @@ void comm_free(rbphd_navigator* nav)
     if (nav->stream) cudaStreamSynchronize(nav->stream);
     nccl_api()->CommDestroy((ncclComm_t)nav->comm);
     nav->comm = nullptr;
-    cudaFree(nav->gweights); cudaFree(nav->ganc); cudaFree(nav->gcounts); cudaFree(nav->local_src);
+    cudaFree(nav->gweights); cudaFree(nav->gcum); cudaFree(nav->ganc); cudaFree(nav->gcounts); cudaFree(nav->local_src);
     cudaFree(nav->rec_off); cudaFree(nav->send_idx); cudaFree(nav->send_off); cudaFree(nav->plan_hdr);
     cudaFree(nav->sendbuf); cudaFree(nav->recvbuf);
-    nav->gweights = nullptr; nav->ganc = nullptr; nav->gcounts = nullptr; nav->local_src = nullptr;
+    nav->gweights = nullptr; nav->gcum = nullptr; nav->ganc = nullptr; nav->gcounts = nullptr; nav->local_src = nullptr;
     nav->rec_off = nullptr; nav->send_idx = nullptr; nav->send_off = nullptr; nav->plan_hdr = nullptr;
     nav->sendbuf = nullptr; nav->recvbuf = nullptr;
     nav->world = 1; nav->rank = 0; nav->total = 0;
@@ -1217,7 +1221,7 @@ int comm_slam_tail(rbphd_navigator* nav, double u, cudaEvent_t* ev)
     ncclComm_t comm = (ncclComm_t)nav->comm;
     const int world = nav->world, rank = nav->rank, total = nav->total;
     if (int r = comm_allgather<double>(nav, nav->weights, nav->gweights, ncclDouble)) return r;
-    launch_normalize_resample(nav->stream, nav->dcfg, total, nav->gweights, u, 0, nav->ganc, nav->st);
+    launch_normalize_resample(nav->stream, nav->dcfg, total, nav->gweights, u, 0, nav->ganc, nav->st, nav->gcum);
     const int lo = part_lo_host(rank, world, total);
     CK(cudaMemcpyAsync(nav->weights, nav->gweights + lo, sizeof(double) * (size_t)nav->P, cudaMemcpyDeviceToDevice,
                        nav->stream));
@@ -1229,14 +1233,26 @@ int comm_slam_tail(rbphd_navigator* nav, double u, cudaEvent_t* ev)
     nav->last_best = st.best;
     nav->last_resampled = st.resampled;
     if (st.resampled) {
+        static const bool trace = std::getenv("RBPHD_COMM_TRACE") != nullptr;   // debugging: per-step wall times
+        auto t_prev = std::chrono::steady_clock::now();
+        auto lap = [&](const char* what) {
+            if (!trace) return;
+            cudaStreamSynchronize(nav->stream);
+            auto now = std::chrono::steady_clock::now();
+            std::fprintf(stderr, "[rbphd comm rank %d] %-16s %8.3f ms\n", rank, what,
+                         std::chrono::duration<double, std::milli>(now - t_prev).count());
+            t_prev = now;
+        };
         const int post = 1 - st.cur;   // the wheel does not publish: the posterior maps are in buffer 1-cur
         if (int r = comm_allgather<int>(nav, nav->counts[post], nav->gcounts, ncclInt32)) return r;
+        lap("allgather counts");
         launch_migration_plan(nav->stream, nav->ganc, nav->gcounts, total, world, rank, nav->local_src, nav->rec_off,
                               nav->send_idx, nav->send_off, nav->plan_hdr);
         long long* hdr = (long long*)nav->h_plan.get(sizeof(long long) * (2 * kMaxCommRanks + 4));
         if (!hdr) return fail(nav, RBPHD_ERR_CUDA, "pinned allocation failed");
         CK(cudaMemcpyAsync(hdr, nav->plan_hdr, sizeof(long long) * (2 * world + 3), cudaMemcpyDeviceToHost, nav->stream));
         CK(cudaStreamSynchronize(nav->stream));
+        lap("plan");
         if (!hdr[2 * world + 2]) return fail(nav, RBPHD_ERR_GENERIC, "migration plan: ancestors are not sorted");
         long long send_total = 0, recv_total = 0;
         for (int r = 0; r < world; r++) { send_total += hdr[r]; recv_total += hdr[world + r]; }
@@ -1244,6 +1260,7 @@ int comm_slam_tail(rbphd_navigator* nav, double u, cudaEvent_t* ev)
             return fail(nav, RBPHD_ERR_CAPACITY, "migration buffers too small");
         launch_pack_records(nav->stream, nav->cap, nav->maps[post], nav->counts[post], nav->poses, nav->send_idx,
                             nav->send_off, (int)hdr[2 * world], nav->sendbuf);
+        lap("pack");
         CKNCCL(nc->GroupStart());
         long long soff = 0, roff = 0;
         for (int r = 0; r < world; r++) {
@@ -1253,9 +1270,11 @@ int comm_slam_tail(rbphd_navigator* nav, double u, cudaEvent_t* ev)
             roff += hdr[world + r];
         }
         CKNCCL(nc->GroupEnd());
+        lap("send/recv");
         launch_unpack_records(nav->stream, nav->P, nav->cap, nav->maps[post], nav->counts[post], nav->maps[st.cur],
                               nav->counts[st.cur], nav->poses, nav->poses_tmp, nav->local_src, nav->rec_off, nav->recvbuf);
         launch_copy_doubles(nav->stream, 7 * (size_t)nav->P, nav->poses, nav->poses_tmp);
+        lap("unpack");
         nav->launches += 4;
         nav->comm_resamples += 1;
         nav->comm_sent_bytes += 8 * send_total;
@@ -1305,6 +1324,7 @@ int rbphd_comm_init_rank(rbphd_navigator* nav, const unsigned char id128[128], i
     nav->sendcap = rec * ((size_t)nav->P + world);
     nav->recvcap = rec * (size_t)nav->P;
     CK(cudaMalloc(&nav->gweights, sizeof(double) * (size_t)total_particles));
+    CK(cudaMalloc(&nav->gcum, sizeof(double) * ((size_t)total_particles + 1)));
     CK(cudaMalloc(&nav->ganc, sizeof(int) * (size_t)total_particles));
     CK(cudaMalloc(&nav->gcounts, sizeof(int) * (size_t)total_particles));
     CK(cudaMalloc(&nav->local_src, sizeof(int) * (size_t)nav->P));
@@ -1317,6 +1337,25 @@ int rbphd_comm_init_rank(rbphd_navigator* nav, const unsigned char id128[128], i
     if (!nav->h_plan.get(sizeof(long long) * (2 * kMaxCommRanks + 4))) return fail(nav, RBPHD_ERR_CUDA, "pinned allocation failed");
     // the reference starts every particle at 1 / P_total (PHD:245-266), whatever the size of this rank's block
     launch_fill_doubles(nav->stream, (size_t)nav->P, nav->weights, 1.0 / total_particles);
+    // NCCL connects its point-to-point channels lazily, a few hundred ms each the first time a channel to a peer
+    // carries data (measured: every other exchange of the first dozen).  Pay that here, not in a resampling
+    // frame: a few all-to-all rounds over the (still empty) exchange buffers, sized to use every channel.
+    if (world > 1) {
+        size_t warm = std::min(nav->sendcap, nav->recvcap) / (size_t)world;
+        warm = std::min(warm, (size_t)8 << 20);   // 64 MB per peer
+        if (warm > 0) {
+            CK(cudaMemsetAsync(nav->sendbuf, 0, sizeof(double) * warm * (size_t)world, nav->stream));
+            for (int rep = 0; rep < 16; rep++) {
+                CKNCCL(nc->GroupStart());
+                for (int r = 0; r < world; r++) {
+                    if (r == rank) continue;
+                    CKNCCL(nc->Send(nav->sendbuf + warm * (size_t)r, warm, ncclDouble, r, comm, nav->stream));
+                    CKNCCL(nc->Recv(nav->recvbuf + warm * (size_t)r, warm, ncclDouble, r, comm, nav->stream));
+                }
+                CKNCCL(nc->GroupEnd());
+            }
+        }
+    }
     CK(cudaStreamSynchronize(nav->stream));
     nav->comm_resamples = nav->comm_sent_bytes = nav->comm_recv_bytes = nav->comm_records = 0;
     return RBPHD_OK;

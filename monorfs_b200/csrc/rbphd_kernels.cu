@@ -1400,21 +1400,59 @@ __global__ void __launch_bounds__(kBlock) k_frame_prep(DevCfg cfg, const double*
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight normalisation, best particle, ESS test, systematic wheel (PHD:343-358, 724-777).
-// One CTA.  The reference's sums and the wheel are running floating-point recurrences; they are
-// replayed serially by thread 0 (tiles staged through shared memory) so that ancestors are bit-exact.
+// weight normalisation, best particle, ESS test, systematic wheel (PHD:343-358, 724-777).  One CTA.
+// The reference's sums and the wheel are running floating-point recurrences.  The sums are taken here as
+// fixed-order tree sums (deterministic; they differ from the in-order sums by a few ulps, far inside the
+// 1e-9 bar on weights -- the weights already carry ~1e-15 of summation-order noise from Map.Evaluate).
+// The wheel's DECISIONS must be exact: ancestor(i) = (number of prefix sums C_k = w_0 + .. + w_{k-1} below
+// T_i = u/P + i/P) - 1 is found by a binary search over parallel prefix sums, and every decision is checked
+// against a rigorous bound on what the reference's interleaved recurrence (random -= w[k]; random += 1/P)
+// can differ from C_k and T_i by; if any T_i comes that close to a prefix sum, the whole wheel is replayed
+// serially, operation by operation (thread 0, tiles staged through shared memory).
 // ------------------------------------------------------------------------------------------------
 constexpr int kTile = 4096;
 
+__device__ __forceinline__ double block_sum_ordered(double* warp_part, double v)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) warp_part[warp] = v;
+    __syncthreads();
+    double s = 0;
+    for (int w = 0; w < kWarps; w++) s += warp_part[w];
+    return s;
+}
+
+// (value, index) maximum with the lowest index among equal values; returns the winner to every thread
+__device__ __forceinline__ void block_argmax_first(double* warp_w, int* warp_i, double& bw, int& bi)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ow = __shfl_down_sync(0xffffffffu, bw, o);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+        if (ow > bw || (ow == bw && oi < bi)) { bw = ow; bi = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { warp_w[warp] = bw; warp_i[warp] = bi; }
+    __syncthreads();
+    bw = warp_w[0]; bi = warp_i[0];
+    for (int w = 1; w < kWarps; w++)
+        if (warp_w[w] > bw || (warp_w[w] == bw && warp_i[w] < bi)) { bw = warp_w[w]; bi = warp_i[w]; }
+}
+
 __global__ void __launch_bounds__(kBlock) k_normalize_resample(DevCfg cfg, int P, double* weights, double u,
-                                                              int force, int* ancestors, DeviceState* st)
+                                                              int force, int* ancestors, DeviceState* st,
+                                                              double* cum)
 {
     __shared__ double tile[kTile];
-    __shared__ double s_sum, s_cum;
-    __shared__ int s_best, s_dep;
+    __shared__ double s_part[kWarps + 1];
     __shared__ double s_maxw[kWarps];
     __shared__ int s_maxi[kWarps];
-    const int tid = threadIdx.x;
+    __shared__ int s_best, s_dep;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // a capacity error in this frame's map update (status bits set by k_particle_update): the frame's results
     // are not trustworthy -- leave the weights un-normalised, do not resample, do not publish the new maps;
@@ -1424,49 +1462,30 @@ __global__ void __launch_bounds__(kBlock) k_normalize_resample(DevCfg cfg, int P
         if (tid == 0) { st->resampled = 0; st->depleted = 0; }
         return;
     }
+    // every thread owns a contiguous run of particles
+    const int per = (P + kBlock - 1) / kBlock;
+    const int i0 = min(P, tid * per), i1 = min(P, i0 + per);
 
     if (force != 2) {
-        // sum (serial order)
-        if (tid == 0) s_sum = 0;
-        for (int base = 0; base < P; base += kTile) {
-            int n = min(kTile, P - base);
-            for (int i = tid; i < n; i += kBlock) tile[i] = weights[base + i];
-            __syncthreads();
-            if (tid == 0) { double sacc = s_sum; for (int i = 0; i < n; i++) sacc += tile[i]; s_sum = sacc; }
-            __syncthreads();
-        }
-        double sum = s_sum;
+        double part = 0;
+        for (int i = i0; i < i1; i++) part += weights[i];
+        double sum = block_sum_ordered(s_part, part);
         sum = (sum == 0) ? 1 : sum;
-        // normalise, first-maximum argmax (strict >, starting from 0: PHD:347-354)
-        double bw = 0; int bi = 0x7fffffff;
-        for (int i = tid; i < P; i += kBlock) {
-            double w = weights[i] / sum;
+        // normalise, first-maximum argmax (strict >, starting from 0: PHD:347-354), ESS (PHD:768-777)
+        double bw = 0, sq = 0;
+        int bi = 0x7fffffff;
+        for (int i = i0; i < i1; i++) {
+            const double w = weights[i] / sum;
             weights[i] = w;
+            sq += w * w;
             if (w > bw) { bw = w; bi = i; }
         }
-        for (int o = 16; o > 0; o >>= 1) {
-            double ow = __shfl_down_sync(0xffffffffu, bw, o);
-            int oi = __shfl_down_sync(0xffffffffu, bi, o);
-            if (ow > bw || (ow == bw && oi < bi)) { bw = ow; bi = oi; }
-        }
-        if ((tid & 31) == 0) { s_maxw[tid >> 5] = bw; s_maxi[tid >> 5] = bi; }
-        __syncthreads();
+        block_argmax_first(s_maxw, s_maxi, bw, bi);
+        const double cumsq = block_sum_ordered(s_part, sq);
         if (tid == 0) {
-            for (int w = 1; w < kWarps; w++)
-                if (s_maxw[w] > bw || (s_maxw[w] == bw && s_maxi[w] < bi)) { bw = s_maxw[w]; bi = s_maxi[w]; }
             s_best = (bw > 0 && bi != 0x7fffffff) ? bi : st->best;
-            s_cum = 0;
+            s_dep = ((1.0 / cumsq < cfg.min_eff * P) || force == 1) ? 1 : 0;
         }
-        __syncthreads();
-        // ESS (PHD:768-777)
-        for (int base = 0; base < P; base += kTile) {
-            int n = min(kTile, P - base);
-            for (int i = tid; i < n; i += kBlock) tile[i] = weights[base + i];
-            __syncthreads();
-            if (tid == 0) { double cacc = s_cum; for (int i = 0; i < n; i++) cacc += tile[i] * tile[i]; s_cum = cacc; }
-            __syncthreads();
-        }
-        if (tid == 0) s_dep = ((1.0 / s_cum < cfg.min_eff * P) || force == 1) ? 1 : 0;
         __syncthreads();
     }
     else {
@@ -1487,7 +1506,77 @@ __global__ void __launch_bounds__(kBlock) k_normalize_resample(DevCfg cfg, int P
         if (tid == 0) { st->best = s_best; st->resampled = 0; st->depleted = 1; }
         return;
     }
-    // systematic wheel (PHD:724-760), serial
+
+    // ---- systematic wheel (PHD:724-760) ----
+    const double invP = 1.0 / P;
+    int ambiguous = 0;
+    // exclusive prefix sums C_k of the normalised weights: cum[k] = w_0 + .. + w_{k-1}, cum[P] = total
+    double wmax = 0;
+    {
+        double part = 0;
+        for (int i = i0; i < i1; i++) { const double w = weights[i]; part += w; wmax = fmax(wmax, fabs(w)); }
+        double incl = part;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        __syncthreads();
+        if (lane == 31) s_part[warp] = incl;
+        __syncthreads();
+        if (tid == 0) {
+            double run = 0;
+            for (int w = 0; w < kWarps; w++) { const double t = s_part[w]; s_part[w] = run; run += t; }
+            s_part[kWarps] = run;
+        }
+        __syncthreads();
+        double c = s_part[warp] + (incl - part);
+        for (int i = i0; i < i1; i++) { cum[i] = c; c += weights[i]; }
+        if (i1 == P && i0 < P) cum[P] = c;
+        const double total = s_part[kWarps];
+        if (!(total == total) || isinf(total) || !(u == u)) ambiguous = 1;   // NaN / inf: the serial replay decides
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wmax = fmax(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        __syncthreads();
+        if (lane == 0) s_maxw[warp] = wmax;
+        __syncthreads();
+        for (int w = 0; w < kWarps; w++) wmax = fmax(wmax, s_maxw[w]);
+    }
+    __syncthreads();
+    // The reference's `random` after any number of steps is (u/P + i/P - C_k) up to the rounding of at most 2P + 2
+    // additions of values bounded by 1/P + wmax, and C_k / T_i here carry at most P roundings each: margin
+    const double delta = 8.0 * 2.220446049250313e-16 * ((double)P + 64.0) * (invP + wmax + 1.0 * invP) + 1e-300;
+    const double start = u / P;
+    double bw = 0;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < P; i += kBlock) {
+        const double T = start + (double)i * invP;
+        // k = number of weights consumed once particle i is served = smallest k in [0, P] with C_k >= T
+        int lo = 0, hi = P + 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cum[mid] >= T) hi = mid; else lo = mid + 1;
+        }
+        const int k = min(lo, P);
+        if (k <= P && fabs(cum[k] - T) <= delta) ambiguous = 1;
+        if (k > 0 && fabs(cum[k - 1] - T) <= delta) ambiguous = 1;
+        const int a = (k == 0) ? 0 : k - 1;
+        ancestors[i] = a;
+        const double wa = weights[a];
+        if (wa > bw) { bw = wa; bi = i; }   // PHD:745-748: first new particle whose ancestor has the largest weight
+    }
+    if (!__syncthreads_or(ambiguous)) {
+        block_argmax_first(s_maxw, s_maxi, bw, bi);
+        __syncthreads();
+        for (int i = tid; i < P; i += kBlock) weights[i] = invP;
+        if (tid == 0) {
+            st->best = (bw > 0 && bi != 0x7fffffff) ? bi : s_best;
+            st->resampled = 1; st->depleted = 1;
+        }
+        return;
+    }
+
+    // ---- serial replay (some T_i within rounding distance of a prefix sum, or non-finite weights) ----
     __shared__ double s_random, s_maxweight;
     __shared__ int s_k, s_i, s_newbest;
     if (tid == 0) { s_random = u / P; s_maxweight = 0; s_k = 0; s_i = 0; s_newbest = s_best; }
@@ -1500,7 +1589,6 @@ __global__ void __launch_bounds__(kBlock) k_normalize_resample(DevCfg cfg, int P
         if (tid == 0) {
             double random = s_random, maxweight = s_maxweight;
             int k = s_k, i = s_i, nb = s_newbest;
-            const double invP = 1.0 / P;
             const bool last_tile = (base + n >= P);
             while (i < P) {
                 // inner loop of PHD:736: consume weights while random > 0
@@ -1819,9 +1907,9 @@ void launch_particle_update(cudaStream_t s, const KParams& prm, int grid, size_t
 }
 
 void launch_normalize_resample(cudaStream_t s, const DevCfg& cfg, int P, double* weights, double u, int force,
-                               int* ancestors, DeviceState* st)
+                               int* ancestors, DeviceState* st, double* cum)
 {
-    k_normalize_resample<<<1, kBlock, 0, s>>>(cfg, P, weights, u, force, ancestors, st);
+    k_normalize_resample<<<1, kBlock, 0, s>>>(cfg, P, weights, u, force, ancestors, st, cum);
 }
 
 void launch_copy_particles(cudaStream_t s, int P, int cap, double* const maps[2], int* const counts[2],

@@ -96,8 +96,9 @@ void launch_frame_prep(cudaStream_t s, const DevCfg& cfg, const double* z, int M
 void launch_particle_update(cudaStream_t s, const KParams& prm, int grid, size_t smem);
 // force: 0 = SlamUpdate tail (PHD:343-358); 1 = same but always resample; 2 = ResampleParticles() alone (PHD:724-760);
 // 3 = SlamUpdate tail up to the depletion decision (the wheel follows later with force = 2)
+// cum: P + 1 doubles of scratch (prefix sums of the wheel)
 void launch_normalize_resample(cudaStream_t s, const DevCfg& cfg, int P, double* weights, double u, int force,
-                               int* ancestors, DeviceState* st);
+                               int* ancestors, DeviceState* st, double* cum);
 void launch_copy_particles(cudaStream_t s, int P, int cap, double* const maps[2], int* const counts[2],
                            double* poses, double* poses_tmp, const int* ancestors, DeviceState* st);
 void launch_flip(cudaStream_t s, DeviceState* st);
