@@ -182,6 +182,81 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def run_sim_workload(args, device):
+    """BASELINE configs 1 and 5 around the GPU navigator (single GPU, host buffers every frame by construction):
+    c1 = `monorfs -i=simulation -f=map.world -c=movements.in -p=20 -x` on a synthesised scene / command file,
+    written out as data.zip in the reference's format and read back; c5 = a 1000-frame recorded run (data.zip)
+    replayed through a 1000-particle navigator (the recorded-run input path of the Loopy PHD processor; the
+    smoother itself stays in the C# host)."""
+    import tempfile
+    from monorfs_b200 import recordio, simulation, synth
+    tmp = tempfile.mkdtemp(prefix="monorfs_")
+    if args.workload == "c1":
+        P, n_lm, nfr = 20, 200, max(args.steps, 30)
+        pose0, measurer, landmarks = simulation.synthetic_scene(n_lm)
+        commands = simulation.synthetic_commands(nfr)
+        with open(os.path.join(tmp, "map.world"), "w") as fh:
+            fh.write(recordio.scene_to_text(pose0, measurer, landmarks, lossless=True))
+        with open(os.path.join(tmp, "movements.in"), "w") as fh:
+            fh.write(recordio.commands_to_text(commands))
+        pose0, measurer, landmarks = recordio.parse_scene(open(os.path.join(tmp, "map.world")).read())
+        commands = recordio.parse_commands(open(os.path.join(tmp, "movements.in")).read())
+        run = simulation.HeadlessRun(pose0, measurer, landmarks, commands, P, device=device)
+        rec = run.run()
+        secs, nres = run.gpu_seconds, run.resamples
+        run.close()
+        recordio.save(rec, os.path.join(tmp, "data.zip"))
+        back = recordio.load(os.path.join(tmp, "data.zip"))
+        ok = len(back.trajectory) == nfr and len(back.maps) == nfr and len(back.measurements) == nfr
+        comps = float(np.mean([len(m[1][0]) for m in rec.maps]))
+        meas = float(np.mean([len(z) for _, z in rec.measurements]))
+        extra = {"data_zip_round_trip": bool(ok), "data_zip_bytes": os.path.getsize(os.path.join(tmp, "data.zip")),
+                 "landmarks": n_lm, "mean_best_map_components": comps, "mean_measurements": meas}
+        # the same frames through the oracle (the CPU reference arm of this config)
+        cpu = None
+        if not args.no_cpu_baseline:
+            from oracle import orc
+            prm = synth.params(n_lm)
+            prm["measurer"] = [float(v) for v in measurer]
+            prm["nthreads"] = os.cpu_count() or 1
+            nav = orc.Navigator(orc.make_config(prm), P, pose0)
+            rng = np.random.default_rng(synth.SEED + 1)
+            t0 = time.perf_counter()
+            for (t, reading), (_, z) in zip(rec.odometry, rec.measurements):
+                nav.update(reading, synth.DT, rng.normal(size=(P, 6)))
+                nav.slam_update(z, float(rng.random()))
+            cs = time.perf_counter() - t0
+            nav.close()
+            cpu = {"value": P * nfr / cs, "unit": UNIT, "cores": min(P, os.cpu_count() or 1), "kind": "port",
+                   "sample": "all %d particles x %d frames of the recorded run" % (P, nfr)}
+    else:
+        P, n_lm, nfr = 1000, 200, 1000
+        pose0, measurer, landmarks = simulation.synthetic_scene(n_lm)
+        gen = simulation.HeadlessRun(pose0, measurer, landmarks, simulation.synthetic_commands(nfr), 8, device=device)
+        rec = gen.run()
+        gen.close()
+        recordio.save(rec, os.path.join(tmp, "data.zip"))
+        back = recordio.load(os.path.join(tmp, "data.zip"))
+        est, fmap, secs, nres = simulation.replay(back, P, device=device)
+        extra = {"recorded_frames": len(back.odometry), "data_zip_bytes": os.path.getsize(os.path.join(tmp, "data.zip")),
+                 "final_best_map_components": int(len(fmap[0])), "landmarks": n_lm,
+                 "note": "PHD navigator replay of the recorded run; the Loopy smoother's outer loop is not part of this repository"}
+        cpu = None
+    value = P * nfr / secs
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": nfr, "warmup": 0,
+            "ms_per_step": 1e3 * secs / nfr, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": dict({"workload": args.workload, "particles": P, "frames": nfr, "resampling_frames": nres,
+                            "timing": "navigator calls through the C ABI with host buffers (rbphd_update + rbphd_slam_update "
+                                      "+ pose / best-map read-back), wall clock; the simulated vehicle is host code"}, **extra),
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 8 * (6 * P + 6), "d2h_bytes_per_step": 8 * 7 * P,
+                    "steps": nfr, "resampling_frames": nres},
+            "gpu_launches": None}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+
+
 def kernel_counters():
     """ncu-derived per-particle-frame counters of k_particle_update (profiles/kernel_counters.json, written by
     tools/ncu_summary.py from a --set full capture); only trusted when they were taken on this tree."""
@@ -204,7 +279,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "tiny", "c4s", "c4m", "c2x"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "tiny", "c4s", "c4m", "c2x", "c1", "c5"])
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="frames of the host-buffer pass (default: steps)")
     ap.add_argument("--settle", type=int, default=-1, help="untimed frames before the warm-up (default 15 - warmup)")
@@ -224,6 +299,10 @@ def main():
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    if args.workload in ("c1", "c5"):
+        if rank == 0:
+            run_sim_workload(args, local_rank)
+        return
     import torch.distributed as dist
     from monorfs_b200 import capi, sharded, synth
 
