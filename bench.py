@@ -30,7 +30,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "particle_frames_per_sec"
 UNIT = "particle-frames/s"
-MAPPING_ONLY = {"c3"}
+MAPPING_ONLY = {"c3", "c3l"}
+LEAVE_ONE_OUT = {"c3l"}
 RECORD_BYTES = 80          # algorithmic FP64 record: weight + mean[3] + symmetric cov[6]
 PER_PARTICLE_BYTES = 128   # pose read+written (112) + weight read+written (16)
 SETTLE_TO = 15             # untimed frames (settle + warm-up) before the timed region
@@ -119,7 +120,7 @@ def cpu_sample_size(workload, cores):
     from monorfs_b200 import synth
     wl = synth.WORKLOADS[workload]
     per_core = {"c4": SAMPLE_PER_CORE, "c4s": SAMPLE_PER_CORE, "c4m": SAMPLE_PER_CORE, "c2": 4 * SAMPLE_PER_CORE,
-                "c2x": 4 * SAMPLE_PER_CORE, "c3": 1, "tiny": 4}.get(workload, SAMPLE_PER_CORE)
+                "c2x": 4 * SAMPLE_PER_CORE, "c3": 1, "c3l": 1, "tiny": 4}.get(workload, SAMPLE_PER_CORE)
     return max(1, min(wl["P"], per_core * cores))
 
 
@@ -279,7 +280,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "tiny", "c4s", "c4m", "c2x", "c1", "c5"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "c3l", "tiny", "c4s", "c4m", "c2x", "c1", "c5"])
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="frames of the host-buffer pass (default: steps)")
     ap.add_argument("--settle", type=int, default=-1, help="untimed frames before the warm-up (default 15 - warmup)")
@@ -355,7 +356,17 @@ def main():
             h.upload_frame_inputs(fr.gauss[lo:hi], fr.z, slot=f)
         h.synchronize()
         stream = torch.cuda.ExternalStream(h.stream, device=local_rank)
+        loo = name in LEAVE_ONE_OUT
+
+        def loo_prepare(f):
+            # leave-one-out batch: every filter gets this frame's trajectory pose, filter (f mod P) skips the frame
+            h.set_poses(np.tile(frames[f].true_pose.reshape(1, 7), (Pl, 1)))
+            g = f % P
+            h.set_holdout(g - lo if lo <= g < hi else -1)
+
         for f in range(skip):
+            if loo:
+                loo_prepare(f)
             nav.frame(frames[f].reading, synth.DT, M, frames[f].u, slot=f, only_mapping=mapping)
         h.synchronize()
         h.counters(reset=True)
@@ -371,6 +382,8 @@ def main():
         torch.cuda.synchronize()
         e0.record(stream)
         for f in range(skip, nframes):
+            if loo:
+                loo_prepare(f)
             nav.frame(frames[f].reading, synth.DT, M, frames[f].u, slot=f, only_mapping=mapping)
         e1.record(stream)
         h.synchronize()
@@ -405,8 +418,13 @@ def main():
             h2d = d2h = 0
             nres = 0
 
-            def host_frame(fr):
+            def host_frame(fr, f=0):
                 nonlocal h2d, d2h, nres
+                if loo:
+                    h.set_poses(np.tile(fr.true_pose.reshape(1, 7), (Pl, 1)))
+                    g = f % P
+                    h.set_holdout(g - lo if lo <= g < hi else -1)
+                    h2d += 8 * 7 * Pl
                 if world == 1:
                     if not mapping:
                         h.update(fr.reading, synth.DT, fr.gauss[lo:hi])
@@ -427,14 +445,14 @@ def main():
                     d2h += 4 * P
 
             for f in range(skip):
-                host_frame(frames[f])
+                host_frame(frames[f], f)
             h.synchronize()
             barrier()
             h2d = d2h = 0
             nres = 0
             t0 = time.perf_counter()
             for f in range(skip, skip + ne):
-                host_frame(frames[f])
+                host_frame(frames[f], f)
             h.synchronize()
             dt = time.perf_counter() - t0
             barrier()
@@ -623,7 +641,7 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ncpu = os.cpu_count() or 1
-        nfr = {"c4": 2, "c4s": 2, "c4m": 2, "c2": 4, "c2x": 4, "c3": 1, "tiny": 4}.get(args.workload, 2)
+        nfr = {"c4": 2, "c4s": 2, "c4m": 2, "c2": 4, "c2x": 4, "c3": 1, "c3l": 1, "tiny": 4}.get(args.workload, 2)
         line["cpu_baseline"] = run_oracle(args.workload, cpu_sample_size(args.workload, ncpu), 1, nfr, synth.SEED)
 
     if "final" in main_res and rank == 0:

@@ -108,6 +108,12 @@ int rbphd_slam_update(rbphd_navigator* nav, const double* z, int m, int only_map
 int rbphd_slam_update_begin(rbphd_navigator* nav, const double* z, int m, int only_mapping, int* best,
                             int* depleted);
 int rbphd_slam_update_finish(rbphd_navigator* nav, double u_resample, int* best);
+/* Leave-one-out batches (LoopyPHDNavigator.FilterMissing, LoopyPHDNavigator.cs:729-763, called for every frame
+ * index by UpdateMessagesFromMap, :511-552): the T one-particle, mapping-only re-filters of a smoothing pass differ
+ * only in which frame they skip, so they run as T "particles" of one navigator -- every frame rbphd_set_poses gives
+ * all of them that frame's trajectory pose, rbphd_set_holdout names the one filter that skips it (its map is
+ * carried over unchanged), and a mapping-only frame updates the rest.  particle < 0 clears the hold-out. */
+int rbphd_set_holdout(rbphd_navigator* nav, int particle);
 /* Device-resident frame loop: Update + SlamUpdate enqueued on the handle's stream with nothing copied
  * back and no host synchronisation.  The frame's inputs (gauss: particles x 6, z: m x 3) are uploaded
  * beforehand into input slot `slot` (0 <= slot < resident_frames); either pointer may be NULL to keep

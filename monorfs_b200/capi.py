@@ -49,7 +49,7 @@ EXPORTS = [
     "rbphd_debug_migration_plan", "rbphd_kernel_launches", "rbphd_profile_enable",
     "rbphd_profile_read", "rbphd_get_counters", "rbphd_get_phase_cycles", "rbphd_stream",
     "rbphd_launch_shape", "rbphd_bench_fp64", "rbphd_slam_update_begin", "rbphd_slam_update_finish",
-    "rbphd_set_likelihood", "rbphd_quasi_set_loglikelihood", "rbphd_set_loglike_matrix",
+    "rbphd_set_likelihood", "rbphd_quasi_set_loglikelihood", "rbphd_set_loglike_matrix", "rbphd_set_holdout",
 ]
 
 _lib = None
@@ -272,6 +272,25 @@ class Handle:
         self._ck(self.lib.rbphd_slam_update(self._h, _p(z), len(z), int(only_mapping), C.c_double(u),
                                             C.byref(best), C.byref(res)))
         return best.value, bool(res.value)
+
+    def set_holdout(self, particle):
+        self._ck(self.lib.rbphd_set_holdout(self._h, int(particle)))
+
+    def filter_missing_batch(self, trajectory, factors, to=None):
+        """All leave-one-out maps of LoopyPHDNavigator.FilterMissing (LOOPY:729-763) in one pass: particle j ends
+        with the map filtered over frames 0..to-1 except frame j (j >= to: nothing skipped).  The navigator must
+        hold len(trajectory) particles with empty (or common prior) maps."""
+        T = len(trajectory)
+        to = T if to is None else min(T, to)
+        assert self.particles >= T
+        for i in range(to):
+            self.set_poses(np.tile(_d(trajectory[i]).reshape(1, 7), (self.particles, 1)))
+            self.set_holdout(i)
+            z = _d(factors[i]).reshape(-1, 3)
+            self.upload_frame_inputs(None, z, slot=0)
+            self.frame_async(None, 0.0, len(z), 0.0, only_mapping=True, slot=0)
+        self.set_holdout(-1)
+        self.synchronize()
 
     def slam_update_begin(self, z, only_mapping=False):
         z = _d(z).reshape(-1, 3)

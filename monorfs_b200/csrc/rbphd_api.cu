@@ -92,6 +92,7 @@ struct rbphd_navigator {
     std::vector<double> o_w, o_m, o_P;
     std::vector<int> o_anc, o_rows, o_cols;
     int ll_flags = 0;
+    int holdout = -1;             // rbphd_set_holdout
     int64_t launches = 0;
     std::string error;
     rbphd_navigator* stage = nullptr;   // lazily created 2-slot navigator for the stage entry points
@@ -284,6 +285,7 @@ KParams base_params(rbphd_navigator* nav, int mode, int M, int only_mapping, int
     k.dump_cap = nav->dump_cap;
     k.smem_sort_cap = nav->sort_cap;
     k.ll_flags = nav->ll_flags;
+    k.holdout = nav->holdout;
     return k;
 }
 
@@ -515,6 +517,14 @@ void rbphd_delete(rbphd_navigator* nav)
 }
 
 int rbphd_particle_count(const rbphd_navigator* nav) { return nav ? nav->P : 0; }
+
+int rbphd_set_holdout(rbphd_navigator* nav, int particle)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (particle >= nav->P) return fail(nav, RBPHD_ERR_ARGUMENT, "hold-out particle out of range");
+    nav->holdout = particle < 0 ? -1 : particle;
+    return RBPHD_OK;
+}
 
 int rbphd_reset(rbphd_navigator* nav, int particles, const double* pose7, int n, const double* w,
                 const double* mean, const double* cov)

@@ -1246,6 +1246,15 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) k_particle_update(const __
     for (int particle = p.first + blockIdx.x; particle < p.first + p.P; particle += gridDim.x) {
         const double* in = p.maps[cur] + (size_t)particle * kFields * p.cap;
         double* out = p.maps[1 - cur] + (size_t)particle * kFields * p.cap;
+        if (p.mode == MODE_FRAME && particle == p.holdout) {
+            // held-out filter of a leave-one-out batch (LoopyPHDNavigator.FilterMissing, LOOPY:729-763): this frame's
+            // factor is skipped, the map moves to the other buffer unchanged
+            const int n = min(p.counts[cur][particle], p.cap);
+            for (int f = 0; f < kFields; f++)
+                for (int t = tid; t < n; t += kBlock) out[(size_t)f * p.cap + t] = in[(size_t)f * p.cap + t];
+            if (tid == 0) p.counts[1 - cur][particle] = n;
+            continue;
+        }
         if (tid == 0) {
             Ctx& c = sm.ctx;
             c.N = min(p.counts[cur][particle], p.cap);

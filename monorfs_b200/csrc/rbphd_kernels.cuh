@@ -84,6 +84,7 @@ struct KParams {
     int dump_cap;
     size_t smem_sort_cap;  // elements of the shared-memory sort buffer
     int ll_flags;          // LikelihoodFlags of a MODE_STAGE_SETLL call
+    int holdout;           // MODE_FRAME: this particle skips the frame (its map is carried over unchanged); -1 = none
 };
 
 enum LikelihoodFlags { LL_QUASI = 1, LL_DUMP_MATRIX = 2 };   // KParams::ll_flags (MODE_STAGE_SETLL)

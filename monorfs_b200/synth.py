@@ -21,6 +21,8 @@ WORKLOADS = {
     "tiny": dict(P=64, N=60, M=24),
     "c4s": dict(P=1480, N=2000, M=500),   # config 4's per-particle shape on 1480 particles (profiling runs)
     "c4m": dict(P=2960, N=2000, M=500),   # the same on 2960 particles (10 per CTA at two CTAs per SM)
+    "c3l": dict(P=200, N=50000, M=1000),  # config 3 as Loopy's leave-one-out batch: 200 mapping-only filters that share
+                                          # the trajectory pose of each frame, one of them skipping it (LOOPY:729-763)
     "c2x": dict(P=20000, N=500, M=100),   # config 2's per-particle shape on config 4's particle count: resamples
                                           # every frame, so it exercises the multi-GPU map migration
 }
@@ -196,5 +198,5 @@ def make_scene(P, N, M, seed=SEED, box_scale=1.0, **over):
 def make_workload(name, seed=SEED, **over):
     w = dict(WORKLOADS[name])
     w.update({k: over.pop(k) for k in ("P", "N", "M") if k in over})
-    scale = 25.0 if name == "c3" else 1.0
+    scale = 25.0 if name in ("c3", "c3l") else 1.0
     return make_scene(w["P"], w["N"], w["M"], seed=seed, box_scale=over.pop("box_scale", scale), **over)

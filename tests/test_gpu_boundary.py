@@ -121,3 +121,36 @@ def test_two_step_slam_update_equals_one_step(capi, synth, meff):
     assert (ndep > 0) == (meff > 0.5)
     a.close()
     b.close()
+
+
+def test_filter_missing_batch_equals_single_filters(capi, orc, synth):
+    """LoopyPHDNavigator.FilterMissing for every held-out index as one batch of "particles" (LOOPY:729-763)."""
+    T, N, M = 7, 30, 14
+    sc = synth.make_scene(1, N, M, seed=21)
+    frames = [sc.next_frame() for _ in range(T)]
+    traj = [fr.true_pose for fr in frames]
+    factors = [fr.z for fr in frames]
+    factors[3] = np.zeros((0, 3))                       # a frame without measurements
+    h = capi.Handle(sc.params, max_particles=T + 1, max_components=256, max_measurements=M)
+    h.reset(T + 1, traj[0], np.zeros(0), np.zeros((0, 3)), np.zeros((0, 3, 3)))
+    h.filter_missing_batch(traj + [traj[-1]], factors + [factors[-1]], to=T)
+    ocfg = orc.make_config(sc.params)
+    for j in range(T + 1):                              # particle T holds out nothing: the plain filter
+        nav = orc.Navigator(ocfg, 1, traj[0], only_mapping=True)
+        for i in range(T):
+            if i == j:
+                continue
+            nav.set_pose(0, traj[i])
+            nav.slam_update(factors[i], 0.0)
+        ow, om, oP = nav.get_map(0)
+        gw, gm, gP = h.get_map(j)
+        assert len(gw) == len(ow), (j, len(gw), len(ow))
+        assert np.allclose(gw, ow, rtol=RTOL, atol=1e-300)
+        assert np.allclose(gm, om, rtol=RTOL, atol=1e-12)
+        # merged covariances: raw-moment conditioning floor, as in tests/test_gpu_parity.py (DESIGN.md section 5)
+        floor = 64 * np.finfo(float).eps * np.sum(om ** 2, axis=1)[:, None, None]
+        assert np.all(np.abs(gP - oP) <= RTOL * np.abs(oP) + floor + 1e-15)
+        nav.close()
+    counts = h.get_map_counts()
+    assert len(set(counts.tolist())) > 1                # the held-out frame matters
+    h.close()
