@@ -215,9 +215,9 @@ int rbphd_profile_read(rbphd_navigator* nav, double* ms, int max_frames, int* fr
 /* device-side work counters since the last reset: prior components read, pruned components written,
  * gated (component, measurement) pairs evaluated, particle-frames processed */
 int rbphd_get_counters(rbphd_navigator* nav, int64_t out4[4], int reset);
-/* diagnostics: SM cycles per internal phase of the fused kernel summed over CTAs (32 entries) followed
+/* diagnostics: SM cycles per internal phase of the fused kernel summed over CTAs (64 entries) followed
  * by 16 event counters */
-int rbphd_get_phase_cycles(rbphd_navigator* nav, int64_t out48[48]);
+int rbphd_get_phase_cycles(rbphd_navigator* nav, int64_t out80[80]);
 /* launch geometry of the fused per-particle kernel on this handle: threads per CTA, resident CTAs per SM,
  * dynamic shared memory per CTA (bytes), scratch slabs (= CTAs launched), bytes per scratch slab */
 int rbphd_launch_shape(const rbphd_navigator* nav, int64_t out5[5]);

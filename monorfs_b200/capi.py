@@ -433,21 +433,23 @@ class Handle:
               "B6 merge+write", "C1-3 map estimate", "C4 eval predicted", "C4 eval corrected", "C5 set likelihood",
               "tail", "A4a undecided list", "A4b density accumulate", "A4c decide", "B3a merge grid build",
               "C4a zero", "C4b accumulate", "C4c log-sum", "C3b query grid build", "C5a gate edges", "C5b components",
-              "C5c edge sort", "A4b1 gather points", "A4b2 mini grid build", "C4b enumerate", "C4b dense process", "A3a gated component update")
+              "C5c edge sort", "A4b1 gather points", "A4b2 mini grid build", "C4b enumerate", "C4b dense process", "A3a gated component update",
+              "B3b cell-ordered copies", "B3c exact edge tests", "B3d edge sort", "B6a survivor scan", "B1a candidate compaction",
+              "C1 expected size", "C2 multiset expand", "C3 multiset sort", "C5d block enumeration") + tuple("p%d" % i for i in range(41, 64))
 
     DEBUG_COUNTERS = ("undecided measurements", "explore hits", "gated components", "merge edges", "W0",
                       "candidates", "eval pairs", "wide components", "eval cell rows", "likelihood edges", "J",
                       "murty blocks", "d12", "d13", "d14", "d15")
 
     def phase_cycles(self):
-        out = (C.c_int64 * 48)()
+        out = (C.c_int64 * 80)()
         self._ck(self.lib.rbphd_get_phase_cycles(self._h, out))
         return {k: int(out[i]) for i, k in enumerate(self.PHASES)}
 
     def debug_counters(self):
-        out = (C.c_int64 * 48)()
+        out = (C.c_int64 * 80)()
         self._ck(self.lib.rbphd_get_phase_cycles(self._h, out))
-        return {k: int(out[32 + i]) for i, k in enumerate(self.DEBUG_COUNTERS)}
+        return {k: int(out[64 + i]) for i, k in enumerate(self.DEBUG_COUNTERS)}
 
     @property
     def kernel_launches(self):

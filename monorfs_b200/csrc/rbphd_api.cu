@@ -1436,14 +1436,14 @@ int rbphd_debug_migration_plan(int device, const int* ancestors, const int* coun
     return RBPHD_OK;
 }
 
-int rbphd_get_phase_cycles(rbphd_navigator* nav, int64_t out16[48])
+int rbphd_get_phase_cycles(rbphd_navigator* nav, int64_t out80[80])
 {
-    if (!nav || !out16) return RBPHD_ERR_ARGUMENT;
+    if (!nav || !out80) return RBPHD_ERR_ARGUMENT;
     if (int r = set_device(nav)) return r;
     DeviceState st;
     if (int r = read_state(nav, &st)) return r;
-    for (int a = 0; a < 32; a++) out16[a] = (int64_t)st.phase_cycles[a];
-    for (int a = 0; a < 16; a++) out16[32 + a] = (int64_t)st.dbg[a];
+    for (int a = 0; a < 64; a++) out80[a] = (int64_t)st.phase_cycles[a];
+    for (int a = 0; a < 16; a++) out80[64 + a] = (int64_t)st.dbg[a];
     return RBPHD_OK;
 }
 
@@ -1489,7 +1489,7 @@ int rbphd_get_counters(rbphd_navigator* nav, int64_t out4[4], int reset)
     out4[0] = (int64_t)st.comps_in; out4[1] = (int64_t)st.comps_out;
     out4[2] = (int64_t)st.pairs; out4[3] = (int64_t)st.particle_frames;
     if (reset) {
-        CK(cudaMemsetAsync(&nav->st->comps_in, 0, 52 * sizeof(unsigned long long), nav->stream));
+        CK(cudaMemsetAsync(&nav->st->comps_in, 0, (4 + 64 + 16) * sizeof(unsigned long long), nav->stream));
         CK(cudaStreamSynchronize(nav->stream));
     }
     return RBPHD_OK;

@@ -27,7 +27,7 @@ struct Ctx {
     CellGrid grid;
     CellGrid vg;       // copy of the frame's camera-frame measurement grid header
     long long tlast;
-    unsigned long long tphase[32];
+    unsigned long long tphase[64];
     unsigned int dbg[16];
 };
 #define DBG_ADD(sm, idx, v) atomicAdd(&(sm).ctx.dbg[idx], (unsigned int)(v))
@@ -902,6 +902,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
         if (tid == 0) sm.ctx.ncand = total;
         __syncthreads();
     }
+    PHASE_MARK(sm, 36);
     const int nc = sm.ctx.ncand;
     unsigned int* sval = s.sval;   // list positions in sorted order (wherever the sort leaves them)
     {
@@ -993,6 +994,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
     }
     if (tid == 0) sm.ctx.nedges = 0;
     __syncthreads();
+    PHASE_MARK(sm, 32);
     unsigned long long* elist = s.llkey;   // (r << 32 | r') edge keys; capacity cap_ll
     const int cape = p.lay.cap_ll;
     {
@@ -1058,9 +1060,10 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
                         }
                     }
             },
-            test, 8, 8);
+            test, 8, 33);
     }
     __syncthreads();
+    PHASE_MARK(sm, 33);
     int ne = sm.ctx.nedges;
     if (tid == 0) { sm.ctx.dbg[2] += sm.ctx.nact; sm.ctx.dbg[3] += ne; sm.ctx.dbg[4] += W0; sm.ctx.dbg[5] += sm.ctx.ncand; if (ne > cape) sm.ctx.status |= ST_OVER_EDGES; }
     ne = min(ne, cape);
@@ -1075,7 +1078,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
     }
     else if (tid == 0) sm.ctx.status |= ST_OVER_EDGES;
 
-    PHASE_MARK(sm, 8);
+    PHASE_MARK(sm, 34);
     // B4: which candidates survive.  A component is absorbed iff some surviving earlier candidate is
     // close to it; resolve in rounds (the lowest undecided rank is always decidable).
     for (int r = tid; r < W0; r += kBlock) { s.nstate[r] = 0; s.nflag[r] = 0; s.nowner[r] = 0x7fffffff; }
@@ -1112,6 +1115,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
     for (int r = tid; r < W0; r += kBlock) s.nflag[r] = (s.nstate[r] == 1) ? 1 : 0;
     __syncthreads();
     int nout = block_scan_array(sm.sh, s.nflag, W0);
+    PHASE_MARK(sm, 35);
     if (nout > p.cap) { nout = p.cap; if (tid == 0) sm.ctx.status |= ST_OVER_COMPONENTS; }
     for (int r = tid; r < W0; r += kBlock) {
         if (s.nstate[r] != 1) continue;
@@ -1242,7 +1246,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) k_particle_update(const __
 
     if (tid == 0) sm.ctx.vg = p.vgrid->g;
     unsigned long long acc_in = 0, acc_out = 0, acc_pairs = 0, acc_pf = 0;   // thread 0 only
-    if (tid == 0) { for (int a = 0; a < 32; a++) sm.ctx.tphase[a] = 0; for (int a = 0; a < 16; a++) sm.ctx.dbg[a] = 0; sm.ctx.tlast = clock64(); }
+    if (tid == 0) { for (int a = 0; a < 64; a++) sm.ctx.tphase[a] = 0; for (int a = 0; a < 16; a++) sm.ctx.dbg[a] = 0; sm.ctx.tlast = clock64(); }
     for (int particle = p.first + blockIdx.x; particle < p.first + p.P; particle += gridDim.x) {
         const double* in = p.maps[cur] + (size_t)particle * kFields * p.cap;
         double* out = p.maps[1 - cur] + (size_t)particle * kFields * p.cap;
@@ -1353,7 +1357,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) k_particle_update(const __
     if (tid == 0 && p.mode == MODE_FRAME) {
         atomicAdd(&p.st->comps_in, acc_in); atomicAdd(&p.st->comps_out, acc_out);
         atomicAdd(&p.st->pairs, acc_pairs); atomicAdd(&p.st->particle_frames, acc_pf);
-        for (int a = 0; a < 32; a++) atomicAdd(&p.st->phase_cycles[a], sm.ctx.tphase[a]);
+        for (int a = 0; a < 64; a++) atomicAdd(&p.st->phase_cycles[a], sm.ctx.tphase[a]);
         for (int a = 0; a < 16; a++) atomicAdd(&p.st->dbg[a], (unsigned long long)sm.ctx.dbg[a]);
     }
 }

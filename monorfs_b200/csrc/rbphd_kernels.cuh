@@ -32,7 +32,7 @@ struct DeviceState {
     int depleted;
     int pad[3];
     unsigned long long comps_in, comps_out, pairs, particle_frames;   // work counters
-    unsigned long long phase_cycles[32];
+    unsigned long long phase_cycles[64];
     unsigned long long dbg[16];            // diagnostic event counts (see capi.Handle.DEBUG_COUNTERS)   // SM cycles spent per phase of k_particle_update (thread 0, all CTAs)
 };
 

@@ -508,6 +508,7 @@ __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab
         int m = lexicographical_values(Mx, n, J, vals);
         contrib += log_sum_exp(vals, m);
     }
+    PHASE_MARK(sm, 40);
     // isolated landmarks (1x1 block: ln(1 - PD)) and isolated measurements (1x1 block: ln clutter)
     for (int t = tid; t < J; t += kBlock) if (deg[t] == 0) contrib += log(1 - s.jpd[t]);
     for (int k = tid; k < M; k += kBlock) if (deg[J + k] == 0) contrib += c.logclutter;
@@ -548,6 +549,7 @@ __device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const 
         }
     }
     int size = (ccount > 0) ? ((ccount < 2.0e9) ? (int)ccount : 2000000000) : 0;
+    PHASE_MARK(sm, 37);
 
     // MAP:119-142 BestMapEstimate: the `size` largest values of the multiset {w_i - j : j = 0,1,..},
     // ties ordered (generation, index) -- what the reference's append-and-stable-re-sort produces
@@ -580,6 +582,7 @@ __device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const 
         }
     }
     __syncthreads();
+    PHASE_MARK(sm, 38);
     const int tot = min(total, gcap);
     const int wantj = min(size, tot);
     unsigned long long* skey = direct ? sm.skey() : s.skey;
@@ -620,6 +623,7 @@ __device__ double phase_weight(const KParams& p, Smem& sm, const Slab& s, const 
         }
     }
     __syncthreads();
+    PHASE_MARK(sm, 39);
     int J = min(size, total);
     if (J > capj) { J = capj; if (tid == 0) sm.ctx.status |= ST_OVER_JMAP; }
     for (int t = tid; t < J; t += kBlock) {

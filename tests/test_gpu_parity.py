@@ -328,11 +328,12 @@ def test_resample_reference_invariants(ctx, orc):
     assert seen0 < iters and seen3 < iters
 
 
-def run_both(capi, orc, synth, P, N, M, frames, seed, only_mapping=False, merge_floor=0.0, **over):
+def run_both(capi, orc, synth, P, N, M, frames, seed, only_mapping=False, merge_floor=0.0, max_pairs=0,
+             final_counts=None, **over):
     sc = synth.make_scene(P, N, M, seed=seed, **over)
     ocfg = orc.make_config(sc.params)
     h = capi.Handle(sc.params, max_particles=P, max_components=max(2 * N, 64), max_measurements=M,
-                    max_pairs=max(8 * M, 256))
+                    max_pairs=max_pairs or max(8 * M, 256))
     nav = orc.Navigator(ocfg, P, sc.poses[0], only_mapping=only_mapping)
     h.reset(P, sc.poses[0], sc.map_w, sc.map_m, sc.map_P)
     h.set_poses(sc.poses)
@@ -365,6 +366,8 @@ def run_both(capi, orc, synth, P, N, M, frames, seed, only_mapping=False, merge_
             assert_maps_equal(h.get_map(i), nav.get_map(i), f"{tag} particle {i}", merge_floor)
             assert counts[i] == len(nav.get_map(i)[0])
         nres += int(gres)
+    if final_counts is not None:
+        final_counts.extend(h.get_map_counts().tolist())
     h.close()
     return nres
 
@@ -541,6 +544,17 @@ def test_c4_shape_sampled_parity(capi, orc, synth):
     for k in ("pcount", "ccount", "ploglik", "cloglik", "setloglik"):
         assert close_rel(got[k], exp[k]), (k, got[k], exp[k])
     h.close()
+
+
+def test_c4_shape_saturated_parity(capi, orc, synth):
+    """The regime bench.py times: config 4's per-particle shape followed for 14 consecutive frames, by which
+    time the map has grown from 2000 to ~3850 components and the MaxQuantity cut (4000 heaviest candidates,
+    PHD:924-927) is active on every frame.  Two particles against the oracle."""
+    counts = []
+    nres = run_both(capi, orc, synth, P=2, N=2000, M=500, frames=14, seed=35, merge_floor=64.0, max_pairs=16 * 500,
+                    final_counts=counts)
+    assert nres == 0    # (the set likelihood underflows at 500 measurements: weights 0, never depleted)
+    assert min(counts) > 3500, counts   # saturated: the MaxQuantity cut has been deciding the survivors
 
 
 def test_big_particle_fallback_lanes(capi, orc, synth):
