@@ -220,17 +220,34 @@ void make_layout(ScratchLayout& l, int cap, int Mcap, int cap_pairs, int maxq)
     take(l.bidx, I * (cap_pairs + 2));
     take(l.pkey, U * cap_pairs);     take(l.pt, D * cap_pairs);    take(l.pmean, 3 * D * cap_pairs);
     take(l.pwgt, D * cap_pairs);
-    take(l.crec, kRecFields * D * l.cap_pred); take(l.cpn, 9 * D * l.cap_pred);
+    // Three groups of arrays with disjoint lifetimes share one region, so that the slab touches fewer distinct
+    // cache lines per particle (the L2 holds ~0.85 MB per resident CTA):
+    //   the Kalman records (written by comp_update, dead once the pairs are evaluated: A3 - A7),
+    //   the ranked candidates of PruneModel (B2 - B6),
+    //   the map-estimate points of WeightAlpha (C3 - C5).
+    {
+        const size_t base = off;
+        take(l.crec, kRecFields * D * l.cap_pred);
+        const size_t end_a = off;
+        off = base;
+        take(l.tw, D * l.cap_top);   take(l.tm, 3 * D * l.cap_top);
+        take(l.tloc, sizeof(unsigned) * l.cap_top);
+        take(l.rho, D * l.cap_top);
+        const size_t end_b = off;
+        off = base;
+        take(l.jidx, I * l.cap_j);   take(l.jm, 3 * D * l.cap_j);  take(l.jmp, 3 * D * l.cap_j);
+        take(l.jpd, D * l.cap_j);
+        const size_t end_c = off;
+        off = std::max(end_a, std::max(end_b, end_c));
+    }
+    take(l.cpn, 9 * D * l.cap_pred);
     take(l.hits4, U * l.cap_pred);
     take(l.skey, U * l.cap_sort);    take(l.sval, sizeof(unsigned) * l.cap_sort);
     take(l.skey2, U * l.cap_sort);   take(l.sval2, sizeof(unsigned) * l.cap_sort);
-    take(l.tw, D * l.cap_top);       take(l.tm, 3 * D * l.cap_top); take(l.tloc, sizeof(unsigned) * l.cap_top);
-    take(l.rho, D * l.cap_top);
     take(l.edst, I * l.cap_edges);
     take(l.nstate, I * l.cap_nodes); take(l.nowner, I * l.cap_nodes); take(l.nflag, I * l.cap_nodes);
     take(l.gitems, I * l.cap_nodes);
-    take(l.jidx, I * l.cap_j);       take(l.jm, 3 * D * l.cap_j);  take(l.jmp, 3 * D * l.cap_j);
-    take(l.jpd, D * l.cap_j);        take(l.vsum, D * l.cap_j);
+    take(l.vsum, D * l.cap_j);
     take(l.erad, D * l.cap_pred); take(l.erad2, D * l.cap_pred); take(l.cnorm, D * l.cap_pred); take(l.crad, D * l.cap_pred);   // exploration bound per component
     take(l.llkey, U * l.cap_ll);     take(l.llval, D * l.cap_ll);
     take(l.uf, I * (l.cap_j + Mcap + 2)); take(l.bcnt, I * (l.cap_j + Mcap + 2));
