@@ -165,7 +165,13 @@ __device__ double eval_map_at_points(const KParams& p, Smem& sm, const Slab& s, 
                                 in = dx * dx + dy * dy + dz * dz <= r2;
                             }
                             if (in) {
-                                const int idx = atomicAdd(&sm.ctx.nsel2, 1);
+                                // one atomic per group of lanes that hit together (thousands of hits per particle
+                                // on one shared-memory counter serialise otherwise)
+                                const unsigned act = __activemask();
+                                const int leader = __ffs(act) - 1;
+                                int idx = 0;
+                                if (lane == leader) idx = atomicAdd(&sm.ctx.nsel2, __popc(act));
+                                idx = __shfl_sync(act, idx, leader) + __popc(act & ((1u << lane) - 1u));
                                 if (idx < list_cap) list[idx] = make_uint2((unsigned)i, (unsigned)t);
                                 else if (idx - list_cap < ovf_cap) ovf[idx - list_cap] = make_uint2((unsigned)i, (unsigned)t);
                                 else sm.ctx.status |= ST_OVER_PAIRS;

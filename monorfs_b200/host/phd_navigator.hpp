@@ -94,11 +94,13 @@ public:
         for (size_t k = 0; k < measurements.size(); k++) {
             z_[3 * k] = measurements[k].X; z_[3 * k + 1] = measurements[k].Y; z_[3 * k + 2] = measurements[k].Range;
         }
-        int best = 0, resampled = 0;
-        check(rbphd_slam_update(nav_, z_.data(), (int)measurements.size(), OnlyMapping ? 1 : 0, UniformDraw(), &best,
-                                &resampled));
+        // two steps, so that the uniform of the wheel is drawn exactly when the reference draws it (only when
+        // ParticleDepleted(), PHD:355-357 -> PHD:727)
+        int best = 0, depleted = 0;
+        check(rbphd_slam_update_begin(nav_, z_.data(), (int)measurements.size(), OnlyMapping ? 1 : 0, &best, &depleted));
+        if (depleted) check(rbphd_slam_update_finish(nav_, UniformDraw(), &best));
         BestParticle = best;
-        LastResampled = resampled != 0;
+        LastResampled = depleted != 0;
     }
     bool LastResampled = false;
 
@@ -187,6 +189,25 @@ public:
                                        pw.data(), pm.data(), pP.data(), (int)corrected.size(), fw_.data(), fm_.data(),
                                        fP_.data(), out));
         return out[0];
+    }
+    // the static likelihood functions over a landmark list (PHD:395-406, 526-532)
+    double SetLikelihood(const std::vector<PixelRangeMeasurement>& measurements, const Map& map, const Pose3D& pose)
+    {
+        pack(measurements);
+        flatten(map);
+        double v = 0;
+        check(rbphd_set_likelihood(nav_, pose.State, (int)map.size(), fm_.data(), z_.data(), (int)measurements.size(), &v));
+        return v;
+    }
+    double QuasiSetLogLikelihood(const std::vector<PixelRangeMeasurement>& measurements, const Map& map,
+                                 const Pose3D& pose)
+    {
+        pack(measurements);
+        flatten(map);
+        double v = 0;
+        check(rbphd_quasi_set_loglikelihood(nav_, pose.State, (int)map.size(), fm_.data(), z_.data(),
+                                            (int)measurements.size(), &v));
+        return v;
     }
 
 private:
