@@ -108,6 +108,12 @@ int rbphd_slam_update(rbphd_navigator* nav, const double* z, int m, int only_map
 int rbphd_slam_update_begin(rbphd_navigator* nav, const double* z, int m, int only_mapping, int* best,
                             int* depleted);
 int rbphd_slam_update_finish(rbphd_navigator* nav, double u_resample, int* best);
+/* KinectMeasurer (BaseStructures/Measurers/KinectMeasurer.cs:123-173, KinectTrackVehicle.cs:61-74): attach the
+ * current depth frame, depth_xy[x * resy + y] in metres (NaN = no reading), so that the detection probability of a
+ * landmark also ramps to 0 as it moves behind the measured surface (occlusion).  The configured film rectangle must
+ * already be the border-deflated one the reference gives its KinectMeasurer.  The frame is copied; pass NULL to
+ * return to the plain pixel-range measurer.  Upload a new frame before each SlamUpdate (1.2 MB at 640 x 480). */
+int rbphd_set_depth_frame(rbphd_navigator* nav, const float* depth_xy, int resx, int resy);
 /* Leave-one-out batches (LoopyPHDNavigator.FilterMissing, LoopyPHDNavigator.cs:729-763, called for every frame
  * index by UpdateMessagesFromMap, :511-552): the T one-particle, mapping-only re-filters of a smoothing pass differ
  * only in which frame they skip, so they run as T "particles" of one navigator -- every frame rbphd_set_poses gives

@@ -49,7 +49,7 @@ EXPORTS = [
     "rbphd_debug_migration_plan", "rbphd_kernel_launches", "rbphd_profile_enable",
     "rbphd_profile_read", "rbphd_get_counters", "rbphd_get_phase_cycles", "rbphd_stream",
     "rbphd_launch_shape", "rbphd_bench_fp64", "rbphd_slam_update_begin", "rbphd_slam_update_finish",
-    "rbphd_set_likelihood", "rbphd_quasi_set_loglikelihood", "rbphd_set_loglike_matrix", "rbphd_set_holdout",
+    "rbphd_set_likelihood", "rbphd_quasi_set_loglikelihood", "rbphd_set_loglike_matrix", "rbphd_set_holdout", "rbphd_set_depth_frame",
 ]
 
 _lib = None
@@ -272,6 +272,14 @@ class Handle:
         self._ck(self.lib.rbphd_slam_update(self._h, _p(z), len(z), int(only_mapping), C.c_double(u),
                                             C.byref(best), C.byref(res)))
         return best.value, bool(res.value)
+
+    def set_depth_frame(self, depth_xy):
+        """Attach a Kinect depth frame, depth_xy[x, y] in metres (float32, NaN = no reading); None detaches it."""
+        if depth_xy is None:
+            self._ck(self.lib.rbphd_set_depth_frame(self._h, None, 0, 0))
+            return
+        d = np.ascontiguousarray(depth_xy, dtype=np.float32)
+        self._ck(self.lib.rbphd_set_depth_frame(self._h, d.ctypes.data_as(C.POINTER(C.c_float)), d.shape[0], d.shape[1]))
 
     def set_holdout(self, particle):
         self._ck(self.lib.rbphd_set_holdout(self._h, int(particle)))

@@ -93,6 +93,8 @@ struct rbphd_navigator {
     std::vector<int> o_anc, o_rows, o_cols;
     int ll_flags = 0;
     int holdout = -1;             // rbphd_set_holdout
+    float* depth = nullptr;       // rbphd_set_depth_frame: device copy of the Kinect depth frame
+    size_t depth_cap = 0;
     int64_t launches = 0;
     std::string error;
     rbphd_navigator* stage = nullptr;   // lazily created 2-slot navigator for the stage entry points
@@ -191,6 +193,7 @@ void make_devcfg(const rbphd_config& c, DevCfg& d, double gate_radius_override, 
     d.right = left + (int)c.measurer[5];
     d.bottom = top + (int)c.measurer[6];
     d.rmin = (double)(float)c.measurer[1];   // AForge.Range holds floats (PRM:65,110)
+    d.rmin_f = (float)c.measurer[1];
     d.rmax = (double)(float)c.measurer[2];
     d.maxq = c.max_quantity;
 }
@@ -263,7 +266,7 @@ void free_device(rbphd_navigator* nav)
     cudaFree(nav->alpha_parts); cudaFree(nav->z); cudaFree(nav->gauss); cudaFree(nav->pts);
     cudaFree(nav->ancestors); cudaFree(nav->cumw); cudaFree(nav->st); cudaFree(nav->vgrid); cudaFree(nav->zgrid);
     cudaFree(nav->vitems); cudaFree(nav->zitems); cudaFree(nav->scratch); cudaFree(nav->dump);
-    cudaFree(nav->dump_count);
+    cudaFree(nav->dump_count); cudaFree(nav->depth);
     for (auto& e : nav->pev) cudaEventDestroy(e);
     if (nav->stream) cudaStreamDestroy(nav->stream);
 }
@@ -414,6 +417,11 @@ int ensure_stage(rbphd_navigator* nav)
     lim.max_components = nav->cap + nav->Mcap;   // a predicted map holds the prior components plus the births
     nav->stage = rbphd_new(&nav->cfg, &lim);
     if (!nav->stage) return fail(nav, RBPHD_ERR_CUDA, "stage navigator: " + g_last_error);
+    {
+        DevCfg& d = nav->stage->dcfg;
+        d.depth = nav->dcfg.depth; d.resx = nav->dcfg.resx; d.resy = nav->dcfg.resy;
+        d.half_x = nav->dcfg.half_x; d.half_y = nav->dcfg.half_y;
+    }
     return RBPHD_OK;
 }
 
@@ -534,6 +542,36 @@ void rbphd_delete(rbphd_navigator* nav)
 }
 
 int rbphd_particle_count(const rbphd_navigator* nav) { return nav ? nav->P : 0; }
+
+int rbphd_set_depth_frame(rbphd_navigator* nav, const float* depth_xy, int resx, int resy)
+{
+    if (!nav) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    if (!depth_xy) {   // back to the plain pixel-range measurer
+        nav->dcfg.depth = nullptr;
+        if (nav->stage) nav->stage->dcfg.depth = nullptr;
+        return RBPHD_OK;
+    }
+    if (resx < 1 || resy < 1) return fail(nav, RBPHD_ERR_ARGUMENT, "depth frame resolution");
+    const size_t n = (size_t)resx * resy;
+    CK(cudaStreamSynchronize(nav->stream));
+    if (n > nav->depth_cap) {
+        cudaFree(nav->depth);
+        nav->depth = nullptr;
+        CK(cudaMalloc(&nav->depth, sizeof(float) * n));
+        nav->depth_cap = n;
+    }
+    if (int r = upload(nav, nav->depth, depth_xy, sizeof(float) * n)) return r;
+    CK(cudaStreamSynchronize(nav->stream));
+    nav->dcfg.depth = nav->depth;
+    nav->dcfg.resx = resx; nav->dcfg.resy = resy;
+    nav->dcfg.half_x = (double)((float)resx / 2.0f); nav->dcfg.half_y = (double)((float)resy / 2.0f);
+    if (nav->stage) {   // the stage navigator evaluates with the same measurer
+        DevCfg& d = nav->stage->dcfg;
+        d.depth = nav->depth; d.resx = resx; d.resy = resy; d.half_x = nav->dcfg.half_x; d.half_y = nav->dcfg.half_y;
+    }
+    return RBPHD_OK;
+}
 
 int rbphd_set_holdout(rbphd_navigator* nav, int particle)
 {
@@ -996,6 +1034,8 @@ int rbphd_stage_correct(rbphd_navigator* nav, const double* pose7, int n, const 
     if (int r = stage_run(nav, &s, pose7, n, w, mean, cov, z, m)) return r;
     DevCfg saved = s->dcfg;
     make_devcfg(s->cfg, s->dcfg, gate_radius, true);
+    s->dcfg.depth = saved.depth; s->dcfg.resx = saved.resx; s->dcfg.resy = saved.resy;
+    s->dcfg.half_x = saved.half_x; s->dcfg.half_y = saved.half_y;
     if ((long long)n * m + n > s->dump_cap && gate_radius < 0) {
         s->dcfg = saved;
         return fail(nav, RBPHD_ERR_CAPACITY, "ungated stage_correct output exceeds max_pairs");

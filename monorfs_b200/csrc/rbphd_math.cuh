@@ -31,6 +31,11 @@ struct DevCfg {
     double focal, left, right, top, bottom, rmin, rmax;
     int    maxq;
     int    ungated;        // stage tests: gate_radius < 0
+    // KinectMeasurer (KinectMeasurer.cs:123-173): the current depth frame, depth[x * resy + y], or null
+    const float* depth;
+    int    resx, resy;
+    double half_x, half_y; // ResX / 2, ResY / 2 (float divisions, promoted)
+    float  rmin_f;         // RangeClip.Min as the float it is
 };
 
 struct Quat { double w, x, y, z; };
@@ -124,7 +129,8 @@ __device__ __forceinline__ void measure_from_local(const DevCfg& c, const double
     mp[1] = c.focal * local.y / local.z;
 }
 
-// PRM:277-291 (+ SIMV:324-339: times detectionProbability)
+// PRM:277-291 (+ SIMV:324-339: times detectionProbability); with a depth frame attached the occlusion-aware
+// KinectMeasurer.FuzzyVisibleM (KinectMeasurer.cs:151-173): a landmark behind the measured surface is invisible
 __device__ __forceinline__ double detection_probability(const DevCfg& c, const double* z)
 {
     double mind = INFINITY;
@@ -134,7 +140,19 @@ __device__ __forceinline__ double detection_probability(const DevCfg& c, const d
     mind = fmin(mind, (c.bottom - z[1]) / c.ramp[1]);
     mind = fmin(mind, (z[2] - c.rmin) / c.ramp[2]);
     mind = fmin(mind, (c.rmax - z[2]) / c.ramp[2]);
-    return fmax(0.0, fmin(1.0, mind)) * c.pd;
+    mind = fmax(0.0, fmin(1.0, mind));
+    if (c.depth != nullptr) {
+        if (mind == 0) return 0.0;                       // outside of the image region: no depth to look up
+        const int x = (int)(z[0] + c.half_x), y = (int)(z[1] + c.half_y);
+        if (x < 0 || x >= c.resx || y < 0 || y >= c.resy) return 0.0;
+        const float d = c.depth[(size_t)x * c.resy + y];
+        if (d != d) return 0.0;
+        const float range = (float)z[2];
+        mind = fmin(mind, (double)(range - c.rmin_f) / c.ramp[2]);
+        mind = fmin(mind, (double)(d - range) / c.ramp[2]);
+        mind = fmax(0.0, fmin(1.0, mind));
+    }
+    return mind * c.pd;
 }
 
 // PRM:299-312

@@ -296,6 +296,15 @@ def set_loglikelihood(cfg, pose, jm, z):
     return lib().orc_set_loglikelihood(C.byref(cfg), _pose(pose)[1], len(jm), _p(jm), len(z), _p(z))
 
 
+def set_depth_frame(depth_xy):
+    """KinectMeasurer variant: depth_xy[x, y] float32 metres (NaN = no reading); None detaches."""
+    if depth_xy is None:
+        lib().orc_set_depth_frame(None, 0, 0)
+        return
+    d = np.ascontiguousarray(depth_xy, dtype=np.float32)
+    lib().orc_set_depth_frame(d.ctypes.data_as(C.POINTER(C.c_float)), d.shape[0], d.shape[1])
+
+
 def quasi_set_loglikelihood(cfg, pose, jm, z):
     jm = np.ascontiguousarray(jm, dtype=np.float64).reshape(-1, 3)
     z = _z(z)

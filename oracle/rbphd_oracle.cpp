@@ -368,6 +368,11 @@ void measure_to_map(const orc_config* c, const double* pose, const double* z, do
     out[0] = p.t[0] + r.x; out[1] = p.t[1] + r.y; out[2] = p.t[2] + r.z;
 }
 
+/* depth frame of the KinectMeasurer variant (test infrastructure: one global frame, set by orc_set_depth_frame) */
+static const float* g_depth = nullptr;
+static int g_resx = 0, g_resy = 0;
+static std::vector<float> g_depth_store;
+
 double fuzzy_visible(const orc_config* c, const double* z)
 {
     double mind = kInf;
@@ -389,7 +394,20 @@ double fuzzy_visible(const orc_config* c, const double* z)
     mind = std::fmin(mind, (bottom - z[1]) / c->visibility_ramp[1]);
     mind = std::fmin(mind, (z[2] - rmin) / c->visibility_ramp[2]);
     mind = std::fmin(mind, (rmax - z[2]) / c->visibility_ramp[2]);
-    return std::fmax(0, std::fmin(1, mind));
+    mind = std::fmax(0, std::fmin(1, mind));
+    if (g_depth) {   /* KinectMeasurer.FuzzyVisibleM, KinectMeasurer.cs:151-173 */
+        if (mind == 0) return 0;
+        float resx = (float)g_resx, resy = (float)g_resy;
+        int x = (int)(z[0] + resx / 2), y = (int)(z[1] + resy / 2);
+        if (x < 0 || x >= g_resx || y < 0 || y >= g_resy) return 0;   /* (the C# would throw; unreachable inside the film) */
+        float d = g_depth[(size_t)x * g_resy + y];
+        if (std::isnan(d)) return 0;
+        float range = (float)z[2], rminf = (float)c->measurer[1];
+        mind = std::fmin(mind, (range - rminf) / c->visibility_ramp[2]);
+        mind = std::fmin(mind, (d - range) / c->visibility_ramp[2]);
+        mind = std::fmax(0, std::fmin(1, mind));
+    }
+    return mind;
 }
 
 /* SIMV:324-339 */
@@ -1317,6 +1335,12 @@ double orc_set_loglikelihood(const orc_config* c, const double* pose, int J, con
                              const double* z)
 {
     return set_loglikelihood(c, pose, J, jm, M, z);
+}
+void orc_set_depth_frame(const float* depth_xy, int resx, int resy)
+{
+    if (!depth_xy) { g_depth = nullptr; g_depth_store.clear(); return; }
+    g_depth_store.assign(depth_xy, depth_xy + (size_t)resx * resy);
+    g_depth = g_depth_store.data(); g_resx = resx; g_resy = resy;
 }
 double orc_quasi_set_loglikelihood(const orc_config* c, const double* pose, int J, const double* jm, int M,
                                    const double* z)

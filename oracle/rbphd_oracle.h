@@ -86,6 +86,9 @@ int orc_prune(const orc_config* c, int n, const double* w, const double* m, cons
 int orc_best_map_estimate(int n, const double* w, int cap, int* picks);
 double orc_set_loglikelihood(const orc_config* c, const double* pose, int J, const double* jm, int M,
                              const double* z);
+/* KinectMeasurer.FuzzyVisibleM (KinectMeasurer.cs:151-173): attach a depth frame depth_xy[x * resy + y] to the
+ * PRM3D measurer of every following call (NULL detaches).  One global frame: test infrastructure. */
+void orc_set_depth_frame(const float* depth_xy, int resx, int resy);
 /* PHD:526-532, 561-713 (value only): full visibility, gate d < 12 */
 double orc_quasi_set_loglikelihood(const orc_config* c, const double* pose, int J, const double* jm, int M,
                                    const double* z);

@@ -154,3 +154,67 @@ def test_filter_missing_batch_equals_single_filters(capi, orc, synth):
     counts = h.get_map_counts()
     assert len(set(counts.tolist())) > 1                # the held-out frame matters
     h.close()
+
+
+def test_kinect_depth_visibility(capi, orc, synth):
+    """KinectMeasurer.FuzzyVisibleM (KinectMeasurer.cs:151-173): with a depth frame attached, landmarks behind the
+    measured surface lose their detection probability -- SLAM frames and the per-stage calls against the oracle."""
+    P, N, M = 4, 80, 30
+    border = 8
+    meas = list(synth.MEASURER)
+    meas[3], meas[4], meas[5], meas[6] = -320 + border, -240 + border, 640 - 2 * border, 480 - 2 * border   # deflated film
+    sc = synth.make_scene(P, N, M, seed=51, measurer=meas, min_effective_particle=0.5)
+    # a wall at 6 m over the left half of the image, open space on the right, a band without readings
+    depth = np.full((640, 480), 9.5, dtype=np.float32)
+    depth[:300, :] = 6.0
+    depth[300:330, :] = np.nan
+    xs = np.arange(640)[:, None]
+    depth[:300, :] += (0.002 * xs[:300]).astype(np.float32)
+    ocfg = orc.make_config(sc.params)
+    h = capi.Handle(sc.params, max_particles=P, max_components=512, max_measurements=M)
+    nav = orc.Navigator(ocfg, P, sc.poses[0])
+    h.reset(P, sc.poses[0], sc.map_w, sc.map_m, sc.map_P)
+    h.set_poses(sc.poses)
+    for i in range(P):
+        nav.set_pose(i, sc.poses[i])
+        nav.set_map(i, sc.map_w, sc.map_m, sc.map_P)
+    try:
+        orc.set_depth_frame(depth)
+        h.set_depth_frame(depth)
+        fr = sc.next_frame()
+        # the stage entry points see the same measurer
+        exp = orc.correct(ocfg, sc.poses[0], sc.map_w, sc.map_m, sc.map_P, fr.z)
+        got = h.stage_correct(sc.poses[0], sc.map_w, sc.map_m, sc.map_P, fr.z)
+        assert len(got[0]) == len(exp[0]) and np.allclose(got[0], exp[0], rtol=RTOL, atol=1e-300)
+        plain = None
+        for f in range(4):
+            h.update(fr.reading, synth.DT, fr.gauss)
+            nav.update(fr.reading, synth.DT, fr.gauss)
+            gbest, gres = h.slam_update(fr.z, fr.u)
+            obest, ores, oanc = nav.slam_update(fr.z, fr.u)
+            assert (gbest, gres) == (obest, ores), f
+            assert h.get_ancestors().tolist() == oanc.tolist()
+            with np.errstate(divide="ignore"):
+                assert np.allclose(np.log(h.get_alphas()), np.log(nav.get_alphas()), rtol=RTOL, atol=0)
+            for i in range(P):
+                gw, gm, gP = h.get_map(i)
+                ow, om, oP = nav.get_map(i)
+                assert len(gw) == len(ow), (f, i)
+                assert np.allclose(gw, ow, rtol=RTOL, atol=1e-300) and np.allclose(gm, om, rtol=RTOL, atol=1e-12)
+            if f == 0:
+                plain = h.get_map(0)[0].copy()
+            fr = sc.next_frame()
+        # occlusion changes the result: the same first frame without the depth frame gives other weights
+        orc.set_depth_frame(None)
+        h.set_depth_frame(None)
+        h.reset(P, sc.poses[0], sc.map_w, sc.map_m, sc.map_P)
+        h.set_poses(sc.poses)
+        sc2 = synth.make_scene(P, N, M, seed=51, measurer=meas, min_effective_particle=0.5)
+        fr0 = sc2.next_frame()
+        h.update(fr0.reading, synth.DT, fr0.gauss)
+        h.slam_update(fr0.z, fr0.u)
+        w0 = h.get_map(0)[0]
+        assert len(w0) != len(plain) or not np.allclose(w0, plain, rtol=1e-6)
+    finally:
+        orc.set_depth_frame(None)
+        h.close()
