@@ -118,7 +118,7 @@ def debug_migration_plan(ancestors, counts, world, rank, device=0):
                 n_recv=int(hdr[2 * world + 1]), sorted=bool(hdr[2 * world + 2]))
 
 
-def bench_fp64(device=0, outer=2000):
+def bench_fp64(device=0, outer=600):
     """FP64 pipe microbenchmark (rbphd_microbench.cu): dict of measured peaks on `device`."""
     lib = load()
     out = (C.c_double * 6)()
