@@ -26,6 +26,10 @@ thread_local std::string g_last_error;
 struct PinnedBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf&) = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
+    PinnedBuf(PinnedBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
     void* get(size_t n)
     {
         if (n > bytes) {
@@ -89,6 +93,8 @@ struct rbphd_navigator {
     int prof_frames = 0, prof_max = 0;
     // host mirrors (library-owned outputs)
     PinnedBuf h_in, h_out, h_state, h_map, h_plan;
+    std::vector<PinnedBuf> slot_stage;     // per input slot: pinned staging of (gauss, z)
+    std::vector<cudaEvent_t> slot_ev;      // ... and the event after its last host-to-device copy
     std::vector<double> o_w, o_m, o_P;
     std::vector<int> o_anc, o_rows, o_cols;
     int ll_flags = 0;
@@ -268,6 +274,7 @@ void free_device(rbphd_navigator* nav)
     cudaFree(nav->vitems); cudaFree(nav->zitems); cudaFree(nav->scratch); cudaFree(nav->dump);
     cudaFree(nav->dump_count); cudaFree(nav->depth);
     for (auto& e : nav->pev) cudaEventDestroy(e);
+    for (auto& e : nav->slot_ev) if (e) cudaEventDestroy(e);
     if (nav->stream) cudaStreamDestroy(nav->stream);
 }
 
@@ -634,14 +641,28 @@ int rbphd_upload_frame_inputs(rbphd_navigator* nav, int slot, const double* gaus
     if (m < 0 || m > nav->Mcap) return fail(nav, RBPHD_ERR_ARGUMENT, "m > max_measurements");
     if (slot < 0 || slot >= nav->slots) return fail(nav, RBPHD_ERR_ARGUMENT, "input slot out of range");
     if (int r = set_device(nav)) return r;
-    size_t gb = gauss ? sizeof(double) * 6 * (size_t)nav->P : 0;
-    size_t zb = z ? sizeof(double) * 3 * (size_t)m : 0;
-    // the pinned staging buffer may still be in flight from the previous frame; size it for both copies
-    // first so that the second cannot reallocate it under the first
-    CK(cudaStreamSynchronize(nav->stream));
-    if (!nav->h_in.get(gb + zb + 16)) return fail(nav, RBPHD_ERR_CUDA, "pinned allocation failed");
-    if (gauss) if (int r = upload(nav, nav->gauss + nav->gstride * (size_t)slot, gauss, gb, 0)) return r;
-    if (z) if (int r = upload(nav, nav->z + nav->zstride * (size_t)slot, z, zb, gb)) return r;
+    const size_t gb = gauss ? sizeof(double) * 6 * (size_t)nav->P : 0;
+    const size_t zb = z ? sizeof(double) * 3 * (size_t)m : 0;
+    if (gb + zb == 0) return RBPHD_OK;
+    // every input slot has its own pinned staging area and an event that says when its last copy has left it: the
+    // upload of frame t+1 does not wait for frame t's kernels (no stream synchronisation here)
+    if ((int)nav->slot_stage.size() < nav->slots) {
+        nav->slot_stage.resize(nav->slots);
+        nav->slot_ev.resize(nav->slots, nullptr);
+    }
+    if (nav->slot_ev[slot]) CK(cudaEventSynchronize(nav->slot_ev[slot]));
+    else CK(cudaEventCreateWithFlags(&nav->slot_ev[slot], cudaEventDisableTiming));
+    char* h = (char*)nav->slot_stage[slot].get(sizeof(double) * (6 * (size_t)nav->maxP + 3 * (size_t)nav->Mcap) + 16);
+    if (!h) return fail(nav, RBPHD_ERR_CUDA, "pinned allocation failed");
+    if (gauss) {
+        std::memcpy(h, gauss, gb);
+        CK(cudaMemcpyAsync(nav->gauss + nav->gstride * (size_t)slot, h, gb, cudaMemcpyHostToDevice, nav->stream));
+    }
+    if (z) {
+        std::memcpy(h + gb, z, zb);
+        CK(cudaMemcpyAsync(nav->z + nav->zstride * (size_t)slot, h + gb, zb, cudaMemcpyHostToDevice, nav->stream));
+    }
+    CK(cudaEventRecord(nav->slot_ev[slot], nav->stream));
     return RBPHD_OK;
 }
 
