@@ -179,6 +179,16 @@ int rbphd_quasi_set_loglikelihood(rbphd_navigator* nav, const double* pose7, int
                                   const double* z, int m, double* loglik);
 int rbphd_set_loglike_matrix(rbphd_navigator* nav, const double* pose7, int j, const double* jmean, const double* z,
                              int m, const int** rows, const int** cols, const double** vals, int* nnz);
+/* QuasiSetLogLikelihood(measurements, map, pose, out gradient) (PHD:544-549, 561-713): the value as this overload
+ * computes it and the pose gradient (6 entries, MeasurementJacobianP's parametrisation, PRM:185-209) -- what
+ * LogLikeGradientAscent / LogLikeFitCovariance evaluate (LoopyPHDNavigator.cs:928-934, 989-994).  The reference's
+ * TemperedAverage (Util/MatrixExtensions.cs:400-440) overwrites the shared 200-entry buffer in place and normalises
+ * it with Accord's Normalize(): sum_normalised = 0 follows that literally (Euclidean norm of the whole buffer);
+ * sum_normalised = 1 divides by the sum instead, the variant the reference's own LogLike2D test
+ * (LoopyPHDNavigatorTest.cs:352-425) passes (oracle/README.md D10). */
+int rbphd_quasi_set_loglikelihood_gradient(rbphd_navigator* nav, const double* pose7, int j, const double* jmean,
+                                           const double* z, int m, int sum_normalised, double* loglik,
+                                           double* gradient6);
 
 /* ---- multi-GPU: particles sharded by rank, collectives inside the library.
  * One navigator per GPU / rank; rank g owns the block [g*P/G, (g+1)*P/G) of the P global particles.  NCCL is

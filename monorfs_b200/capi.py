@@ -50,6 +50,7 @@ EXPORTS = [
     "rbphd_profile_read", "rbphd_get_counters", "rbphd_get_phase_cycles", "rbphd_stream",
     "rbphd_launch_shape", "rbphd_bench_fp64", "rbphd_slam_update_begin", "rbphd_slam_update_finish",
     "rbphd_set_likelihood", "rbphd_quasi_set_loglikelihood", "rbphd_set_loglike_matrix", "rbphd_set_holdout", "rbphd_set_depth_frame",
+    "rbphd_quasi_set_loglikelihood_gradient",
 ]
 
 _lib = None
@@ -391,6 +392,14 @@ class Handle:
         self._ck(self.lib.rbphd_quasi_set_loglikelihood(self._h, _p(_d(pose)), len(jm), _p(jm), _p(z), len(z),
                                                         C.byref(out)))
         return out.value
+
+    def quasi_set_loglikelihood_gradient(self, pose, jm, z, sum_normalised=False):
+        """(value, gradient[6]) of QuasiSetLogLikelihood(..., out gradient) (PHD:544-549)."""
+        jm, z = _d(jm).reshape(-1, 3), _d(z).reshape(-1, 3)
+        out, g = C.c_double(), np.zeros(6)
+        self._ck(self.lib.rbphd_quasi_set_loglikelihood_gradient(self._h, _p(_d(pose)), len(jm), _p(jm), _p(z), len(z),
+                                                                 int(sum_normalised), C.byref(out), _p(g)))
+        return out.value, g
 
     def set_loglike_matrix(self, pose, jm, z):
         """SetLogLikeMatrix (PHD:415-460) as sorted (row, col, value) triplets."""

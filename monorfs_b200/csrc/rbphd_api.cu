@@ -258,7 +258,7 @@ void make_layout(ScratchLayout& l, int cap, int Mcap, int cap_pairs, int maxq)
     take(l.gitems, I * l.cap_nodes);
     take(l.vsum, D * l.cap_j);
     take(l.erad, D * l.cap_pred); take(l.erad2, D * l.cap_pred); take(l.cnorm, D * l.cap_pred); take(l.crad, D * l.cap_pred);   // exploration bound per component
-    take(l.llkey, U * l.cap_ll);     take(l.llval, D * l.cap_ll);
+    take(l.llkey, U * l.cap_ll);     take(l.llval, D * l.cap_ll);   take(l.llgrad, 6 * D * l.cap_ll);
     take(l.uf, I * (l.cap_j + Mcap + 2)); take(l.bcnt, I * (l.cap_j + Mcap + 2));
     take(l.mslots, murty_workspace_bytes());
     l.bytes = align_up(off, 256);
@@ -1160,6 +1160,19 @@ int rbphd_quasi_set_loglikelihood(rbphd_navigator* nav, const double* pose7, int
 {
     if (!nav) return RBPHD_ERR_ARGUMENT;
     return stage_setll(nav, pose7, j, jmean, z, m, LL_QUASI, loglik, nullptr);
+}
+
+int rbphd_quasi_set_loglikelihood_gradient(rbphd_navigator* nav, const double* pose7, int j, const double* jmean,
+                                           const double* z, int m, int sum_normalised, double* loglik, double* gradient6)
+{
+    if (!nav || !gradient6) return RBPHD_ERR_ARGUMENT;
+    rbphd_navigator* s = nullptr;
+    const int flags = LL_QUASI | LL_GRADIENT | (sum_normalised ? LL_TEMPERED_SUM : 0);
+    if (int r = stage_setll(nav, pose7, j, jmean, z, m, flags, loglik, &s)) return r;
+    void* h;
+    if (int r = download(s, s->alpha_parts, sizeof(double) * 8, &h)) return fail(nav, r, s->error);
+    std::memcpy(gradient6, h, 6 * sizeof(double));
+    return RBPHD_OK;
 }
 
 int rbphd_set_loglike_matrix(rbphd_navigator* nav, const double* pose7, int j, const double* jmean, const double* z,

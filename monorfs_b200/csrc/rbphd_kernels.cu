@@ -13,6 +13,8 @@
 // -fmad=false so results match the CPU oracle bit for bit apart from libm transcendentals.
 #include "rbphd_kernels.cuh"
 
+#include <mutex>
+
 
 namespace rbphd {
 
@@ -24,6 +26,7 @@ struct Ctx {
     int status;
     unsigned long long selkey;
     double pose[7];
+    double grad[6];    // MODE_STAGE_SETLL with LL_GRADIENT: pose gradient of the quasi set log-likelihood
     CellGrid grid;
     CellGrid vg;       // copy of the frame's camera-frame measurement grid header
     long long tlast;
@@ -109,7 +112,7 @@ struct Slab {
     int *jidx;
     double *jm, *jmp, *jpd, *vsum, *erad, *erad2, *cnorm, *crad;
     unsigned long long* llkey;
-    double* llval;
+    double *llval, *llgrad;
     int *uf;
     int* bcnt;
     unsigned char* mslots;
@@ -136,6 +139,7 @@ __device__ __forceinline__ Slab make_slab(unsigned char* base, const ScratchLayo
     s.erad2 = (double*)(base + l.erad2);
     s.cnorm = (double*)(base + l.cnorm); s.crad = (double*)(base + l.crad);
     s.llkey = (unsigned long long*)(base + l.llkey); s.llval = (double*)(base + l.llval);
+    s.llgrad = (double*)(base + l.llgrad);
     s.uf = (int*)(base + l.uf); s.bcnt = (int*)(base + l.bcnt);
     s.mslots = base + l.mslots;
     return s;
@@ -1343,7 +1347,11 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) k_particle_update(const __
             }
             __syncthreads();
             double ll = phase_set_loglikelihood(p, sm, s, min(J, capj));
-            if (tid == 0) p.alphas[particle] = ll;
+            if (tid == 0) {
+                p.alphas[particle] = ll;
+                if ((p.ll_flags & LL_GRADIENT) && p.alpha_parts)
+                    for (int a = 0; a < 6; a++) p.alpha_parts[(size_t)particle * 8 + a] = sm.ctx.grad[a];
+            }
         }
         __syncthreads();
         PHASE_MARK(sm, 15);
@@ -1908,7 +1916,20 @@ size_t particle_update_smem(int max_measurements, size_t* sort_cap)
 
 int particle_update_max_ctas_per_sm(size_t smem)
 {
-    cudaFuncSetAttribute(k_particle_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // The attribute belongs to the function on the current device, not to a handle: navigators with different
+    // max_measurements coexist (and a smaller one created later must not lower the limit under an older, larger one)
+    static std::mutex mu;
+    static size_t granted[64] = {0};
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        size_t& g = granted[(dev >= 0 && dev < 64) ? dev : 0];
+        if (smem > g) {
+            if (cudaFuncSetAttribute(k_particle_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess)
+                g = smem;
+        }
+    }
     int n = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_particle_update, kBlock, smem);
     return n;

@@ -53,7 +53,7 @@ struct ScratchLayout {
     size_t tw, tm, tloc, rho;
     size_t edst, nstate, nowner, nflag, gitems;
     // weight stage
-    size_t jidx, jm, jmp, jpd, vsum, erad, erad2, cnorm, crad, llkey, llval, uf, bcnt, mslots;
+    size_t jidx, jm, jmp, jpd, vsum, erad, erad2, cnorm, crad, llkey, llval, llgrad, uf, bcnt, mslots;
     size_t bytes;
 };
 
@@ -87,7 +87,7 @@ struct KParams {
     int holdout;           // MODE_FRAME: this particle skips the frame (its map is carried over unchanged); -1 = none
 };
 
-enum LikelihoodFlags { LL_QUASI = 1, LL_DUMP_MATRIX = 2 };   // KParams::ll_flags (MODE_STAGE_SETLL)
+enum LikelihoodFlags { LL_QUASI = 1, LL_DUMP_MATRIX = 2, LL_GRADIENT = 4, LL_TEMPERED_SUM = 8 };   // KParams::ll_flags (MODE_STAGE_SETLL)
 
 struct Reading6 { double v[6]; };
 void launch_predict_pose(cudaStream_t s, const DevCfg& cfg, int P, double* poses, Reading6 reading, double dt,

@@ -32,6 +32,8 @@ struct MurtyWork {
     double bigvals[kMurtyBig][200];
     int bigcnt[kMurtyBig], bighead[kMurtyBig];
     double tmpvals[200];
+    double lgrad[200 * 6];       // gradient lane: pose-gradient sum of every assignment of the current block
+    signed char lperm[200 * 5];  // ... and the assignments of a lexicographically enumerated block
 };
 
 // GC:64-175 on a dense n x n matrix whose undefined entries are -inf.  false = "no solution".

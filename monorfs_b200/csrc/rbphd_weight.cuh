@@ -263,7 +263,8 @@ __device__ inline void fill_block(const DevCfg& c, const Slab& s, const unsigned
     }
 }
 
-__device__ inline int lexicographical_values(const double* Mx, int n, int modelsize, double* vals);
+__device__ inline int lexicographical_values(const double* Mx, int n, int modelsize, double* vals,
+                                             signed char* perms = nullptr);
 
 // logcomp[m] as the reference's shared 200-entry buffer holds it when the block starting at edge `head`
 // begins (quirk A9.4): the m-th value of the most recent earlier block that produced more than m values
@@ -339,8 +340,10 @@ __device__ double murty_lane(const KParams& p, Smem& sm, const Slab& s, MurtyWor
     return contrib;
 }
 
-// GC:280-350 on a dense n x n block (n <= 5), values pushed to vals (at most 200: PHD:469,503)
-__device__ inline int lexicographical_values(const double* Mx, int n, int modelsize, double* vals)
+// GC:280-350 on a dense n x n block (n <= 5), values pushed to vals (at most 200: PHD:469,503); perms (optional):
+// the assignment of every value, five entries each
+__device__ inline int lexicographical_values(const double* Mx, int n, int modelsize, double* vals,
+                                             signed char* perms)
 {
     int perm[5];
     for (int i = 0; i < n; i++) perm[i] = i;
@@ -358,9 +361,13 @@ __device__ inline int lexicographical_values(const double* Mx, int n, int models
         for (int i = 1; i < n; i++) if (perm[i - 1] < perm[i]) return false;
         return true;
     };
+    auto push = [&](int m) {
+        vals[m] = value();
+        if (perms) for (int i = 0; i < 5; i++) perms[5 * m + i] = (signed char)((i < n) ? perm[i] : -1);
+    };
     int m = 0;
     reverse(ms, n);
-    vals[m++] = value();
+    push(m++);
     while (!last() && m < 200) {
         int a, b;
         for (a = n - 2; a > 0; a--) if (perm[a] < perm[a + 1]) break;
@@ -368,9 +375,120 @@ __device__ inline int lexicographical_values(const double* Mx, int n, int models
         int t = perm[a]; perm[a] = perm[b]; perm[b] = t;
         reverse(a + 1, n);
         reverse(ms, n);
-        vals[m++] = value();
+        push(m++);
     }
     return m;
+}
+
+// MeasurementJacobianP (PRM:185-209): d h(m) / d pose, 3 x 6 row-major: Jproj * [ -R(q*) | -R(q*) [diff]_x ]
+__device__ inline void jacobian_p(const DevCfg& c, const Pose& p, const double* diff, const Quat& l, double* Jp)
+{
+    double mag = ((l.z > 0) ? 1 : -1) * sqrt(l.x * l.x + l.y * l.y + l.z * l.z);
+    double jp[9];
+    jp[0] = c.focal / l.z; jp[1] = 0;             jp[2] = -c.focal * l.x / (l.z * l.z);
+    jp[3] = 0;             jp[4] = c.focal / l.z; jp[5] = -c.focal * l.y / (l.z * l.z);
+    jp[6] = l.x / mag;     jp[7] = l.y / mag;     jp[8] = l.z / mag;
+    double rot[9], jloc[9], jrot[9];
+    qtomatrix(qconj(p.q), rot);
+    for (int i = 0; i < 9; i++) jloc[i] = -1.0 * rot[i];
+    const double cross[9] = {0, -diff[2], diff[1], diff[2], 0, -diff[0], -diff[1], diff[0], 0};   // UTIL:107-112
+    mat3_mul(jloc, cross, jrot);
+    for (int r = 0; r < 3; r++)
+        for (int cc = 0; cc < 6; cc++) {
+            double s = 0;
+            for (int k = 0; k < 3; k++) s += jp[r * 3 + k] * ((cc < 3) ? jloc[k * 3 + cc] : jrot[k * 3 + cc - 3]);
+            Jp[r * 6 + cc] = s;
+        }
+}
+
+// QuasiSetLogLikelihood with the gradient (PHD:544-549, 561-713), one thread, blocks in the reference's order with
+// its REAL shared 200-entry logcomp buffer: TemperedAverage (MX:400-440) overwrites logcomp[0, m) with exp(w - max)
+// and normalises over the whole buffer (stale entries included), and the Murty lane's early exit reads that buffer.
+// skey / sval: the detection edges sorted by (block label, landmark, measurement); grads: 6 doubles per edge.
+__device__ double quasi_gradient_serial(const KParams& p, Smem& sm, const Slab& s, MurtyWork& mw,
+                                        const unsigned long long* skey, const unsigned int* sval, int nll, int J,
+                                        const int* deg, double* gradient)
+{
+    const DevCfg& c = p.cfg;
+    const int M = p.M;
+    double* logcomp = mw.tmpvals;          // 200 entries, persistent across the blocks
+    double* dl = mw.lgrad;                 // 200 x 6: gradient sum of every assignment of the current block
+    for (int i = 0; i < 200; i++) logcomp[i] = 0;
+    for (int a = 0; a < 6; a++) gradient[a] = 0;
+    double total = 0;
+    const bool sumnorm = (p.ll_flags & LL_TEMPERED_SUM) != 0;
+    auto edge_grad = [&](int e, int end, int t, int k) -> const double* {
+        for (int q = e; q < end; q++)
+            if ((int)((skey[q] >> 20) & 0xfffff) == t && (int)(skey[q] & 0xfffff) == k) return s.llgrad + 6 * (size_t)sval[q];
+        return nullptr;
+    };
+    auto finish_block = [&](int m) {
+        total += log_sum_exp(logcomp, m);
+        double mx = -INFINITY;
+        for (int i = 0; i < m; i++) mx = fmax(mx, logcomp[i]);
+        if (isinf(mx) && mx < 0) return;
+        for (int i = 0; i < m; i++) logcomp[i] = exp(logcomp[i] - mx);
+        double norm = 0;
+        if (sumnorm) { for (int i = 0; i < 200; i++) norm += logcomp[i]; }
+        else { for (int i = 0; i < 200; i++) norm += logcomp[i] * logcomp[i]; norm = sqrt(norm); }
+        double avg[6] = {0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < m; i++) {
+            const double wi = (norm == 0) ? logcomp[i] : logcomp[i] / norm;
+            for (int a = 0; a < 6; a++) avg[a] = avg[a] + wi * dl[6 * i + a];
+        }
+        for (int a = 0; a < 6; a++) gradient[a] = gradient[a] + avg[a];
+    };
+    for (int e = 0; e < nll;) {
+        const unsigned long long lab = skey[e] >> 40;
+        int end = e + 1;
+        while (end < nll && (skey[end] >> 40) == lab) end++;
+        int ts[kMurtyN], ks[kMurtyN], a, b;
+        const int n = collect_block(skey, e, end, kMurtyN, ts, ks, &a, &b);
+        if (n < 0) { sm.ctx.status |= ST_OVER_BLOCK; e = end; continue; }
+        int m = 0;
+        if (n <= 5) {
+            double Mx[25];
+            signed char* perms = mw.lperm;
+            fill_block(c, s, skey, sval, e, end, ts, ks, a, b, Mx, 5);
+            m = lexicographical_values(Mx, n, J, logcomp, perms);
+            for (int i = 0; i < m; i++) {
+                for (int q = 0; q < 6; q++) dl[6 * i + q] = 0;
+                for (int r = 0; r < a; r++) {
+                    const int col = perms[5 * i + r];
+                    if (col >= 0 && col < b) {
+                        const double* g = edge_grad(e, end, ts[r], ks[col]);
+                        if (g) for (int q = 0; q < 6; q++) dl[6 * i + q] = dl[6 * i + q] + g[q];
+                    }
+                }
+            }
+        }
+        else {
+            fill_block(c, s, skey, sval, e, end, ts, ks, a, b, mw.profit, kMurtyN);
+            murty_begin(mw, n);
+            double v;
+            while (murty_next(mw, n, &v)) {
+                if (m >= 200 || logcomp[m] - logcomp[0] < -10) break;   // PHD:503 on the live buffer
+                logcomp[m] = v;
+                for (int q = 0; q < 6; q++) dl[6 * m + q] = 0;
+                const MurtyNode& nd = mw.nodes[mw.best];
+                for (int r = 0; r < a; r++) {
+                    const int col = nd.assign[r];
+                    if (col >= 0 && col < b) {
+                        const double* g = edge_grad(e, end, ts[r], ks[col]);
+                        if (g) for (int q = 0; q < 6; q++) dl[6 * m + q] = dl[6 * m + q] + g[q];
+                    }
+                }
+                m++;
+            }
+            if (mw.overflow) sm.ctx.status |= ST_OVER_MURTY;
+        }
+        finish_block(m);
+        e = end;
+    }
+    // blocks without a detection (one value each, no gradient; they come last and only ever touch logcomp[0])
+    for (int t = 0; t < J; t++) if (deg[t] == 0) total += log(1 - s.jpd[t]);
+    for (int k = 0; k < M; k++) if (deg[J + k] == 0) total += c.logclutter;
+    return total;
 }
 
 __device__ __forceinline__ bool grid_range3(const CellGrid& g, const double* q, const double* r, int* lo, int* hi)
@@ -403,6 +521,7 @@ __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab
     // QuasiSetLogLikelihood (PHD:561-713) is the same computation with full visibility (PD_i = PD) and a wider
     // association gate (d < 12 instead of d < 5)
     const bool quasi = (p.ll_flags & LL_QUASI) != 0;
+    const bool want_grad = (p.ll_flags & LL_GRADIENT) != 0;
     const double gate = quasi ? 12.0 : 5.0;
     const double rad[3] = {gate * sqrt(c.R[0]) * (1 + 1e-9), gate * sqrt(c.R[4]) * (1 + 1e-9),
                            gate * sqrt(c.R[8]) * (1 + 1e-9)};
@@ -430,6 +549,21 @@ __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab
                         if (idx < capll) {
                             s.llkey[idx] = ((unsigned long long)t << 32) | (unsigned)k;
                             s.llval[idx] = lw + c.logmultR - 0.5 * d * d;
+                            if (want_grad) {   // (z - h)^T R^-1 Jp (PHD:620-623)
+                                double Jp[18], row[3];
+                                jacobian_p(c, pose, diff, local, Jp);
+                                const double dz[3] = {-d3[0], -d3[1], -d3[2]};
+                                for (int bb = 0; bb < 3; bb++) {
+                                    double sum = 0;
+                                    for (int aa = 0; aa < 3; aa++) sum += dz[aa] * c.Rinv[aa * 3 + bb];
+                                    row[bb] = sum;
+                                }
+                                for (int l = 0; l < 6; l++) {
+                                    double sum = 0;
+                                    for (int bb = 0; bb < 3; bb++) sum += row[bb] * Jp[bb * 6 + l];
+                                    s.llgrad[6 * (size_t)idx + l] = sum;
+                                }
+                            }
                         }
                         atomicAdd(&deg[t], 1);
                         atomicAdd(&deg[J + k], 1);
@@ -491,6 +625,16 @@ __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab
     block_bitonic_sort(skey, sval, n2);
 
     PHASE_MARK(sm, 26);
+    if (want_grad) {
+        __shared__ double s_total;
+        if (tid == 0) {
+            double g[6];
+            s_total = quasi_gradient_serial(p, sm, s, *reinterpret_cast<MurtyWork*>(s.mslots), skey, sval, nll, J, deg, g);
+            for (int a = 0; a < 6; a++) sm.ctx.grad[a] = g[a];
+        }
+        __syncthreads();
+        return s_total;
+    }
     double contrib = 0;
     __shared__ int s_nbig;
     if (tid == 0) s_nbig = 0;

@@ -62,6 +62,7 @@ def lib():
         _lib.orc_gaussian_evaluate.restype = C.c_double
         _lib.orc_set_loglikelihood.restype = C.c_double
         _lib.orc_quasi_set_loglikelihood.restype = C.c_double
+        _lib.orc_quasi_set_loglikelihood_gradient.restype = C.c_double
         _lib.orc_nav_new.restype = C.c_void_p
     return _lib
 
@@ -309,6 +310,21 @@ def quasi_set_loglikelihood(cfg, pose, jm, z):
     jm = np.ascontiguousarray(jm, dtype=np.float64).reshape(-1, 3)
     z = _z(z)
     return lib().orc_quasi_set_loglikelihood(C.byref(cfg), _pose(pose)[1], len(jm), _p(jm), len(z), _p(z))
+
+
+def quasi_set_loglikelihood_gradient(cfg, pose, jm, z):
+    """(value, gradient[OdoSize]) of PHD:544-549."""
+    jm = np.ascontiguousarray(jm, dtype=np.float64).reshape(-1, 3)
+    z = _z(z)
+    g = np.zeros(6)
+    v = lib().orc_quasi_set_loglikelihood_gradient(C.byref(cfg), _pose(pose)[1], len(jm), _p(jm), len(z), _p(z), _p(g))
+    return v, g[:(6 if cfg.model == 0 else 2)]
+
+
+def measurement_jacobian_p(cfg, pose, m):
+    out = np.zeros(18)
+    lib().orc_measurement_jacobian_p(C.byref(cfg), _pose(pose)[1], _p(np.ascontiguousarray(m, dtype=np.float64)), _p(out))
+    return out.reshape(3, 6)
 
 
 def set_loglike_matrix(cfg, pose, jm, z, quasi=False):

@@ -352,6 +352,36 @@ void jacobian_l(const orc_config* c, const double* pose, const double* m, double
     matmul(jp, 3, 3, 3, jr, 3, 3, H, 3);
 }
 
+inline int odo_size(const orc_config* c) { return c->model == 0 ? 6 : 2; }
+
+/* MeasurementJacobianP: dz x OdoSize, stride 6 (PRM:185-209; Linear2DMeasurer.cs:133-137) */
+void jacobian_p(const orc_config* c, const double* pose, const double* m, double* Jp)
+{
+    for (int i = 0; i < 18; i++) Jp[i] = 0;
+    if (c->model == 1) {
+        Jp[0] = -1; Jp[6 + 1] = -1;
+        return;
+    }
+    Pose p = pose_load(pose);
+    double diff[3] = {m[0] - p.t[0], m[1] - p.t[1], m[2] - p.t[2]};
+    Quat l = qmul(qmul(qconj(p.q), Quat{0, diff[0], diff[1], diff[2]}), p.q);
+    double f = c->measurer[0];
+    double mag = ((l.z > 0) ? 1 : -1) * std::sqrt(l.x * l.x + l.y * l.y + l.z * l.z);
+    double jp[9] = {f / l.z, 0,       -f * l.x / (l.z * l.z),
+                    0,       f / l.z, -f * l.y / (l.z * l.z),
+                    l.x / mag, l.y / mag, l.z / mag};
+    double rot[9], jloc[9], cross[9], jrot[9];
+    qtomatrix(qconj(p.q), rot);
+    for (int i = 0; i < 9; i++) jloc[i] = -1.0 * rot[i];                 /* (-1.0).Multiply(R(q*)) */
+    double cr[9] = {0, -diff[2], diff[1], diff[2], 0, -diff[0], -diff[1], diff[0], 0};   /* UTIL:107-112 */
+    std::memcpy(cross, cr, sizeof cr);
+    matmul(jloc, 3, 3, 3, cross, 3, 3, jrot, 3);
+    double jlocal[18];
+    for (int r = 0; r < 3; r++)
+        for (int k = 0; k < 3; k++) { jlocal[r * 6 + k] = jloc[r * 3 + k]; jlocal[r * 6 + 3 + k] = jrot[r * 3 + k]; }
+    matmul(jp, 3, 3, 3, jlocal, 6, 6, Jp, 6);
+}
+
 void measure_to_map(const orc_config* c, const double* pose, const double* z, double* out)
 {
     if (c->model == 1) {   /* Linear2DMeasurer.cs:198-201 */
@@ -1042,6 +1072,112 @@ double set_loglikelihood(const orc_config* c, const double* pose, int J, const d
     return total;
 }
 
+/* MX:400-440 TemperedAverage: softmax-like average of the vectors with log-weights weights[begin, end) -- which it
+ * overwrites IN PLACE with exp(w - max) (the caller's logcomp buffer), then normalises with Accord's Normalize():
+ * the EUCLIDEAN norm of the whole array, stale entries beyond `end` included (the same extension method makes unit
+ * vectors in QuaternionTest.cs:103 and Manipulator.cs:720).  nvec = length of the arrays (200). */
+static int g_tempered_sum = 0;
+void tempered_average(const std::vector<std::vector<double> >& vectors, double* weights, int nvec, int begin, int end,
+                      int dim, double* value)
+{
+    for (int a = 0; a < dim; a++) value[a] = 0;
+    double mx = -kInf;
+    for (int i = begin; i < end; i++) mx = std::fmax(mx, weights[i]);
+    if (std::isinf(mx) && mx < 0) return;
+    for (int i = begin; i < end; i++) weights[i] = std::exp(weights[i] - mx);
+    double norm = 0;
+    if (g_tempered_sum) { for (int i = 0; i < nvec; i++) norm += weights[i]; }   /* experiment switch, see orc_set_tempered_norm */
+    else { for (int i = 0; i < nvec; i++) norm += weights[i] * weights[i]; norm = std::sqrt(norm); }
+    for (int i = begin; i < end; i++) {
+        double wi = (norm == 0) ? weights[i] : weights[i] / norm;
+        for (int a = 0; a < dim; a++) value[a] = value[a] + wi * vectors[i][a];
+    }
+}
+
+/* PHD:561-713 with calcgradient = true: the value (its Murty early exit reads the buffer TemperedAverage mutated, so
+ * it can differ from the value-only overload) and the pose gradient (OdoSize entries) */
+double quasi_set_loglikelihood_gradient(const orc_config* c, const double* pose, int J, const double* jm, int M,
+                                        const double* z, double* gradient)
+{
+    const int dz = meas_dim(c), od = odo_size(c);
+    Sparse llmatrix(J + M, J + M, -kInf);
+    const double logPD = std::log(c->pd), log1PD = std::log(1 - c->pd), logclutter = std::log(c->clutter);
+    std::vector<Gaussian> zprobs(J);
+    std::vector<double> zjac(18 * (size_t)std::max(J, 1));
+    for (int i = 0; i < J; i++) {
+        double ml[3];
+        measure_perfect(c, pose, jm + 3 * i, ml);
+        zprobs[i] = make_gaussian(ml, c->R, 1.0, dz);
+    }
+    for (int i = 0; i < J; i++) jacobian_p(c, pose, jm + 3 * i, &zjac[18 * (size_t)i]);
+    std::vector<std::vector<double> > dlldp((size_t)J * std::max(M, 1));   /* [i * M + k], empty = zeros */
+    for (int i = 0; i < J; i++)
+        for (int k = 0; k < M; k++) {
+            const double* m = z + 3 * k;
+            double d = mahalanobis(zprobs[i], m);
+            if (d < 12) {
+                llmatrix.set(i, k, logPD + std::log(zprobs[i].mult) - 0.5 * d * d);
+                double diff[3], row[3];
+                for (int a = 0; a < dz; a++) diff[a] = m[a] - zprobs[i].m[a];
+                for (int b = 0; b < dz; b++) {          /* (1 x dz) . Sigma^-1 */
+                    double sum = 0;
+                    for (int a = 0; a < dz; a++) sum += diff[a] * zprobs[i].Pinv[a * 3 + b];
+                    row[b] = sum;
+                }
+                std::vector<double> g(od);
+                for (int l = 0; l < od; l++) {          /* . zjacobians[i] */
+                    double sum = 0;
+                    for (int b = 0; b < dz; b++) sum += row[b] * zjac[18 * (size_t)i + b * 6 + l];
+                    g[l] = sum;
+                }
+                dlldp[(size_t)i * M + k] = g;
+            }
+        }
+    for (int i = 0; i < J; i++) llmatrix.set(i, M + i, log1PD);
+    for (int i = 0; i < M; i++) llmatrix.set(J + i, i, logclutter);
+
+    std::vector<Sparse> connected = connected_components(llmatrix);
+    double logcomp[200];
+    for (int i = 0; i < 200; i++) logcomp[i] = 0;
+    std::vector<std::vector<double> > dlogcompdp(200);
+    double total = 0;
+    for (int a = 0; a < od; a++) gradient[a] = 0;
+
+    for (size_t ci = 0; ci < connected.size(); ci++) {
+        std::vector<int> rows, cols;
+        Sparse component = connected[ci].compact(rows, cols);
+        for (size_t k = 0; k < rows.size(); k++)
+            if (rows[k] >= J)
+                for (size_t h = 0; h < cols.size(); h++)
+                    if (cols[h] >= M) component.set((int)k, (int)h, 0);
+        PairingEnumerator* en;
+        bool enumerateall;
+        if (component.rows.size() <= 5) { en = new LexEnumerator(component, J); enumerateall = true; }
+        else                            { en = new MurtyEnumerator(component);  enumerateall = false; }
+        int m = 0;
+        std::vector<int> perm;
+        double value;
+        while (en->next(perm, value)) {
+            if (m >= 200 || (!enumerateall && logcomp[m] - logcomp[0] < -10)) break;
+            logcomp[m] = value;
+            dlogcompdp[m].assign(od, 0.0);
+            for (size_t p = 0; p < perm.size(); p++) {
+                int r = rows[p], q = cols[perm[p]];
+                if (r < J && q < M && !dlldp[(size_t)r * M + q].empty())
+                    for (int a = 0; a < od; a++) dlogcompdp[m][a] = dlogcompdp[m][a] + dlldp[(size_t)r * M + q][a];
+            }
+            m++;
+        }
+        delete en;
+        total += log_sum_exp(logcomp, 0, m);
+        double avg[6];
+        for (int i = m; i < 200; i++) if (dlogcompdp[i].empty()) dlogcompdp[i].assign(od, 0.0);
+        tempered_average(dlogcompdp, logcomp, 200, 0, m, od, avg);
+        for (int a = 0; a < od; a++) gradient[a] = gradient[a] + avg[a];
+    }
+    return total;
+}
+
 /* PHD:373-393 */
 void weight_alpha(const orc_config* c, const double* pose, int M, const double* z, const Map& predicted,
                   const Map& corrected, double* out)
@@ -1346,6 +1482,16 @@ double orc_quasi_set_loglikelihood(const orc_config* c, const double* pose, int 
                                    const double* z)
 {
     return set_loglikelihood(c, pose, J, jm, M, z, true);
+}
+double orc_quasi_set_loglikelihood_gradient(const orc_config* c, const double* pose, int J, const double* jm, int M,
+                                            const double* z, double* gradient)
+{
+    return quasi_set_loglikelihood_gradient(c, pose, J, jm, M, z, gradient);
+}
+void orc_set_tempered_norm(int sum_instead_of_euclidean) { g_tempered_sum = sum_instead_of_euclidean; }
+void orc_measurement_jacobian_p(const orc_config* c, const double* pose, const double m[3], double out[18])
+{
+    jacobian_p(c, pose, m, out);
 }
 int orc_set_loglike_matrix(const orc_config* c, const double* pose, int J, const double* jm, int M, const double* z,
                            int quasi, int cap, int* rows, int* cols, double* vals)

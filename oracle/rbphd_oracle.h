@@ -92,6 +92,13 @@ void orc_set_depth_frame(const float* depth_xy, int resx, int resy);
 /* PHD:526-532, 561-713 (value only): full visibility, gate d < 12 */
 double orc_quasi_set_loglikelihood(const orc_config* c, const double* pose, int J, const double* jm, int M,
                                    const double* z);
+/* PHD:544-549, 561-713 with the gradient: returns the value, fills gradient[OdoSize] (6 for PRM3D, 2 for Linear2D) */
+double orc_quasi_set_loglikelihood_gradient(const orc_config* c, const double* pose, int J, const double* jm, int M,
+                                            const double* z, double* gradient);
+/* experiment switch for D10 (oracle/README.md): 1 = TemperedAverage normalises by the sum instead of Accord's Euclidean norm */
+void orc_set_tempered_norm(int sum_instead_of_euclidean);
+/* MeasurementJacobianP (PRM:185-209, Linear2DMeasurer.cs:133-137): dz x OdoSize, row stride 6 */
+void orc_measurement_jacobian_p(const orc_config* c, const double* pose, const double m[3], double out[18]);
 /* PHD:415-460 (quasi: PHD:561-640) as triplets in insertion order; returns the number of entries */
 int orc_set_loglike_matrix(const orc_config* c, const double* pose, int J, const double* jm, int M, const double* z,
                            int quasi, int cap, int* rows, int* cols, double* vals);

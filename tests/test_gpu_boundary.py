@@ -218,3 +218,41 @@ def test_kinect_depth_visibility(capi, orc, synth):
     finally:
         orc.set_depth_frame(None)
         h.close()
+
+
+@pytest.mark.parametrize("sum_normalised", [False, True])
+def test_quasi_set_loglikelihood_gradient(ctx, orc, sum_normalised):
+    """QuasiSetLogLikelihood(..., out gradient) (PHD:544-549, 561-713) incl. the in-place TemperedAverage on the
+    shared logcomp buffer, in both normalisations (oracle/README.md D10)."""
+    h, ocfg = ctx["h"], ctx["ocfg"]
+    orc.lib().orc_set_tempered_norm(1 if sum_normalised else 0)
+    try:
+        n = 0
+        for pose, lm, z in scenes(ctx, orc):
+            ev, eg = orc.quasi_set_loglikelihood_gradient(ocfg, pose, lm, z)
+            gv, gg = h.quasi_set_loglikelihood_gradient(pose, lm, z, sum_normalised=sum_normalised)
+            assert abs(gv - ev) <= RTOL * max(1.0, abs(ev)), (n, gv, ev)
+            assert np.allclose(gg, eg, rtol=1e-9, atol=1e-9 * max(1.0, float(np.max(np.abs(eg))))), (n, gg, eg)
+            n += 1
+        assert n >= 8
+    finally:
+        orc.lib().orc_set_tempered_norm(0)
+
+
+def test_quasi_gradient_is_the_derivative_in_the_sum_normalised_variant(ctx, orc):
+    """With sum normalisation the gradient is the derivative of the value along MeasurementJacobianP's
+    parametrisation (translation in the world frame, PRM:200-206): central differences on the translation part."""
+    h, ocfg = ctx["h"], ctx["ocfg"]
+    pose = np.array([0.02, -0.01, 0.03, 1, 0, 0, 0.0])
+    rng = np.random.default_rng(77)
+    zc = np.stack([rng.uniform(-60, 60, 6), rng.uniform(-40, 40, 6), rng.uniform(2.0, 2.8, 6)], axis=1)
+    lms = np.array([orc.measure_to_map(ocfg, pose, zz) for zz in zc])
+    zs = zc + rng.normal(size=(6, 3)) * [1.0, 1.0, 0.02]
+    _, g = h.quasi_set_loglikelihood_gradient(pose, lms, zs, sum_normalised=True)
+    eps = 1e-6
+    for a in range(3):
+        pp, pm = pose.copy(), pose.copy()
+        pp[a] += eps
+        pm[a] -= eps
+        num = (h.quasi_set_loglikelihood(pp, lms, zs) - h.quasi_set_loglikelihood(pm, lms, zs)) / (2 * eps)
+        assert abs(num - g[a]) <= 1e-4 * max(1.0, abs(g[a])), (a, num, g[a])
