@@ -407,3 +407,34 @@ def test_jacobian_matches_independent_restatement(orc):
         d[j] = 1e-6
         num[:, j] = (orc.measure_perfect(cfg, pose, lm + d) - orc.measure_perfect(cfg, pose, lm - d)) / 2e-6
     assert np.allclose(H, num, rtol=1e-6, atol=1e-5)
+
+
+def test_loglike2d_gradient_reference_test_pins_the_tempered_average():
+    """LoopyPHDNavigatorTest.LogLike2D (LoopyPHDNavigatorTest.cs:352-425) restated: the analytic pose gradient of
+    QuasiSetLogLikelihood against central differences of its value on a grid of poses, tolerance 0.5.  It passes when
+    TemperedAverage (MX:400-440) divides by the SUM of the tempered weights; with the Euclidean norm -- what Accord's
+    Normalize() does elsewhere in the reference -- a fifth of the grid fails (oracle/README.md D10)."""
+    from oracle import orc
+    p = orc.linear2d_params()
+    p.update(R=np.diag([5e-2, 5e-2, 1.0]), pd=0.9, clutter=0.0)      # Setup(): only the measurement covariance is set
+    cfg = orc.make_config(p)
+    lm = np.array([[0, 1.45, 0], [0, 0.65, 0], [1.0, 0, 0]])
+    z = np.array([[0, 1, 0], [0.2, 0.6, 0]])
+    n = 101
+    xs = (np.arange(n) / (n - 1) - 0.5) / 0.5
+    frac = {}
+    try:
+        for mode in (1, 0):
+            orc.lib().orc_set_tempered_norm(mode)
+            L, G = np.zeros((n, n)), np.zeros((n, n, 2))
+            for i, x in enumerate(xs):
+                for k, y in enumerate(xs):
+                    L[i, k], G[i, k] = orc.quasi_set_loglikelihood_gradient(cfg, [x, y], lm, z)
+            num_x = (L[2:, 1:-1] - L[:-2, 1:-1]) / (xs[2:] - xs[:-2])[:, None]
+            num_y = (L[1:-1, 2:] - L[1:-1, :-2]) / (xs[2:] - xs[:-2])[None, :]
+            ok = (np.abs(num_x - G[1:-1, 1:-1, 0]) < 0.5) & (np.abs(num_y - G[1:-1, 1:-1, 1]) < 0.5)
+            frac[mode] = float(ok.mean())
+    finally:
+        orc.lib().orc_set_tempered_norm(0)
+    assert frac[1] == 1.0, frac
+    assert frac[0] < 0.95, frac
