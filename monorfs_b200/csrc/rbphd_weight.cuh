@@ -401,11 +401,40 @@ __device__ inline void jacobian_p(const DevCfg& c, const Pose& p, const double* 
         }
 }
 
+// d ll[t, k] / d pose of every detection edge: (z_k - h(m_t))^T R^-1 Jp(m_t) (PHD:620-623), 6 doubles per edge
+__device__ __noinline__ void edge_gradients(const KParams& p, Smem& sm, const Slab& s, int nll)
+{
+    const DevCfg& c = p.cfg;
+    const int capj = p.lay.cap_j;
+    const Pose pose = pose_load(sm.ctx.pose);
+    for (int e = threadIdx.x; e < nll; e += kBlock) {
+        const int t = (int)(s.llkey[e] >> 32), k = (int)(s.llkey[e] & 0xffffffffu);
+        const double m[3] = {s.jm[t], s.jm[capj + t], s.jm[2 * capj + t]};
+        double diff[3], mp[3], Jp[18], row[3];
+        Quat local;
+        to_local(pose, m, diff, local);
+        measure_from_local(c, diff, local, mp);
+        jacobian_p(c, pose, diff, local, Jp);
+        const double dz[3] = {sm.zs()[3 * k] - mp[0], sm.zs()[3 * k + 1] - mp[1], sm.zs()[3 * k + 2] - mp[2]};
+        for (int bb = 0; bb < 3; bb++) {
+            double sum = 0;
+            for (int aa = 0; aa < 3; aa++) sum += dz[aa] * c.Rinv[aa * 3 + bb];
+            row[bb] = sum;
+        }
+        for (int l = 0; l < 6; l++) {
+            double sum = 0;
+            for (int bb = 0; bb < 3; bb++) sum += row[bb] * Jp[bb * 6 + l];
+            s.llgrad[6 * (size_t)e + l] = sum;
+        }
+    }
+    __syncthreads();
+}
+
 // QuasiSetLogLikelihood with the gradient (PHD:544-549, 561-713), one thread, blocks in the reference's order with
 // its REAL shared 200-entry logcomp buffer: TemperedAverage (MX:400-440) overwrites logcomp[0, m) with exp(w - max)
 // and normalises over the whole buffer (stale entries included), and the Murty lane's early exit reads that buffer.
 // skey / sval: the detection edges sorted by (block label, landmark, measurement); grads: 6 doubles per edge.
-__device__ double quasi_gradient_serial(const KParams& p, Smem& sm, const Slab& s, MurtyWork& mw,
+__device__ __noinline__ double quasi_gradient_serial(const KParams& p, Smem& sm, const Slab& s, MurtyWork& mw,
                                         const unsigned long long* skey, const unsigned int* sval, int nll, int J,
                                         const int* deg, double* gradient)
 {
@@ -549,21 +578,6 @@ __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab
                         if (idx < capll) {
                             s.llkey[idx] = ((unsigned long long)t << 32) | (unsigned)k;
                             s.llval[idx] = lw + c.logmultR - 0.5 * d * d;
-                            if (want_grad) {   // (z - h)^T R^-1 Jp (PHD:620-623)
-                                double Jp[18], row[3];
-                                jacobian_p(c, pose, diff, local, Jp);
-                                const double dz[3] = {-d3[0], -d3[1], -d3[2]};
-                                for (int bb = 0; bb < 3; bb++) {
-                                    double sum = 0;
-                                    for (int aa = 0; aa < 3; aa++) sum += dz[aa] * c.Rinv[aa * 3 + bb];
-                                    row[bb] = sum;
-                                }
-                                for (int l = 0; l < 6; l++) {
-                                    double sum = 0;
-                                    for (int bb = 0; bb < 3; bb++) sum += row[bb] * Jp[bb * 6 + l];
-                                    s.llgrad[6 * (size_t)idx + l] = sum;
-                                }
-                            }
                         }
                         atomicAdd(&deg[t], 1);
                         atomicAdd(&deg[J + k], 1);
@@ -576,6 +590,7 @@ __device__ double phase_set_loglikelihood(const KParams& p, Smem& sm, const Slab
     __syncthreads();
     const int nll = s_nll;
     if (tid == 0) { sm.ctx.dbg[9] += nll; sm.ctx.dbg[10] += J; }
+    if (want_grad) edge_gradients(p, sm, s, nll);   // (kept out of the gate loop above: the frame path never needs it)
     if (p.ll_flags & LL_DUMP_MATRIX) {
         // SetLogLikeMatrix (PHD:415-460) as (row, column, value) triplets: detections, misses, clutter
         const int total = nll + J + M;
