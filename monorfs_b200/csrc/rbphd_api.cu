@@ -1442,7 +1442,9 @@ int rbphd_comm_init_rank(rbphd_navigator* nav, const unsigned char id128[128], i
     // carries data (measured: every other exchange of the first dozen).  Pay that here, not in a resampling
     // frame: a few all-to-all rounds over the (still empty) exchange buffers, sized to use every channel.
     if (world > 1) {
-        size_t warm = std::min(nav->sendcap, nav->recvcap) / (size_t)world;
+        // (the same size on every rank, also when the block partition is uneven: counts of a send and its receive
+        // must agree)
+        size_t warm = rec * (size_t)(total_particles / world) / (size_t)world;
         warm = std::min(warm, (size_t)8 << 20);   // 64 MB per peer
         if (warm > 0) {
             CK(cudaMemsetAsync(nav->sendbuf, 0, sizeof(double) * warm * (size_t)world, nav->stream));

@@ -18,6 +18,9 @@ from monorfs_b200 import capi, sharded, synth  # noqa: E402
 
 
 def main():
+    import faulthandler
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(240, exit=True)   # a hang dumps every thread's stack instead of eating the GPU lease
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
