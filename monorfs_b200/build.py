@@ -28,11 +28,16 @@ NVCC_FLAGS = [
 ]
 
 
+DEVICE_SOURCES = ["rbphd_kernels.cu", "rbphd_math.cuh", "rbphd_block.cuh", "rbphd_kernels.cuh", "rbphd_weight.cuh",
+                  "rbphd_murty.cuh"]
+
+
 def source_hash():
-    """Hash of the device sources + the C ABI header: ties ncu-derived counters under profiles/ to a tree."""
+    """Hash of the files k_particle_update is compiled from (not the host-side ABI): ties ncu-derived counters
+    under profiles/ to the kernel they were captured on."""
     import hashlib
     h = hashlib.sha256()
-    for f in sorted(SOURCES + HEADERS):
+    for f in sorted(DEVICE_SOURCES):
         path = os.path.join(CSRC, f)
         if os.path.exists(path):
             with open(path, "rb") as fh:
