@@ -327,6 +327,9 @@ int check_async(rbphd_navigator* nav, const char* what)
 int enqueue_map_update(rbphd_navigator* nav, int M, int only_mapping, int mode, int slot = 0,
                        cudaEvent_t* ev = nullptr)
 {
+    if (mode == MODE_FRAME && nav->pending_wheel)
+        return fail(nav, RBPHD_ERR_ARGUMENT,
+                    "rbphd_slam_update_begin reported depleted particles: call rbphd_slam_update_finish first");
     KParams k = base_params(nav, mode, M, only_mapping, slot);
     launch_frame_prep(nav->stream, nav->dcfg, k.z, M, nav->vgrid, nav->vitems, nav->zgrid, nav->zitems, nav->pts);
     if (ev) cudaEventRecord(ev[0], nav->stream);

@@ -256,3 +256,23 @@ def test_quasi_gradient_is_the_derivative_in_the_sum_normalised_variant(ctx, orc
         pm[a] -= eps
         num = (h.quasi_set_loglikelihood(pp, lms, zs) - h.quasi_set_loglikelihood(pm, lms, zs)) / (2 * eps)
         assert abs(num - g[a]) <= 1e-4 * max(1.0, abs(g[a])), (a, num, g[a])
+
+
+def test_two_step_update_must_be_finished(capi, synth):
+    """A frame that found the particles depleted has to be finished before the next one starts."""
+    P, N, M = 8, 30, 12
+    sc = synth.make_scene(P, N, M, seed=12, min_effective_particle=0.99)
+    h = capi.Handle(sc.params, max_particles=P, max_components=128, max_measurements=M)
+    h.reset(P, sc.poses[0], sc.map_w, sc.map_m, sc.map_P)
+    h.set_poses(sc.poses)
+    fr = sc.next_frame()
+    h.update(fr.reading, synth.DT, fr.gauss)
+    _, dep = h.slam_update_begin(fr.z)
+    assert dep
+    with pytest.raises(capi.RbphdError):
+        h.slam_update(fr.z, fr.u)
+    h.slam_update_finish(fr.u)
+    fr = sc.next_frame()
+    h.update(fr.reading, synth.DT, fr.gauss)
+    h.slam_update(fr.z, fr.u)
+    h.close()
