@@ -218,6 +218,26 @@ int rbphd_comm_stats(const rbphd_navigator* nav, int64_t out4[4]);
 int rbphd_debug_migration_plan(int device, const int* ancestors, const int* counts, int total, int world, int rank,
                                int* local_src, int64_t* rec_off, int* send_idx, int64_t* send_off, int64_t* hdr);
 
+/* ---- around the hot path --------------------------------------------------------------
+ * SimulatedVehicle.Measure (mono-rfs-lib/SLAM/Vehicles/SimulatedVehicle.cs:243-295) with the host's random numbers
+ * (the reference draws them from Util.Uniform / Accord's Gaussian, SIMV:215,257; a host passes the same draws):
+ * landmark i is measured when pd_i > 0 and uniforms[i] < pd_i, as h(pose, landmark) + C gauss[3 i ..] with C C^T = R
+ * (chol9 row-major lower root; NULL: computed from the configured R as Util.RandomGaussianVector does,
+ * Util/Util.cs:173-202); then nc clutter points from clutter_u[3 k ..] (PRM3DMeasurer.RandomMeasure,
+ * BaseStructures/Measurers/PRM3DMeasurer.cs:249-256; the Poisson count, capped at 10 lambda, is the host's).
+ * z: room for (n + nc) x 3, assoc (may be NULL): n + nc entries, landmark index or INT_MIN for clutter
+ * (SimulatedVehicle.DataAssociation).  With a depth frame attached the visibility is the occlusion-aware one. */
+int rbphd_generate_measurements(rbphd_navigator* nav, const double* pose7, const double* landmarks, int n,
+                                const double* uniforms, const double* gauss, const double* chol9,
+                                const double* clutter_u, int nc, double* z, int* assoc, int* count);
+
+/* Plot.OSPA (postanalysis/Plot.cs:531-581): OSPA distance of order p and cutoff c between two landmark sets
+ * (positions, na x 3 and nb x 3; swapped when na > nb), the optimal assignment
+ * (GraphCombinatorics.LinearAssignment, mono-rfs-lib/Math/GraphCombinatorics.cs:52-175) found on the device.
+ * cardinality_error may be NULL.  At most 8192 landmarks per set. */
+int rbphd_ospa(rbphd_navigator* nav, const double* a, int na, const double* b, int nb, double c, double p,
+               double* ospa, double* cardinality_error);
+
 /* ---- instrumentation ---- */
 /* number of kernel launches issued on this handle since creation */
 int64_t rbphd_kernel_launches(const rbphd_navigator* nav);

@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "librbphd.so")
-SOURCES = ["rbphd_kernels.cu", "rbphd_api.cu", "rbphd_microbench.cu"]
-HEADERS = ["rbphd_math.cuh", "rbphd_block.cuh", "rbphd_kernels.cuh", "rbphd_weight.cuh", "rbphd_murty.cuh",
+SOURCES = ["rbphd_kernels.cu", "rbphd_api.cu", "rbphd_microbench.cu", "rbphd_analysis.cu"]
+HEADERS = ["rbphd_analysis.cuh", "rbphd_math.cuh", "rbphd_block.cuh", "rbphd_kernels.cuh", "rbphd_weight.cuh", "rbphd_murty.cuh",
            os.path.join("..", "..", "include", "rbphd.h")]
 
 NVCC_FLAGS = [

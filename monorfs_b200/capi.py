@@ -50,7 +50,7 @@ EXPORTS = [
     "rbphd_profile_read", "rbphd_get_counters", "rbphd_get_phase_cycles", "rbphd_stream",
     "rbphd_launch_shape", "rbphd_bench_fp64", "rbphd_slam_update_begin", "rbphd_slam_update_finish",
     "rbphd_set_likelihood", "rbphd_quasi_set_loglikelihood", "rbphd_set_loglike_matrix", "rbphd_set_holdout", "rbphd_set_depth_frame",
-    "rbphd_quasi_set_loglikelihood_gradient",
+    "rbphd_quasi_set_loglikelihood_gradient", "rbphd_generate_measurements", "rbphd_ospa",
 ]
 
 _lib = None
@@ -400,6 +400,28 @@ class Handle:
         self._ck(self.lib.rbphd_quasi_set_loglikelihood_gradient(self._h, _p(_d(pose)), len(jm), _p(jm), _p(z), len(z),
                                                                  int(sum_normalised), C.byref(out), _p(g)))
         return out.value, g
+
+    def generate_measurements(self, pose, landmarks, uniforms, gauss, clutter_u, chol=None):
+        """SimulatedVehicle.Measure (SIMV:243-295) with the host's random numbers -> (z, assoc)."""
+        lm, ga, cu = _d(landmarks).reshape(-1, 3), _d(gauss).reshape(-1, 3), _d(clutter_u).reshape(-1, 3)
+        un = _d(uniforms).reshape(-1)
+        if len(un) != len(lm) or len(ga) != len(lm):
+            raise ValueError("one uniform and three gaussian draws per landmark")
+        z = np.zeros((len(lm) + len(cu), 3))
+        assoc = np.zeros(len(lm) + len(cu), dtype=np.int32)
+        n = C.c_int()
+        ch = _p(_d(chol).reshape(9)) if chol is not None else None
+        self._ck(self.lib.rbphd_generate_measurements(self._h, _p(_d(pose)), _p(lm), len(lm), _p(un), _p(ga), ch, _p(cu),
+                                                      len(cu), _p(z), assoc.ctypes.data_as(c_int_p), C.byref(n)))
+        return z[:n.value].copy(), assoc[:n.value].copy()
+
+    def ospa(self, a, b, c=1.0, p=2.0):
+        """(OSPA, cardinality error) between two landmark position sets (postanalysis/Plot.cs:531-581)."""
+        a, b = _d(a).reshape(-1, 3), _d(b).reshape(-1, 3)
+        out, card = C.c_double(), C.c_double()
+        self._ck(self.lib.rbphd_ospa(self._h, _p(a), len(a), _p(b), len(b), C.c_double(c), C.c_double(p), C.byref(out),
+                                     C.byref(card)))
+        return out.value, card.value
 
     def set_loglike_matrix(self, pose, jm, z):
         """SetLogLikeMatrix (PHD:415-460) as sorted (row, col, value) triplets."""

@@ -3,6 +3,7 @@
 // that computes fails with RBPHD_ERR_NO_DEVICE / RBPHD_ERR_CUDA when the device path is unavailable.
 #include "../../include/rbphd.h"
 #include "rbphd_kernels.cuh"
+#include "rbphd_analysis.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -101,6 +102,8 @@ struct rbphd_navigator {
     int holdout = -1;             // rbphd_set_holdout
     float* depth = nullptr;       // rbphd_set_depth_frame: device copy of the Kinect depth frame
     size_t depth_cap = 0;
+    double* ana = nullptr;        // scratch of rbphd_generate_measurements / rbphd_ospa
+    size_t ana_cap = 0;
     int64_t launches = 0;
     std::string error;
     rbphd_navigator* stage = nullptr;   // lazily created 2-slot navigator for the stage entry points
@@ -272,7 +275,7 @@ void free_device(rbphd_navigator* nav)
     cudaFree(nav->alpha_parts); cudaFree(nav->z); cudaFree(nav->gauss); cudaFree(nav->pts);
     cudaFree(nav->ancestors); cudaFree(nav->cumw); cudaFree(nav->st); cudaFree(nav->vgrid); cudaFree(nav->zgrid);
     cudaFree(nav->vitems); cudaFree(nav->zitems); cudaFree(nav->scratch); cudaFree(nav->dump);
-    cudaFree(nav->dump_count); cudaFree(nav->depth);
+    cudaFree(nav->dump_count); cudaFree(nav->depth); cudaFree(nav->ana);
     for (auto& e : nav->pev) cudaEventDestroy(e);
     for (auto& e : nav->slot_ev) if (e) cudaEventDestroy(e);
     if (nav->stream) cudaStreamDestroy(nav->stream);
@@ -1209,6 +1212,103 @@ int rbphd_set_loglike_matrix(rbphd_navigator* nav, const double* pose7, int j, c
     if (cols) *cols = nav->o_cols.data();
     if (vals) *vals = nav->o_w.data();
     if (nnz) *nnz = cnt;
+    return RBPHD_OK;
+}
+
+// ------------------------------------------------------------------ around the hot path
+static int analysis_scratch(rbphd_navigator* nav, size_t doubles)
+{
+    if (doubles <= nav->ana_cap) return RBPHD_OK;
+    CK(cudaStreamSynchronize(nav->stream));
+    cudaFree(nav->ana);
+    nav->ana = nullptr; nav->ana_cap = 0;
+    CK(cudaMalloc(&nav->ana, sizeof(double) * doubles));
+    nav->ana_cap = doubles;
+    return RBPHD_OK;
+}
+
+int rbphd_generate_measurements(rbphd_navigator* nav, const double* pose7, const double* landmarks, int n,
+                                const double* uniforms, const double* gauss, const double* chol9,
+                                const double* clutter_u, int nc, double* z, int* assoc, int* count)
+{
+    if (!nav || !pose7 || n < 0 || nc < 0 || !z || !count) return RBPHD_ERR_ARGUMENT;
+    if (n > 0 && (!landmarks || !uniforms || !gauss)) return RBPHD_ERR_ARGUMENT;
+    if (nc > 0 && !clutter_u) return RBPHD_ERR_ARGUMENT;
+    if (int r = set_device(nav)) return r;
+    double chol[9] = {0};
+    if (chol9) std::memcpy(chol, chol9, sizeof chol);
+    else {   // UTIL:173-202 on the 3 x 3 measurement covariance
+        double R[9];
+        std::memcpy(R, nav->cfg.R, sizeof R);
+        for (int i = 0; i < 3; i++) if (R[i * 3 + i] < 1e-40) R[i * 3 + i] = 1e-40;
+        for (int j = 0; j < 3; j++) {
+            double d = R[j * 3 + j];
+            for (int k = 0; k < j; k++) d -= chol[j * 3 + k] * chol[j * 3 + k];
+            chol[j * 3 + j] = std::sqrt(d);
+            for (int i = j + 1; i < 3; i++) {
+                double t = R[i * 3 + j];
+                for (int k = 0; k < j; k++) t -= chol[i * 3 + k] * chol[j * 3 + k];
+                chol[i * 3 + j] = t / chol[j * 3 + j];
+            }
+        }
+    }
+    // device layout: pose 7 | chol 9 | landmarks 3n | uniforms n | gauss 3n | clutter 3nc | z 3(n+nc) | assoc, count
+    const size_t N = (size_t)n, NC = (size_t)nc, T = N + NC;
+    const size_t o_pose = 0, o_chol = 8, o_lm = 24, o_un = o_lm + 3 * N, o_ga = o_un + N, o_cl = o_ga + 3 * N,
+                 o_z = o_cl + 3 * NC, o_as = o_z + 3 * T, total = o_as + (T + 2) / 2 + 2;
+    if (int r = analysis_scratch(nav, total)) return r;
+    CK(cudaStreamSynchronize(nav->stream));
+    std::vector<double> in(o_z, 0.0);
+    std::memcpy(&in[o_pose], pose7, 7 * sizeof(double));
+    std::memcpy(&in[o_chol], chol, sizeof chol);
+    if (n) {
+        std::memcpy(&in[o_lm], landmarks, 3 * N * sizeof(double));
+        std::memcpy(&in[o_un], uniforms, N * sizeof(double));
+        std::memcpy(&in[o_ga], gauss, 3 * N * sizeof(double));
+    }
+    if (nc) std::memcpy(&in[o_cl], clutter_u, 3 * NC * sizeof(double));
+    if (int r = upload(nav, nav->ana, in.data(), o_z * sizeof(double))) return r;
+    double* d = nav->ana;
+    int* d_assoc = reinterpret_cast<int*>(d + o_as);
+    int* d_count = d_assoc + T;
+    launch_generate_measurements(nav->stream, nav->dcfg, d + o_pose, d + o_lm, n, d + o_un, d + o_ga, d + o_chol, d + o_cl,
+                                 nc, d + o_z, d_assoc, d_count);
+    CK(cudaGetLastError());
+    nav->launches++;
+    void* h;
+    if (int r = download(nav, d + o_z, sizeof(double) * (total - o_z), &h)) return r;
+    const double* hz = (const double*)h;
+    const int* ha = reinterpret_cast<const int*>(hz + 3 * T);
+    const int cnt = ha[T];
+    std::memcpy(z, hz, sizeof(double) * 3 * (size_t)cnt);
+    if (assoc) std::memcpy(assoc, ha, sizeof(int) * (size_t)cnt);
+    *count = cnt;
+    return RBPHD_OK;
+}
+
+int rbphd_ospa(rbphd_navigator* nav, const double* a, int na, const double* b, int nb, double c, double p,
+               double* ospa, double* cardinality_error)
+{
+    if (!nav || na < 0 || nb < 0 || !ospa) return RBPHD_ERR_ARGUMENT;
+    if ((na > 0 && !a) || (nb > 0 && !b)) return RBPHD_ERR_ARGUMENT;
+    if (na > nb) { std::swap(na, nb); std::swap(a, b); }   // Plot.cs:533-537
+    if (nb > 8192) return fail(nav, RBPHD_ERR_CAPACITY, "rbphd_ospa: more than 8192 landmarks");
+    if (int r = set_device(nav)) return r;
+    const size_t A = 3 * (size_t)na, B = 3 * (size_t)nb;
+    const size_t o_b = A + (A & 1), o_work = o_b + B + (B & 1), o_out = o_work + ospa_workspace_doubles(nb);
+    if (int r = analysis_scratch(nav, o_out + 2)) return r;
+    CK(cudaStreamSynchronize(nav->stream));
+    std::vector<double> in(std::max<size_t>(o_work, 2), 0.0);
+    if (na) std::memcpy(&in[0], a, A * sizeof(double));
+    if (nb) std::memcpy(&in[o_b], b, B * sizeof(double));
+    if (int r = upload(nav, nav->ana, in.data(), in.size() * sizeof(double))) return r;
+    launch_ospa(nav->stream, nav->ana, na, nav->ana + o_b, nb, c, p, nav->ana + o_work, nav->ana + o_out);
+    CK(cudaGetLastError());
+    nav->launches++;
+    void* h;
+    if (int r = download(nav, nav->ana + o_out, 2 * sizeof(double), &h)) return r;
+    *ospa = ((const double*)h)[0];
+    if (cardinality_error) *cardinality_error = ((const double*)h)[1];
     return RBPHD_OK;
 }
 

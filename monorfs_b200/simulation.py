@@ -34,7 +34,8 @@ class TrueVehicle:
             qq[i, i] = max(qq[i, i], 1e-40)
         self.chol = np.linalg.cholesky(qq)
         meas = params["measurer"]
-        self.volume = meas[5] * meas[6] * (float(np.float32(meas[2])) - float(np.float32(meas[1])))   # PRM:119-122
+        self.range_length = float(np.float32(meas[2]) - np.float32(meas[1]))   # AForge.Range.Length: float arithmetic
+        self.volume = meas[5] * meas[6] * self.range_length   # PRM:119-122
         self.clutter_count = params["clutter"] * self.volume
 
     def update(self, reading, dt):
@@ -51,6 +52,20 @@ class TrueVehicle:
         self.ref_odometry = self.pose.copy()
         return reading
 
+    def measure_on_device(self, handle):
+        """SimulatedVehicle.Measure with the measurement model evaluated by librbphd.so (rbphd_generate_measurements);
+        the random numbers are drawn here, in the reference's order of kinds (detection, noise, count, clutter)."""
+        p, rng = self.p, self.rng
+        n = len(self.landmarks)
+        un, ga = rng.random(n), rng.normal(size=(n, 3))
+        ncl = min(int(rng.poisson(self.clutter_count)), int(self.clutter_count * 10)) if self.clutter_count > 0 else 0
+        z, assoc = handle.generate_measurements(self.pose, self.landmarks, un, ga, rng.random((ncl, 3)))
+        zp = synth.measure_perfect(self.pose, self.landmarks, p["measurer"][0]) if n else np.zeros((0, 3))
+        pdet = p["pd"] * synth.fuzzy_visible(zp, p["measurer"], p["visibility_ramp"]) if n else np.zeros(0)
+        hit = np.zeros(n, bool)
+        hit[assoc[assoc >= 0]] = True
+        return z, self.landmarks[pdet > 0], hit[pdet > 0]
+
     def measure(self):
         """SimulatedVehicle.Measure (SimulatedVehicle.cs:243-295)."""
         p, rng = self.p, self.rng
@@ -63,7 +78,7 @@ class TrueVehicle:
         ncl = min(int(rng.poisson(self.clutter_count)), int(self.clutter_count * 10)) if self.clutter_count > 0 else 0
         rmin, rmax = float(np.float32(meas[1])), float(np.float32(meas[2]))
         clutter = np.stack([rng.random(ncl) * meas[5] + meas[3], rng.random(ncl) * meas[6] + meas[4],
-                            rng.random(ncl) * (rmax - rmin) + rmin], axis=1) if ncl else np.zeros((0, 3))
+                            rng.random(ncl) * self.range_length + rmin], axis=1) if ncl else np.zeros((0, 3))
         visible = self.landmarks[pdet > 0]
         return np.ascontiguousarray(np.concatenate([det, clutter], axis=0)), visible, hit[pdet > 0]
 
@@ -93,7 +108,8 @@ class HeadlessRun:
     """One `monorfs -i=simulation ... -x` run with the navigator on the GPU."""
 
     def __init__(self, pose0, measurer, landmarks, commands, particles, params=None, seed=synth.SEED, device=0,
-                 max_components=0, max_measurements=0):
+                 max_components=0, max_measurements=0, device_measure=False):
+        self.device_measure = bool(device_measure)
         self.commands = [np.asarray(c, float) for c in commands]
         self.P = int(particles)
         n_lm = max(1, len(landmarks))
@@ -127,7 +143,8 @@ class HeadlessRun:
             self.only_mapping = True
         self.vehicle.update(command[:6], dt)
         reading = self.vehicle.read_odometry()
-        z, visible, detected = self.vehicle.measure()
+        z, visible, detected = (self.vehicle.measure_on_device(self.h) if self.device_measure
+                                else self.vehicle.measure())
         rec.trajectory.append((t, self.vehicle.pose.copy()))
         rec.odometry.append((t, reading))
         rec.measurements.append((t, z))
@@ -216,3 +233,42 @@ def synthetic_commands(n_frames):
         c = list(synth.ODOMETRY) + [1.0 if f == 0 else 0.0]
         cmds.append(np.array(c))
     return cmds
+
+
+def best_map_estimate(w, m):
+    """Map.BestMapEstimate (Map.cs:119-140): floor(expected size) picks of the heaviest component, each pick
+    re-entering the list with its weight reduced by one.  Returns the picked means (k x 3)."""
+    import heapq
+    w, m = np.asarray(w, float), np.asarray(m, float).reshape(-1, 3)
+    size = int(w.sum()) if len(w) else 0
+    heap = [(-wi, i) for i, wi in enumerate(w)]
+    heapq.heapify(heap)
+    picks = []
+    for _ in range(size):
+        nw, i = heapq.heappop(heap)
+        picks.append(i)
+        heapq.heappush(heap, (nw + 1.0, i))
+    return m[picks] if picks else np.zeros((0, 3))
+
+
+def visited_map(rec):
+    """Plot.VisitedMap (postanalysis/Plot.cs:230-248): every landmark that was visible AND detected in some frame."""
+    seen = []
+    for _, (wts, means, _) in rec.vismaps:
+        for wt, mean in zip(wts, means):
+            if wt > 0 and not any(np.linalg.norm(mean - s) <= 1e-5 for s in seen):
+                seen.append(np.asarray(mean, float))
+    return np.array(seen).reshape(-1, 3)
+
+
+def map_error(rec, handle, c=1.0, p=2.0):
+    """Plot.MapError / SpatialMapError (postanalysis/Plot.cs:477-527) with RefTime = 0 (estimate and groundtruth share
+    the first pose, so the alignment transform is the identity): per recorded frame the OSPA distance between the
+    visited groundtruth landmarks and the best map estimate, evaluated by librbphd.so (rbphd_ospa).
+    Returns [(time, ospa, spatial)]."""
+    visited = visited_map(rec)
+    out = []
+    for t, (w, m, _) in rec.maps:
+        o, card = handle.ospa(visited, best_map_estimate(w, m), c, p)
+        out.append((t, o, max(o ** p - card ** p, 0.0) ** (1.0 / p)))
+    return out

@@ -63,6 +63,7 @@ def lib():
         _lib.orc_set_loglikelihood.restype = C.c_double
         _lib.orc_quasi_set_loglikelihood.restype = C.c_double
         _lib.orc_quasi_set_loglikelihood_gradient.restype = C.c_double
+        _lib.orc_ospa.restype = C.c_double
         _lib.orc_nav_new.restype = C.c_void_p
     return _lib
 
@@ -375,6 +376,29 @@ def hungarian(val, defined=None, defval=0.0):
     ok = lib().orc_hungarian(n, _p(val), defined.ctypes.data_as(c_u8_p), C.c_double(defval),
                              match.ctypes.data_as(c_int_p))
     return match if ok else None
+
+
+def ospa(a, b, c=1.0, p=2.0):
+    """(OSPA, cardinality error) between two landmark position sets (postanalysis/Plot.cs:531-581)."""
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1, 3))
+    b = np.ascontiguousarray(np.asarray(b, dtype=np.float64).reshape(-1, 3))
+    card = C.c_double(0)
+    v = lib().orc_ospa(len(a), _p(a), len(b), _p(b), C.c_double(c), C.c_double(p), C.byref(card))
+    return float(v), float(card.value)
+
+
+def generate_measurements(cfg, pose, landmarks, uniforms, gauss, chol, clutter_u):
+    """SimulatedVehicle.Measure (SIMV:243-295) with the caller's random numbers -> (z, assoc)."""
+    lm = np.ascontiguousarray(np.asarray(landmarks, dtype=np.float64).reshape(-1, 3))
+    un = np.ascontiguousarray(uniforms, dtype=np.float64)
+    ga = np.ascontiguousarray(np.asarray(gauss, dtype=np.float64).reshape(-1, 3))
+    ch = np.ascontiguousarray(chol, dtype=np.float64).reshape(3, 3)
+    cu = np.ascontiguousarray(np.asarray(clutter_u, dtype=np.float64).reshape(-1, 3))
+    z = np.zeros((len(lm) + len(cu), 3))
+    assoc = np.zeros(len(lm) + len(cu), dtype=np.int32)
+    n = lib().orc_generate_measurements(C.byref(cfg), _pose(pose)[1], len(lm), _p(lm), _p(un), _p(ga), _p(ch), len(cu),
+                                        _p(cu), _p(z), assoc.ctypes.data_as(c_int_p))
+    return z[:n].copy(), assoc[:n].copy()
 
 
 def connected_components(defined):

@@ -1526,6 +1526,64 @@ int orc_hungarian(int n, const double* val, const uint8_t* defined, double defva
     for (int i = 0; i < n; i++) match[i] = mx[i];
     return 1;
 }
+/* postanalysis/Plot.cs:531-581 (OSPA) over GC:52-55, 64-175 (one global Hungarian) and SPM:526-542 (Apply also maps
+ * the default value, so undefined entries cost C^P).  a, b: na x 3 and nb x 3 landmark positions. */
+double orc_ospa(int na, const double* a, int nb, const double* b, double C, double P, double* cardinality)
+{
+    if (na > nb) { std::swap(na, nb); std::swap(a, b); }
+    if (na == 0) { *cardinality = (nb == 0) ? 0.0 : C; return *cardinality; }
+    Sparse transport(nb, nb, 0.0);
+    const double CP = std::pow(C, P);
+    for (int i = 0; i < na; i++)
+        for (int k = 0; k < nb; k++) {
+            double d[3] = {a[3 * i] - b[3 * k], a[3 * i + 1] - b[3 * k + 1], a[3 * i + 2] - b[3 * k + 2]};
+            double distance = std::pow(std::fmin(C, euclid(d, 3)), P);   /* Plot.cs:583-586 */
+            if (CP - distance > 1e-5) transport.set(i, k, CP - distance);
+        }
+    transport.height = nb; transport.width = nb;
+    std::vector<int> best;
+    if (!hungarian(transport, best)) { *cardinality = kInf; return kInf; }
+    double total = 0;
+    for (int i = 0; i < nb; i++) {
+        total += CP - transport.get(i, best[i]);
+    }
+    *cardinality = C * std::pow((double)(nb - na) / nb, 1.0 / P);
+    return std::pow(total / nb, 1.0 / P);
+}
+
+/* SIMV:243-295 with the caller's random numbers: uniforms[i] per landmark, gauss[3 i ..] per landmark (used only when
+ * detected), chol = lower root of R (UTIL:173-202), clutter_u[3 k ..] for the nc clutter points (PRM:249-256).
+ * Returns the number of measurements; assoc = landmark index or INT_MIN. */
+int orc_generate_measurements(const orc_config* c, const double* pose, int n, const double* landmarks,
+                              const double* uniforms, const double* gauss, const double* chol, int nc,
+                              const double* clutter_u, double* z, int* assoc)
+{
+    int count = 0;
+    for (int i = 0; i < n; i++) {
+        double mp[3];
+        measure_perfect(c, pose, landmarks + 3 * i, mp);
+        double pd = detection_probability_m(c, mp);
+        if (pd > 0 && uniforms[i] < pd) {
+            for (int r = 0; r < 3; r++) {
+                double sum = 0;
+                for (int k = 0; k < 3; k++) sum += chol[r * 3 + k] * gauss[3 * i + k];
+                z[3 * count + r] = mp[r] + (0.0 + sum);
+            }
+            assoc[count++] = i;
+        }
+    }
+    const int left = (int)c->measurer[3], top = (int)c->measurer[4], width = (int)c->measurer[5],
+              height = (int)c->measurer[6];
+    const float rminf = (float)c->measurer[1], length = (float)c->measurer[2] - rminf;   /* AForge.Range: floats */
+    for (int k = 0; k < nc; k++) {
+        z[3 * count]     = clutter_u[3 * k] * width + left;
+        z[3 * count + 1] = clutter_u[3 * k + 1] * height + top;
+        z[3 * count + 2] = clutter_u[3 * k + 2] * (double)length + (double)rminf;
+        assoc[count++] = std::numeric_limits<int>::min();
+    }
+    return count;
+}
+
 int orc_connected_components(int h, int w, const uint8_t* defined)
 {
     Sparse s = sparse_from_dense(h, w, nullptr, defined, 0.0);

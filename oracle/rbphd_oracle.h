@@ -113,6 +113,12 @@ int orc_normalize_resample(const orc_config* c, int P, double* weights, double u
                            int* ancestors, int force_resample);
 
 /* ---- graph combinatorics (GC, SPM) on dense n x n matrices with a 'defined' mask ---- */
+/* postanalysis/Plot.cs:531-581: OSPA distance between two landmark sets (positions, n x 3) */
+double orc_ospa(int na, const double* a, int nb, const double* b, double C, double P, double* cardinality);
+/* SIMV:243-295 with caller-supplied random numbers; returns the measurement count */
+int orc_generate_measurements(const orc_config* c, const double* pose, int n, const double* landmarks,
+                              const double* uniforms, const double* gauss, const double* chol, int nc,
+                              const double* clutter_u, double* z, int* assoc);
 int orc_hungarian(int n, const double* val, const uint8_t* defined, double defval, int* match);
 int orc_connected_components(int h, int w, const uint8_t* defined);
 int orc_lexicographical(int n, const double* val, const uint8_t* defined, double defval, int modelsize,

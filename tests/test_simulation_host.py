@@ -47,3 +47,26 @@ def test_synthetic_run_files_round_trip():
     c2 = recordio.parse_commands(recordio.commands_to_text(cmds))
     assert len(c2) == 12 and c2[0][6] == 1 and all(c[6] == 0 for c in c2[1:])
     assert np.allclose(c2[3][:6], synth.ODOMETRY)
+
+
+def test_best_map_estimate_matches_the_oracle():
+    """Map.BestMapEstimate (Map.cs:119-140): the host-side post-analysis helper picks the oracle's components."""
+    from oracle import orc
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 7, 60):
+        w = rng.choice([0.05, 0.4, 0.97, 1.6, 2.3], size=n) + rng.random(n) * 1e-3
+        m = rng.normal(size=(n, 3))
+        picks = orc.best_map_estimate(w)
+        got = simulation.best_map_estimate(w, m)
+        assert len(got) == len(picks) == int(w.sum())
+        assert np.array_equal(got, m[picks].reshape(-1, 3))
+
+
+def test_visited_map_keeps_detected_landmarks_once():
+    rec = recordio.Recording(np.zeros(7), np.zeros(7), np.zeros((0, 3)))
+    a, b, c = np.array([1.0, 0, 0]), np.array([0, 2.0, 0]), np.array([0, 0, 3.0])
+    cov = np.tile(np.eye(3) * 1e-3, (2, 1, 1))
+    rec.vismaps.append((0.1, (np.array([1.0, 0.0]), np.array([a, b]), cov)))      # b visible, not detected
+    rec.vismaps.append((0.2, (np.array([1.0, 1.0]), np.array([a + 1e-7, c]), cov)))
+    v = simulation.visited_map(rec)
+    assert len(v) == 2 and np.array_equal(v[0], a) and np.array_equal(v[1], c)
