@@ -15,7 +15,7 @@ namespace rbphd {
 #define RBPHD_CTAS_PER_SM 1
 #endif
 #ifndef RBPHD_GRID_CELLS
-#define RBPHD_GRID_CELLS 8192
+#define RBPHD_GRID_CELLS 4864   // with RBPHD_SORT_CAP 6656: 163 KB of shared memory at 500 measurements (see rbphd_kernels.cu)
 #endif
 #ifndef RBPHD_SORT_BUCKETS
 #define RBPHD_SORT_BUCKETS 4096
@@ -589,7 +589,8 @@ __device__ __forceinline__ int grid_cell(const CellGrid& g, double x, double y, 
 }
 
 // Build.  mincell = smallest useful cell edge (a typical query radius).  start must hold
-// kGridMaxCells + 1 ints of shared memory; items n ints.
+// maxcells + 1 ints of shared memory (maxcells <= kCellsBound); items n ints.
+template <int kCellsBound = kGridMaxCells>
 __device__ inline void grid_build(BlockShared& sh, CellGrid& g, int* start, int* items, const double* px,
                                   const double* py, const double* pz, int n, double mincell0,
                                   double mincell1, double mincell2, int maxcells = kGridMaxCells)
@@ -709,7 +710,7 @@ __device__ inline void grid_build(BlockShared& sh, CellGrid& g, int* start, int*
     // ... then shift right by one to restore the begin offsets (read the whole run first, then write)
     {
         int prev = (c0 > 0 && c0 - 1 <= ncell) ? start[c0 - 1] : 0;
-        constexpr int kPerMax = (kGridMaxCells + kBlock) / kBlock;   // >= per for every grid
+        constexpr int kPerMax = (kCellsBound + kBlock) / kBlock;   // >= per for every grid
         int vals[kPerMax];
         for (int a = 0; a < per && a < kPerMax; a++) { const int cc = c0 + a; vals[a] = (cc <= ncell) ? start[cc] : 0; }
         __syncthreads();

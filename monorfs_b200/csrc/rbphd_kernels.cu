@@ -13,6 +13,7 @@
 // -fmad=false so results match the CPU oracle bit for bit apart from libm transcendentals.
 #include "rbphd_kernels.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 
@@ -36,6 +37,21 @@ struct Ctx {
 #define DBG_ADD(sm, idx, v) atomicAdd(&(sm).ctx.dbg[idx], (unsigned int)(v))
 
 // phase timer: thread 0 attributes the cycles since the previous mark to phase `ph`
+// per-warp section timer (experiment builds, -DRBPHD_WARPTIME): lane 0 of every warp adds the cycles since its
+// previous mark to slot `ph`; the slot then holds the sum over the 32 warps
+#ifdef RBPHD_WARPTIME
+#define WARP_T0() long long wt__ = clock64()
+#define WARP_T(sm, ph)                                                                   \
+    do {                                                                                 \
+        long long n__ = clock64();                                                       \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&(sm).ctx.tphase[ph], (unsigned long long)(n__ - wt__)); \
+        wt__ = n__;                                                                      \
+    } while (0)
+#else
+#define WARP_T0() do {} while (0)
+#define WARP_T(sm, ph) do {} while (0)
+#endif
+
 #define PHASE_MARK(sm, ph)                                                   \
     do {                                                                     \
         if (threadIdx.x == 0) {                                              \
@@ -46,8 +62,12 @@ struct Ctx {
     } while (0)
 
 
+// Buffer sizes are chosen so that the CTA of a 500-measurement frame needs 166 864 B: the SM then runs with the
+// 164 KB shared-memory carveout and 92 KB of L1 instead of 196 KB / 60 KB.  The L1 serves the scattered covariance
+// gathers (B2, B3c, B6, C4b) and the spills: measured on c4s, 28 KB of L1 (carveout forced to 228 KB) costs +21 %,
+// 92 KB instead of 60 KB gains 3 % (profiles/r02_experiments.md section 5).  Config 4 sorts ~6 000 candidates.
 #ifndef RBPHD_SORT_CAP
-#define RBPHD_SORT_CAP 8192
+#define RBPHD_SORT_CAP 6656
 #endif
 #ifndef RBPHD_VS_CAP
 #define RBPHD_VS_CAP 4096
@@ -432,6 +452,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
 
     PHASE_MARK(sm, 0);
     // A2: prior components: miss-detection weight (PHD:837-840), gate lookup, frustum flag
+    WARP_T0();
     for (int i = tid; i < N; i += kBlock) {
         double w = mfield(in, p.cap, 0)[i];
         double m[3] = {mfield(in, p.cap, 1)[i], mfield(in, p.cap, 2)[i], mfield(in, p.cap, 3)[i]};
@@ -446,12 +467,14 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         s.pwmd[i] = (1 - pdi) * w;
         int cnt = 0;
         unsigned long long packed = 0;
+        WARP_T(sm, 41);
         if (do_correct) {
             gate_walk(p, sm, m, local, vgrid_smem, [&](int k) { hits_add(packed, cnt, k); });
             s.nflag[i] = cnt;
             s.nstate[i] = (cnt > 0) ? 1 : 0;
             s.hits4[i] = hits_close(packed, cnt, M);
         }
+        WARP_T(sm, 42);
         if (do_births) {
             // upper bound of ln(w N(x; m, P)) at distance d: ln(w mult) - d^2 / (2 trace P)  (lambda_max <= trace)
             double P[9];
@@ -465,6 +488,7 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
             s.crad[i] = spd ? 1.0 / (2.0 * tr) : 0.0;
             // (frames that go on to WeightAlpha also need the component's cull radius for Map.Evaluate)
             if (eval_recs) s.erad[i] = eval_radius2(P);
+            WARP_T(sm, 43);
             // Early exploration decisions (PHD:956-959, MAP:210-220): one term w_i N(c_k; m_i, P_i) >= threshold
             // decides measurement k (all terms are >= 0).  Only the component's first gated measurements are
             // tried; whatever stays undecided gets the exact sum in A4.
@@ -485,9 +509,11 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
                     }
                 }
             }
+            WARP_T(sm, 44);
         }
     }
     __syncthreads();
+    WARP_T(sm, 45);
     // pair slots: every component's pairs take one contiguous block, blocks in component order, so that the
     // threads of a warp in the per-pair pass read the records of a handful of components (broadcast loads)
     // (and the gated components one slot each, in index order, for their records)
@@ -517,8 +543,13 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
     int a_split = nact_prior;
     if (do_births && nact_prior > kBlock && (nact_prior % kBlock) != 0 && (nact_prior % kBlock) <= kBlock / 2)
         a_split = (nact_prior / kBlock) * kBlock;
-    for (int a = tid; a < a_split; a += kBlock) comp_update(p, sm, s, in, a, 0, vgrid_smem);
-    __syncthreads();
+    {
+        WARP_T0();
+        for (int a = tid; a < a_split; a += kBlock) comp_update(p, sm, s, in, a, 0, vgrid_smem);
+        WARP_T(sm, 46);
+        __syncthreads();
+        WARP_T(sm, 47);
+    }
     PHASE_MARK(sm, 31);
 
     int B = 0;
@@ -550,7 +581,10 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
             }
             __syncthreads();
             PHASE_MARK(sm, 27);
-            grid_build(sm.sh, sm.ctx.grid, sm.gstart(), uitems, ux, uy, uz, nU, c.explore_r, c.explore_r, c.explore_r, 512);
+                        // cell = half the explore radius: most components reach much less than the radius (their own bound
+            // above), so the finer grid halves the points a walk tests (c4: A4b 113 -> 92 k cycles per particle)
+            grid_build(sm.sh, sm.ctx.grid, sm.gstart(), uitems, ux, uy, uz, nU, 0.5 * c.explore_r, 0.5 * c.explore_r,
+                       0.5 * c.explore_r, 4096);
             PHASE_MARK(sm, 28);
             const CellGrid& g = sm.ctx.grid;
             const double logskip = log(c.explore_thr) - 32.3;   // ln(1e-14)
@@ -713,8 +747,13 @@ __device__ void phase_predict_correct(const KParams& p, Smem& sm, const Slab& s,
         comp_update(p, sm, s, in, a, (a < nact_prior) ? 0 : npairs_prior, false);
     __syncthreads();
     PHASE_MARK(sm, 4);
-    for (int j = tid; j < sm.ctx.npairs; j += kBlock) eval_pair(p, sm, s, j);
-    __syncthreads();
+    {
+        WARP_T0();
+        for (int j = tid; j < sm.ctx.npairs; j += kBlock) eval_pair(p, sm, s, j);
+        WARP_T(sm, 48);
+        __syncthreads();
+        WARP_T(sm, 49);
+    }
     PHASE_MARK(sm, 2);
 
     PHASE_MARK(sm, 4);
@@ -980,7 +1019,12 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
     // per hundred components), so they are appended to one list and sorted by (r, r') afterwards.
     const double* tx = s.tm; const double* ty = s.tm + capw; const double* tz = s.tm + 2 * capw;
     double mincell = 2.0 * rmean;
-    grid_build(sm.sh, sm.ctx.grid, sm.gstart(), s.gitems, tx, ty, tz, W0, mincell, mincell, mincell);
+    // (the cell offsets of this grid run from the idle vs buffer through the histogram into gstart -- the three
+    // are contiguous -- so the merge grid gets kMergeCells cells instead of kGridMaxCells: the cells are far larger
+    // than the merge radius at any affordable count, and every extra cell saves tests in the walk)
+    constexpr int kMergeCells = (int)((sizeof(double) * kVsCap + sizeof(int) * 256 + sizeof(int) * (kGridMaxCells + 1)) / sizeof(int)) - 1;
+    int* const mstart = reinterpret_cast<int*>(sm.vs());
+    grid_build<kMergeCells>(sm.sh, sm.ctx.grid, mstart, s.gitems, tx, ty, tz, W0, mincell, mincell, mincell, kMergeCells);
     const double t2 = c.merge_t * c.merge_t;
     PHASE_MARK(sm, 19);
     float* fx = reinterpret_cast<float*>(sm.skey());        // cell-ordered copies (sort buffer is idle here)
@@ -1047,7 +1091,7 @@ __device__ void phase_prune(const KParams& p, Smem& sm, const Slab& s, const dou
                 for (int cz = lo[2]; cz <= hi[2]; cz++)
                     for (int cy = lo[1]; cy <= hi[1]; cy++) {
                         const int rowc = (cz * g.dim[1] + cy) * g.dim[0];
-                        const int qb = sm.gstart()[rowc + lo[0]], qe = sm.gstart()[rowc + hi[0] + 1];
+                        const int qb = mstart[rowc + lo[0]], qe = mstart[rowc + hi[0] + 1];
                         if (fsm) {
                             for (int q = qb; q < qe; q++)
                                 if (fabsf(fx[q] - xf) <= rf && fabsf(fy[q] - yf) <= rf && fabsf(fz[q] - zf) <= rf) {
@@ -1929,6 +1973,8 @@ int particle_update_max_ctas_per_sm(size_t smem)
             if (cudaFuncSetAttribute(k_particle_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess)
                 g = smem;
         }
+        if (const char* co = std::getenv("RBPHD_CARVEOUT"))   // experiments: shared-memory carveout in percent
+            cudaFuncSetAttribute(k_particle_update, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(co));
     }
     int n = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_particle_update, kBlock, smem);
