@@ -567,8 +567,20 @@ __device__ __forceinline__ int lower_bound_u64(const unsigned long long* key, in
 
 // ---------------------------------------------------------------------------------------------
 // Uniform 3-D cell grid over n points given as three arrays.  Cell offsets live in shared memory
-// (start[ncell+1]); the point indices, ascending within each cell, in `items` (any memory).
+// (start[ncell+1]); the point indices of each cell, in no particular order, in `items` (any memory).
 // ---------------------------------------------------------------------------------------------
+// order-preserving 64-bit encoding of a double (for integer atomicMin / atomicMax)
+__device__ __forceinline__ unsigned long long ordered_key(double x)
+{
+    const long long b = __double_as_longlong(x);
+    return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+}
+__device__ __forceinline__ double ordered_value(unsigned long long k)
+{
+    const long long b = (k & 0x8000000000000000ull) ? (long long)(k ^ 0x8000000000000000ull) : (long long)~k;
+    return __longlong_as_double(b);
+}
+
 struct CellGrid {
     double org[3];
     double inv[3];     // 1 / cell size per axis
@@ -604,29 +616,20 @@ __device__ inline void grid_build(BlockShared& sh, CellGrid& g, int* start, int*
         lo[1] = fmin(lo[1], y); hi[1] = fmax(hi[1], y);
         lo[2] = fmin(lo[2], z); hi[2] = fmax(hi[2], z);
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // block-wide bounding box: warp shuffles, then one shared-memory atomic per warp and bound on an order-preserving
+    // 64-bit encoding of the doubles (two barriers instead of two per axis)
+    const int lane = threadIdx.x & 31;
+    unsigned long long* bbk = reinterpret_cast<unsigned long long*>(sh.bb);
+    if (threadIdx.x < 6) bbk[threadIdx.x] = (threadIdx.x < 3) ? ordered_key(INFINITY) : ordered_key(-INFINITY);
+    __syncthreads();
+#pragma unroll
     for (int a = 0; a < 3; a++) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             lo[a] = fmin(lo[a], __shfl_down_sync(0xffffffffu, lo[a], o));
             hi[a] = fmax(hi[a], __shfl_down_sync(0xffffffffu, hi[a], o));
         }
-        __syncthreads();
-        if (lane == 0) { sh.warp_d[warp] = lo[a]; sh.warp_d[kWarps + warp] = hi[a]; }
-        __syncthreads();
-        if (warp == 0) {   // second level by shuffles as well (a serial loop here is ~1.5 k cycles per axis)
-            double l = (lane < kWarps) ? sh.warp_d[lane] : INFINITY;
-            double h = (lane < kWarps) ? sh.warp_d[kWarps + lane] : -INFINITY;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                l = fmin(l, __shfl_down_sync(0xffffffffu, l, o));
-                h = fmax(h, __shfl_down_sync(0xffffffffu, h, o));
-            }
-            if (lane == 0) {
-                if (!(l <= h)) { l = 0; h = 0; }
-                g.org[a] = l; g.hi[a] = h;
-            }
-        }
+        if (lane == 0) { atomicMin(&bbk[a], ordered_key(lo[a])); atomicMax(&bbk[3 + a], ordered_key(hi[a])); }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -634,6 +637,9 @@ __device__ inline void grid_build(BlockShared& sh, CellGrid& g, int* start, int*
         // kGridMaxCells cells (and kGridMaxDim per axis)
         double ext[3], mc[3];
         for (int a = 0; a < 3; a++) {
+            double l = ordered_value(bbk[a]), h = ordered_value(bbk[3 + a]);
+            if (!(l <= h)) { l = 0; h = 0; }
+            g.org[a] = l; g.hi[a] = h;
             ext[a] = g.hi[a] - g.org[a];
             mc[a] = (mincell3[a] > 0 && mincell3[a] < INFINITY) ? mincell3[a] : ext[a] / 16.0;
             if (!(mc[a] > 0)) mc[a] = 1.0;
@@ -685,8 +691,8 @@ __device__ inline void grid_build(BlockShared& sh, CellGrid& g, int* start, int*
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += kBlock) atomicAdd(&start[grid_cell(g, px[i], py[i], pz[i])], 1);
     __syncthreads();
-    // exclusive scan of the ncell + 1 counts: every thread owns a run of consecutive cells, so one
-    // block-wide scan of the run totals suffices
+    // inclusive scan of the ncell + 1 counts (start[c] = END of cell c): every thread owns a run of consecutive
+    // cells, so one block-wide scan of the run totals suffices
     const int per = (ncell + 1 + kBlock - 1) / kBlock;
     const int c0 = threadIdx.x * per;
     {
@@ -696,41 +702,18 @@ __device__ inline void grid_build(BlockShared& sh, CellGrid& g, int* start, int*
         int prefix = block_excl_scan(sh, run, &tot);
         for (int a = 0; a < per; a++) {
             const int cc = c0 + a;
-            if (cc <= ncell) { const int v = start[cc]; start[cc] = prefix; prefix += v; }
+            if (cc <= ncell) { prefix += start[cc]; start[cc] = prefix; }
         }
     }
     __syncthreads();
-    // scatter with the offsets as cursors (start[c] ends up as the END of cell c) ...
+    // scatter downwards from the ends: afterwards start[c] is the BEGIN of cell c (and start[ncell] = n, no point
+    // maps to that slot)
     for (int i = threadIdx.x; i < n; i += kBlock) {
         int c = grid_cell(g, px[i], py[i], pz[i]);
-        int slot = atomicAdd(&start[c], 1);
+        int slot = atomicSub(&start[c], 1) - 1;
         items[slot] = i;
     }
     __syncthreads();
-    // ... then shift right by one to restore the begin offsets (read the whole run first, then write)
-    {
-        int prev = (c0 > 0 && c0 - 1 <= ncell) ? start[c0 - 1] : 0;
-        constexpr int kPerMax = (kCellsBound + kBlock) / kBlock;   // >= per for every grid
-        int vals[kPerMax];
-        for (int a = 0; a < per && a < kPerMax; a++) { const int cc = c0 + a; vals[a] = (cc <= ncell) ? start[cc] : 0; }
-        __syncthreads();
-        if (per <= kPerMax) {
-            for (int a = 0; a < per; a++) {
-                const int cc = c0 + a;
-                if (cc <= ncell) start[cc] = (a == 0) ? prev : vals[a - 1];
-            }
-        }
-        __syncthreads();
-        if (per > kPerMax) {   // (never: per <= kPerMax by construction; kept for safety)
-            for (int base = (ncell / kBlock) * kBlock; base >= 0; base -= kBlock) {
-                int c = base + threadIdx.x;
-                int v = (c <= ncell && c > 0) ? start[c - 1] : 0;
-                __syncthreads();
-                if (c <= ncell) start[c] = v;
-                __syncthreads();
-            }
-        }
-    }
     // (The order of the indices inside a cell is whatever the atomics produced.  Every consumer either
     // sorts what it derives from the walk -- gated pairs, merge edges, likelihood edges -- or only
     // accumulates, so no per-cell sort is needed.)
