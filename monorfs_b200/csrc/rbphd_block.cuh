@@ -65,9 +65,32 @@ __device__ __forceinline__ int block_excl_scan(BlockShared& sh, int v, int* tota
     return res;
 }
 
-// in-place exclusive scan of an int array of length n (any memory space); returns the total
+// in-place exclusive scan of an int array of length n (any memory space); returns the total.
+// Every thread owns a run of consecutive entries (all loads in flight at once, ONE block-wide scan of the run
+// totals); arrays longer than kScanRun * kBlock fall back to kBlock-sized chunks with a carry.
+constexpr int kScanRun = 8;
 __device__ inline int block_scan_array(BlockShared& sh, int* a, int n)
 {
+    if (n <= kScanRun * kBlock) {
+        const int per = (n + kBlock - 1) / kBlock;
+        const int i0 = threadIdx.x * per;
+        int v[kScanRun];
+        int run = 0;
+#pragma unroll
+        for (int j = 0; j < kScanRun; j++) {
+            v[j] = (j < per && i0 + j < n) ? a[i0 + j] : 0;
+            run += v[j];
+        }
+        int tot;
+        int ex = block_excl_scan(sh, run, &tot);
+#pragma unroll
+        for (int j = 0; j < kScanRun; j++) {
+            if (j < per && i0 + j < n) a[i0 + j] = ex;
+            ex += v[j];
+        }
+        __syncthreads();
+        return tot;
+    }
     int carry = 0;
     for (int base = 0; base < n; base += kBlock) {
         int i = base + threadIdx.x;
@@ -88,6 +111,50 @@ __device__ inline void block_scan_array2(BlockShared& sh, int* a, int* b, int n,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long carry = 0;
     unsigned long long* wsum = reinterpret_cast<unsigned long long*>(sh.warp_d);   // kWarps + 1 entries
+    if (n <= kScanRun * kBlock) {
+        // runs of consecutive entries per thread: one block-wide scan (see block_scan_array)
+        const int per = (n + kBlock - 1) / kBlock;
+        const int i0 = threadIdx.x * per;
+        unsigned long long v[kScanRun];
+        unsigned long long run = 0;
+#pragma unroll
+        for (int j = 0; j < kScanRun; j++) {
+            v[j] = (j < per && i0 + j < n) ? ((unsigned long long)(unsigned)a[i0 + j] | ((unsigned long long)(unsigned)b[i0 + j] << 32)) : 0ull;
+            run += v[j];
+        }
+        unsigned long long incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        __syncthreads();
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned long long w = (lane < kWarps) ? wsum[lane] : 0ull;
+            unsigned long long wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            if (lane < kWarps) wsum[lane] = wi - w;
+            if (lane == kWarps - 1) wsum[kWarps] = wi;
+        }
+        __syncthreads();
+        unsigned long long ex = wsum[warp] + incl - run;
+#pragma unroll
+        for (int j = 0; j < kScanRun; j++) {
+            if (j < per && i0 + j < n) { a[i0 + j] = (int)(unsigned)(ex & 0xffffffffull); b[i0 + j] = (int)(unsigned)(ex >> 32); }
+            ex += v[j];
+        }
+        carry = wsum[kWarps];
+        __syncthreads();
+        *tot_a = (int)(unsigned)(carry & 0xffffffffull);
+        *tot_b = (int)(unsigned)(carry >> 32);
+        return;
+    }
     for (int base = 0; base < n; base += kBlock) {
         const int i = base + threadIdx.x;
         unsigned long long v = 0;
