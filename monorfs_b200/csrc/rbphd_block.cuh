@@ -221,6 +221,41 @@ __device__ __forceinline__ int next_pow2(int n)
 __device__ inline void block_bitonic_sort(unsigned long long* key, unsigned int* val, int n)
 {
     __syncthreads();
+    if (n <= kBlock) {
+        // one element per thread, held in registers: the stages with partner distance < 32 exchange by warp
+        // shuffles (no barrier), only the few wider ones go through the arrays (n = 512: 10 of 45 stages)
+        const int t = threadIdx.x;
+        unsigned long long kk = (t < n) ? key[t] : ~0ull;
+        unsigned int vv = (t < n) ? val[t] : ~0u;
+        const int nn = n < 32 ? 32 : n;     // lanes past n in the last warp carry padding (largest key)
+        for (int k = 2; k <= nn; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                unsigned long long ko;
+                unsigned int vo;
+                if (j >= 32) {
+                    __syncthreads();            // everyone has read its partner of the previous wide stage
+                    if (t < n) { key[t] = kk; val[t] = vv; }
+                    __syncthreads();
+                    ko = (t < n) ? key[t ^ j] : ~0ull;
+                    vo = (t < n) ? val[t ^ j] : ~0u;
+                }
+                else {
+                    ko = __shfl_xor_sync(0xffffffffu, kk, j);
+                    vo = __shfl_xor_sync(0xffffffffu, vv, j);
+                }
+                const bool asc = ((t & k) == 0);
+                const bool lower = ((t & j) == 0);
+                const bool mine_gt = (kk > ko) || (kk == ko && vv > vo);
+                // the lower index of the pair keeps the smaller element in an ascending run, the larger otherwise
+                const bool take_other = (lower == asc) ? mine_gt : !mine_gt && !(kk == ko && vv == vo);
+                if (take_other) { kk = ko; vv = vo; }
+            }
+        }
+        __syncthreads();
+        if (t < n) { key[t] = kk; val[t] = vv; }
+        __syncthreads();
+        return;
+    }
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1, lj = 31 - __clz(k >> 1); j > 0; j >>= 1, lj--) {
             for (int t = threadIdx.x; t < (n >> 1); t += kBlock) {
