@@ -85,3 +85,13 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not banned.search(text), os.path.join(dirpath, f)
+
+
+def test_integration_doc_binds_every_export():
+    """INTEGRATION.md shows the C# side of the boundary: every entry point of include/rbphd.h has its
+    DllImport stub there, and the stubs name no symbol the header does not declare."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    bound = set(re.findall(r"\b(rbphd_[a-z0-9_]+)\s*\(", text))
+    declared = set(declared_symbols())
+    assert not (declared - bound), sorted(declared - bound)
+    assert not (bound - declared), sorted(bound - declared)
