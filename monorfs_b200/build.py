@@ -7,6 +7,7 @@ The library is compiled for sm_100a only (no PTX for other architectures, no fal
 scalar C# operation order.
 """
 import os
+import re
 import subprocess
 import sys
 
@@ -32,16 +33,25 @@ DEVICE_SOURCES = ["rbphd_kernels.cu", "rbphd_math.cuh", "rbphd_block.cuh", "rbph
                   "rbphd_murty.cuh"]
 
 
+def _code_only(text):
+    """Source text without comments and with white space collapsed (string literals in the device sources hold no
+    comment markers)."""
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    return re.sub(r"\s+", " ", text).strip()
+
+
 def source_hash():
-    """Hash of the files k_particle_update is compiled from (not the host-side ABI): ties ncu-derived counters
-    under profiles/ to the kernel they were captured on."""
+    """Hash of the CODE k_particle_update is compiled from (the device files without comments and white space, not
+    the host-side ABI): ties ncu-derived counters under profiles/ to the kernel they were captured on, and survives
+    edits of comments."""
     import hashlib
     h = hashlib.sha256()
     for f in sorted(DEVICE_SOURCES):
         path = os.path.join(CSRC, f)
         if os.path.exists(path):
-            with open(path, "rb") as fh:
-                h.update(fh.read())
+            with open(path, "r", errors="replace") as fh:
+                h.update(_code_only(fh.read()).encode())
     return h.hexdigest()[:16]
 
 

@@ -4,8 +4,9 @@
 //   k_frame_prep          per-frame measurement grids (camera frame + measurement space), shared by all particles
 //   k_particle_update     persistent, one CTA per particle at a time: PredictConditional + CorrectConditional
 //                         + PruneModel + WeightAlpha fused; every intermediate (gated pairs, pre-prune list,
-//                         merge graph) stays in a per-CTA scratch slab that is reused particle after particle,
-//                         so it lives in L2 and only the prior map is read from / the pruned map written to HBM
+//                         merge graph) stays in a per-CTA scratch slab that is reused particle after particle
+//                         (L2-resident for small maps; at config 4 the 148 slabs of 3.2 MB exceed the 126 MB L2 and
+//                         measured DRAM traffic is 12x the algorithmic map bytes -- DESIGN.md sections 4 and 7.2)
 //   k_normalize_resample  weight normalisation, best particle, ESS test, systematic wheel   (PHD:343-358, 724-777)
 //   k_copy_particles      device-side copy of the ancestors' maps and poses                (PHD:740-742)
 //
