@@ -64,3 +64,19 @@ def test_migration_plan_is_consistent():
     for r, p in enumerate(plans):
         for dest, idx in p["send"].items():
             assert len(plans[dest]["recv"][r]) == len(idx)
+
+
+def test_kernel_counter_hash_ignores_comments_only():
+    """profiles/kernel_counters.json is tied to the device CODE: comments and white space do not change the hash,
+    a changed token does."""
+    from monorfs_b200 import build
+    a = "int x = 1; // note\n/* block\n comment */ int y = x  +  2;\n"
+    b = "int x = 1;\nint y = x + 2; // other words\n"
+    c = "int x = 1;\nint y = x + 3;\n"
+    assert build._code_only(a) == build._code_only(b)
+    assert build._code_only(a) != build._code_only(c)
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rec = json.load(open(os.path.join(root, "profiles", "kernel_counters.json")))
+    assert rec["source_hash"] == build.source_hash(), "profiles/kernel_counters.json was captured on other device code"
